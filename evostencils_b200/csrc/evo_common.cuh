@@ -1,0 +1,98 @@
+// evo_common.cuh -- shared device/host helpers of the B200 multigrid evaluation library.
+// Compiled only for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false).
+// -fmad=false: the CPU oracle is built with -ffp-contract=off; with identical operation order the
+// pointwise kernels are bit-identical to it, which is what the parity tests assert.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/evostencils_b200.h"
+
+namespace evo {
+
+// ---------------------------------------------------------------------------------------------
+// complex fp64 as one 16-byte word (double2): one Helmholtz unknown per LDG.128/STG.128
+struct __align__(16) cplx {
+    double re, im;
+    __host__ __device__ cplx() : re(0.0), im(0.0) {}
+    __host__ __device__ cplx(double r) : re(r), im(0.0) {}
+    __host__ __device__ cplx(double r, double i) : re(r), im(i) {}
+};
+__host__ __device__ inline cplx operator+(cplx a, cplx b) { return cplx(a.re + b.re, a.im + b.im); }
+__host__ __device__ inline cplx operator-(cplx a, cplx b) { return cplx(a.re - b.re, a.im - b.im); }
+__host__ __device__ inline cplx operator*(cplx a, cplx b) { return cplx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+__host__ __device__ inline cplx operator*(double a, cplx b) { return cplx(a * b.re, a * b.im); }
+__host__ __device__ inline cplx operator/(cplx a, cplx b)
+{
+    // Smith's algorithm (what libgcc's __divdc3 does for finite operands)
+    if (fabs(b.re) < fabs(b.im)) {
+        double ratio = b.re / b.im, denom = b.re * ratio + b.im;
+        return cplx((a.re * ratio + a.im) / denom, (a.im * ratio - a.re) / denom);
+    }
+    double ratio = b.im / b.re, denom = b.im * ratio + b.re;
+    return cplx((a.im * ratio + a.re) / denom, (a.im - a.re * ratio) / denom);
+}
+__host__ __device__ inline double abs2(double a) { return a * a; }
+__host__ __device__ inline double abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+
+template <typename T> struct scalar_traits;
+template <> struct scalar_traits<double> {
+    static constexpr int words = 1;
+    __host__ __device__ static double make(double re, double) { return re; }
+};
+template <> struct scalar_traits<cplx> {
+    static constexpr int words = 2;
+    __host__ __device__ static cplx make(double re, double im) { return cplx(re, im); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// geometry of one level: (2^l + 1)^dim nodes, x fastest, rows padded to a multiple of 16 entries
+// (128 B for fp64) so that every row starts on a cache-line / TMA-legal boundary.
+struct Geom {
+    int n;          // nodes per dimension
+    int dim;        // 2 or 3
+    int pitch;      // entries per row (>= n, multiple of 16)
+    int nz;         // n for 3-D, 1 for 2-D
+    long long plane;  // pitch * n
+    long long total;  // plane * nz
+};
+
+// stencil of one (row field, column field) block, non-zeros in ascending table order
+struct Sten {
+    int nnz;
+    signed char ox[27], oy[27], oz[27];
+    double re[27], im[27];
+};
+struct OpSten {  // passed by value as a __grid_constant__ kernel parameter (constant bank reads)
+    Sten s[EVO_MAX_FIELDS][EVO_MAX_FIELDS];
+};
+
+template <typename T> struct Fields {  // per-field array pointers of one buffer kind
+    T *p[EVO_MAX_FIELDS];
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block reduction: warp shuffles, then warp 0 adds the per-warp values in order
+__device__ __forceinline__ double block_sum(double v, double *smem /* >= 32 doubles */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = lane < nwarp ? smem[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;  // valid in warp 0
+}
+
+}  // namespace evo

@@ -1,0 +1,451 @@
+// evo_kernels.cuh -- generic (any 3^d constant stencil, 1-2 fields, real or complex) kernels of the
+// multigrid evaluation path.  One kernel per statement kind of the reference's emitter
+// (evostencils/code_generation/exastencils.py:684-925); the specialised high-bandwidth kernels for
+// scalar star stencils live in evo_kernels_star.cuh and must produce bit-identical results.
+//
+// Arithmetic contract shared with the CPU oracle (oracle/mg_ops.inc):
+//   A*u at a node   = sum_j sum_q c[i][j][q] * u_j[node + off_q], q ascending, acc = acc + c*u
+//   pointwise solve = s = sum of the non-unknown terms (same order); x = (f - s) / a; u += w (x - u)
+#pragma once
+#include "evo_common.cuh"
+
+namespace evo {
+
+constexpr int BX = 128;  // threads per block of the row-mapped kernels (x fastest)
+
+__device__ __forceinline__ long long node_index(const Geom &g, int x, int y, int z)
+{
+    return (long long)z * g.plane + (long long)y * g.pitch + x;
+}
+
+template <typename T>
+__device__ __forceinline__ T sten_coef(const Sten &s, int q)
+{
+    return scalar_traits<T>::make(s.re[q], s.im[q]);
+}
+
+template <typename T, int NF>
+__device__ __forceinline__ T apply_row(const Geom &g, const OpSten &st, const Fields<T> &u, int i, long long idx)
+{
+    T acc = T(0.0);
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        const Sten &s = st.s[i][j];
+        const T *uj = u.p[j];
+        for (int q = 0; q < s.nnz; ++q) {
+            long long d = (long long)s.oz[q] * g.plane + (long long)s.oy[q] * g.pitch + s.ox[q];
+            acc = acc + sten_coef<T>(s, q) * uj[idx + d];
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gen_residual_<f>@l = RHS@l - (A@l * SOL@l)                          (exastencils.py:837-853)
+// optional fused partial sums of |r|^2 (one double per block, fixed order -> deterministic norm)
+template <typename T, int DIM, int NF, bool NORM>
+__global__ void __launch_bounds__(BX) k_residual(const Geom g, const __grid_constant__ OpSten st, Fields<T> u,
+                                                 Fields<T> f, Fields<T> r, double *partials)
+{
+    __shared__ double red[32];
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    double sq = 0.0;
+    if (x <= g.n - 2) {
+        const long long idx = node_index(g, x, y, z);
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            T v = f.p[i][idx] - apply_row<T, NF>(g, st, u, i, idx);
+            r.p[i][idx] = v;
+            if (NORM) sq += abs2(v);
+        }
+    }
+    if (NORM) {
+        double s = block_sum(sq, red);
+        if (threadIdx.x == 0) partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// |r|^2 partial sums over inner nodes of an existing field (norm of a stored residual)
+template <typename T, int DIM, int NF>
+__global__ void __launch_bounds__(BX) k_norm2(const Geom g, Fields<T> r, double *partials)
+{
+    __shared__ double red[32];
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    double sq = 0.0;
+    if (x <= g.n - 2) {
+        const long long idx = node_index(g, x, y, z);
+#pragma unroll
+        for (int i = 0; i < NF; ++i) sq += abs2(r.p[i][idx]);
+    }
+    double s = block_sum(sq, red);
+    if (threadIdx.x == 0) partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+}
+
+// state of the generated solver's outer loop, resident on the device (one per cycle)
+struct SolveState {
+    double res0, res_prev, res;
+    double sum;       // last reduced sum of squares
+    int it;           // iterations done
+    int done;         // 1 = converged / cap / non-finite
+    int bad;          // non-finite residual seen
+    int pad;
+};
+
+// final, order-fixed reduction of the per-block partial sums (single block)
+__global__ void __launch_bounds__(1024) k_reduce_partials(const double *partials, int n, SolveState *st)
+{
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += partials[i];
+    double s = block_sum(acc, red);
+    if (threadIdx.x == 0) st->sum = s;
+}
+
+// bookkeeping of the outer loop: `until res < tol*res0 or it >= maxIts`
+// (example_problems/Poisson/2D_FD_Poisson_fromL2.exa3:3-4); mode 0 = initial residual, 1 = after a cycle
+__global__ void k_outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double res = sqrt(st->sum);
+    if (mode == 0) {
+        st->res0 = res; st->res_prev = res; st->res = res; st->it = 0; st->bad = 0;
+        hist[0] = res;
+        st->done = (max_iters <= 0) ? 1 : 0;
+        if (!isfinite(res)) { st->bad = 1; st->done = 1; }
+        return;
+    }
+    if (st->done) return;
+    st->it += 1;
+    hist[st->it] = res;
+    st->res_prev = st->res;
+    st->res = res;
+    if (!isfinite(res)) { st->bad = 1; st->done = 1; }
+    else if (res < tol * st->res0 || st->it >= max_iters) st->done = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One `solve locally` statement (exastencils.py:769-822; ir/transformations.py:51-121).
+struct SmoothParams {
+    int nu;                       // unknowns of the local system
+    int field[EVO_MAX_UNKNOWNS];  // field of each unknown
+    int off[EVO_MAX_UNKNOWNS][3]; // node offset of each unknown relative to the anchor
+    int color;                    // -1: every inner node is an anchor; 0/1: anchors with (x+y+z)%2 == color
+    int write_all;                // 1: write every inner unknown (in-place modes); 0: only offset-0 unknowns
+    double omega;
+};
+
+template <typename T, int NU>
+__device__ __forceinline__ void solve_dense(T (&M)[NU][NU], T (&b)[NU])
+{
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        int piv = c;
+        double best = abs2(M[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < NU; ++r) {
+            double v = abs2(M[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (piv != c) {
+#pragma unroll
+            for (int r = 0; r < NU; ++r) {
+                if (r == piv) {
+#pragma unroll
+                    for (int k = 0; k < NU; ++k) { T t = M[c][k]; M[c][k] = M[r][k]; M[r][k] = t; }
+                    T t = b[c]; b[c] = b[r]; b[r] = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = c + 1; r < NU; ++r) {
+            T fac = M[r][c] / M[c][c];
+#pragma unroll
+            for (int k = c + 1; k < NU; ++k) M[r][k] = M[r][k] - fac * M[c][k];
+            b[r] = b[r] - fac * b[c];
+        }
+    }
+#pragma unroll
+    for (int c = NU - 1; c >= 0; --c) {
+        T s = b[c];
+#pragma unroll
+        for (int k = c + 1; k < NU; ++k) s = s - M[c][k] * b[k];
+        b[c] = s / M[c][c];
+    }
+}
+
+// local solve at one anchor; identical construction to oracle/mg_ops.inc local_solve_anchor
+template <typename T, int DIM, int NF, int NU>
+__device__ __forceinline__ void local_solve(const Geom &g, const OpSten &st, const SmoothParams &sp,
+                                            const Fields<T> &src, const Fields<T> &dst, const Fields<T> &rhs,
+                                            int ax, int ay, int az)
+{
+    T M[NU][NU];
+    T b[NU];
+    int ux[NU], uy[NU], uz[NU];
+    bool inner[NU];
+    long long uidx[NU];
+    const int n = g.n;
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        ux[a] = ax + sp.off[a][0];
+        uy[a] = ay + sp.off[a][1];
+        uz[a] = DIM == 3 ? az + sp.off[a][2] : 0;
+        inner[a] = ux[a] >= 1 && ux[a] <= n - 2 && uy[a] >= 1 && uy[a] <= n - 2 &&
+                   (DIM == 2 || (uz[a] >= 1 && uz[a] <= n - 2));
+        bool inside = ux[a] >= 0 && ux[a] <= n - 1 && uy[a] >= 0 && uy[a] <= n - 1 &&
+                      (DIM == 2 || (uz[a] >= 0 && uz[a] <= n - 1));
+        uidx[a] = inside ? node_index(g, ux[a], uy[a], uz[a]) : -1;
+    }
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+#pragma unroll
+        for (int m = 0; m < NU; ++m) M[a][m] = T(0.0);
+        if (!inner[a]) {
+            M[a][a] = T(1.0);
+            b[a] = uidx[a] >= 0 ? src.p[sp.field[a]][uidx[a]] : T(0.0);
+            continue;
+        }
+        const int fi = sp.field[a];
+        T s = T(0.0);
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const Sten &sj = st.s[fi][j];
+            for (int q = 0; q < sj.nnz; ++q) {
+                const int px = ux[a] + sj.ox[q], py = uy[a] + sj.oy[q], pz = uz[a] + sj.oz[q];
+                int hit = -1;
+#pragma unroll
+                for (int m = NU - 1; m >= 0; --m)
+                    if (sp.field[m] == j && ux[m] == px && uy[m] == py && uz[m] == pz) hit = m;
+                const T c = sten_coef<T>(sj, q);
+                if (hit >= 0) {
+#pragma unroll
+                    for (int m = 0; m < NU; ++m)
+                        if (m == hit) M[a][m] = M[a][m] + c;
+                } else {
+                    long long d = (long long)sj.oz[q] * g.plane + (long long)sj.oy[q] * g.pitch + sj.ox[q];
+                    s = s + c * src.p[j][uidx[a] + d];
+                }
+            }
+        }
+        b[a] = rhs.p[fi][uidx[a]] - s;
+    }
+    if (NU == 1) b[0] = b[0] / M[0][0];
+    else solve_dense<T, NU>(M, b);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+        if (!inner[a]) continue;
+        const bool own = sp.off[a][0] == 0 && sp.off[a][1] == 0 && sp.off[a][2] == 0;
+        if (!sp.write_all && !own) continue;
+        const T old = src.p[sp.field[a]][uidx[a]];
+        dst.p[sp.field[a]][uidx[a]] = old + sp.omega * (b[a] - old);
+    }
+}
+
+// parallel sweep: `with jacobi` (src = current slot, dst = next slot; anchors at every inner node in
+// lexicographic order with overlapping blocks == every node keeps the value its own anchor computes,
+// because its own anchor is the last writer) or one colour of an order-independent coloured sweep.
+template <typename T, int DIM, int NF, int NU>
+__global__ void __launch_bounds__(BX) k_smooth(const Geom g, const __grid_constant__ OpSten st,
+                                               const __grid_constant__ SmoothParams sp, Fields<T> src, Fields<T> dst,
+                                               Fields<T> rhs)
+{
+    const int y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    const int t = blockIdx.x * BX + threadIdx.x;
+    int x;
+    if (sp.color < 0) x = 1 + t;
+    else x = 1 + 2 * t + ((1 + y + z + sp.color) & 1);
+    if (x > g.n - 2) return;
+    local_solve<T, DIM, NF, NU>(g, st, sp, src, dst, rhs, x, y, z);
+}
+
+// order-dependent coloured sweep (e.g. collective RB-GS on the elasticity system, whose dxy corner
+// terms couple same-colour nodes): the reference's loop is sequential, i0 fastest; anchors of one row
+// are mutually independent for 3^d stencils, rows depend on the previous row -> one CTA walks the rows
+// in lexicographic order, all threads of a row in parallel.
+template <typename T, int DIM, int NF, int NU>
+__global__ void __launch_bounds__(1024) k_smooth_rowseq(const Geom g, const __grid_constant__ OpSten st,
+                                                        const __grid_constant__ SmoothParams sp, Fields<T> u,
+                                                        Fields<T> rhs)
+{
+    SmoothParams loc = sp;
+    const int z0 = DIM == 3 ? 1 : 0, z1 = DIM == 3 ? g.n - 1 : 1;
+    for (int color = 0; color < 2; ++color) {
+        loc.color = color;
+        for (int z = z0; z < z1; ++z)
+            for (int y = 1; y < g.n - 1; ++y) {
+                for (int t = threadIdx.x;; t += 1024) {
+                    int x = 1 + 2 * t + ((1 + y + z + color) & 1);
+                    if (x > g.n - 2) break;
+                    local_solve<T, DIM, NF, NU>(g, st, loc, u, u, rhs, x, y, z);
+                }
+                __threadfence_block();
+                __syncthreads();
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TransferW {  // non-zero transfer weights in ascending table order
+    int nnz;
+    signed char ox[27], oy[27], oz[27];
+    double w[27];
+};
+
+// dst@(l-1) = R@l * src@l : coarse inner node c reads fine node 2c + o   (exastencils.py:855-873, :1126-1147)
+template <typename T, int DIM, int NF>
+__global__ void __launch_bounds__(BX) k_restrict(const Geom gf, const Geom gc, const __grid_constant__ TransferW R,
+                                                 Fields<T> src, Fields<T> dst)
+{
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    if (x > gc.n - 2) return;
+    const long long fidx = node_index(gf, 2 * x, 2 * y, DIM == 3 ? 2 * z : 0);
+    const long long cidx = node_index(gc, x, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        T acc = T(0.0);
+        for (int q = 0; q < R.nnz; ++q) {
+            long long d = (long long)R.oz[q] * gf.plane + (long long)R.oy[q] * gf.pitch + R.ox[q];
+            acc = acc + R.w[q] * src.p[i][fidx + d];
+        }
+        dst.p[i][cidx] = acc;
+    }
+}
+
+// fused RHS@(l-1) = R@l * (RHS@l - A@l * SOL@l): the fine residual is never stored
+template <typename T, int DIM, int NF>
+__global__ void __launch_bounds__(BX) k_residual_restrict(const Geom gf, const Geom gc,
+                                                          const __grid_constant__ OpSten st,
+                                                          const __grid_constant__ TransferW R, Fields<T> u, Fields<T> f,
+                                                          Fields<T> dst)
+{
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    if (x > gc.n - 2) return;
+    const long long cidx = node_index(gc, x, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        T acc = T(0.0);
+        for (int q = 0; q < R.nnz; ++q) {
+            const int fx = 2 * x + R.ox[q], fy = 2 * y + R.oy[q], fz = DIM == 3 ? 2 * z + R.oz[q] : 0;
+            T rv = T(0.0);  // the residual field is 0 on the boundary layer
+            if (fx >= 1 && fx <= gf.n - 2 && fy >= 1 && fy <= gf.n - 2 && (DIM == 2 || (fz >= 1 && fz <= gf.n - 2))) {
+                const long long idx = node_index(gf, fx, fy, fz);
+                rv = f.p[i][idx] - apply_row<T, NF>(gf, st, u, i, idx);
+            }
+            acc = acc + R.w[q] * rv;
+        }
+        dst.p[i][cidx] = acc;
+    }
+}
+
+// fine inner node x: p = sum over offsets o with x+o even of w[o]*src[(x+o)/2]   (exastencils.py:1103-1124)
+// ADD: SOL@l += w * p (:727-743)   else: dst@l = p (:868-873)
+template <typename T, int DIM, int NF, bool ADD>
+__global__ void __launch_bounds__(BX) k_prolong(const Geom gf, const Geom gc, const __grid_constant__ TransferW P,
+                                                Fields<T> src, Fields<T> dst, double weight)
+{
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    if (x > gf.n - 2) return;
+    const long long idx = node_index(gf, x, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        T acc = T(0.0);
+        for (int q = 0; q < P.nnz; ++q) {
+            const int cx = x + P.ox[q], cy = y + P.oy[q], cz = DIM == 3 ? z + P.oz[q] : 0;
+            if ((cx & 1) || (cy & 1) || (DIM == 3 && (cz & 1))) continue;
+            acc = acc + P.w[q] * src.p[i][node_index(gc, cx >> 1, cy >> 1, cz >> 1)];
+        }
+        if (ADD) dst.p[i][idx] = dst.p[i][idx] + weight * acc;
+        else dst.p[i][idx] = acc;
+    }
+}
+
+// SOL_i += w * (RHS_i - A SOL)_i evaluated from the pre-statement values (see oracle op_richardson):
+// two kernels, k_residual into a scratch field then this axpy
+template <typename T, int DIM>
+__global__ void __launch_bounds__(BX) k_axpy_inner(const Geom g, T *y_, const T *x_, double a)
+{
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    if (x > g.n - 2) return;
+    const long long idx = node_index(g, x, y, z);
+    y_[idx] = y_[idx] + a * x_[idx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// gen_mgCycle@min(): conjugate gradients on the coarsest level, zero initial guess, one CTA
+// (`solver_cgs = "CG"`, example_problems/Poisson/2D_FD_Poisson_fromL2.exa3:12-14).  The whole
+// coarse problem is latency bound, so a single block with block-wide barriers beats any multi-kernel
+// formulation; dot products use the deterministic block reduction.
+template <int DIM, int NF>
+__global__ void __launch_bounds__(1024) k_coarse_cg(const Geom g, const __grid_constant__ OpSten st, Fields<double> x,
+                                                    Fields<double> b, Fields<double> r, Fields<double> p,
+                                                    Fields<double> ap, int max_it, double tol, int *iters_out)
+{
+    __shared__ double red[32];
+    __shared__ double bc;
+    const int ni = g.n - 2;
+    const long long count = (long long)ni * ni * (DIM == 3 ? ni : 1);
+    auto idx_of = [&](long long t) {
+        int ix = (int)(t % ni), iy = (int)((t / ni) % ni), iz = DIM == 3 ? (int)(t / ((long long)ni * ni)) : -1;
+        return node_index(g, ix + 1, iy + 1, iz + 1);
+    };
+    auto dot = [&](const Fields<double> &a_, const Fields<double> &b_) {
+        double acc = 0.0;
+        for (int i = 0; i < NF; ++i)
+            for (long long t = threadIdx.x; t < count; t += blockDim.x) {
+                long long id = idx_of(t);
+                acc += a_.p[i][id] * b_.p[i][id];
+            }
+        double s = block_sum(acc, red);
+        if (threadIdx.x == 0) bc = s;
+        __syncthreads();
+        return bc;
+    };
+    for (int i = 0; i < NF; ++i)
+        for (long long t = threadIdx.x; t < g.total; t += blockDim.x) {
+            x.p[i][t] = 0.0; r.p[i][t] = 0.0; p.p[i][t] = 0.0; ap.p[i][t] = 0.0;
+        }
+    __syncthreads();
+    for (int i = 0; i < NF; ++i)
+        for (long long t = threadIdx.x; t < count; t += blockDim.x) {
+            long long id = idx_of(t);
+            double v = b.p[i][id];
+            r.p[i][id] = v; p.p[i][id] = v;
+        }
+    __syncthreads();
+    double rr = dot(r, r);
+    const double r0 = sqrt(rr);
+    int it = 0;
+    if (r0 != 0.0) {
+        while (it < max_it) {
+            for (int i = 0; i < NF; ++i)
+                for (long long t = threadIdx.x; t < count; t += blockDim.x) {
+                    long long id = idx_of(t);
+                    ap.p[i][id] = apply_row<double, NF>(g, st, p, i, id);
+                }
+            __syncthreads();
+            const double pap = dot(p, ap);
+            const double alpha = rr / pap;
+            for (int i = 0; i < NF; ++i)
+                for (long long t = threadIdx.x; t < count; t += blockDim.x) {
+                    long long id = idx_of(t);
+                    x.p[i][id] = x.p[i][id] + alpha * p.p[i][id];
+                    r.p[i][id] = r.p[i][id] - alpha * ap.p[i][id];
+                }
+            __syncthreads();
+            const double rr_new = dot(r, r);
+            ++it;
+            if (!(sqrt(rr_new) > tol * r0)) break;
+            const double beta = rr_new / rr;
+            for (int i = 0; i < NF; ++i)
+                for (long long t = threadIdx.x; t < count; t += blockDim.x) {
+                    long long id = idx_of(t);
+                    p.p[i][id] = r.p[i][id] + beta * p.p[i][id];
+                }
+            __syncthreads();
+            rr = rr_new;
+        }
+    }
+    if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
+}  // namespace evo

@@ -1,0 +1,981 @@
+// evo_runtime.cu -- host runtime + C-ABI of the B200 multigrid evaluation library.
+//
+// Replaces, for one individual, the reference's  "emit ExaSlang -> java (x2) -> make -> run binary x
+// samples -> parse stdout"  (evostencils/code_generation/exastencils.py:485-537) by
+//   evo_cycle_build : op list -> bound kernel launches, captured once as a CUDA graph whose root is a
+//                     WHILE conditional node (the generated solver's outer loop runs on the device)
+//   evo_cycle_solve : one graph launch per sample, CUDA-event timed, residual history read back
+// No CPU fallback exists: without a CUDA device evo_problem_create fails with EVO_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "evo_kernels.cuh"
+#include "evo_kernels_star.cuh"
+
+using namespace evo;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? EVO_ERR_OOM : EVO_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+#define EV(call)                     \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_ != EVO_OK) return rc_; \
+    } while (0)
+
+static Geom make_geom(int level, int dim)
+{
+    Geom g;
+    g.n = (1 << level) + 1;
+    g.dim = dim;
+    g.pitch = (g.n + 15) / 16 * 16;
+    g.nz = dim == 3 ? g.n : 1;
+    g.plane = (long long)g.pitch * g.n;
+    g.total = g.plane * g.nz;
+    return g;
+}
+
+static TransferW make_transfer(const double *w, int dim)
+{
+    TransferW t;
+    memset(&t, 0, sizeof(t));
+    for (int p = 0; p < 27; ++p) {
+        if (w[p] == 0.0) continue;
+        int ox = p % 3 - 1, oy = (p / 3) % 3 - 1, oz = p / 9 - 1;
+        if (dim == 2 && oz != 0) continue;
+        int q = t.nnz++;
+        t.ox[q] = (signed char)ox; t.oy[q] = (signed char)oy; t.oz[q] = (signed char)oz;
+        t.w[q] = w[p];
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct evo_problem {
+    evo_problem_desc desc;
+    int words;
+    int sm_count;
+    Geom geom[EVO_MAX_LEVELS];
+    TransferW R, P;
+    void *init_sol[EVO_MAX_FIELDS];  // pristine finest-level SOL (incl. boundary values), padded layout
+    void *rhs0[EVO_MAX_FIELDS];      // finest-level RHS, read-only, shared by all cycles
+    std::vector<std::pair<void *, size_t>> pool;  // recycled cycle work slabs
+};
+
+struct LevelMem {
+    void *buf[EVO_BUF_COUNT][EVO_MAX_FIELDS];
+    void *slot[EVO_MAX_FIELDS];  // [next] slot of SOL for `with jacobi` statements
+    bool swapped[EVO_MAX_FIELDS];
+};
+
+struct evo_cycle {
+    evo_problem *p;
+    std::vector<evo_op> ops;
+    OpSten sten[EVO_MAX_LEVELS];
+    bool has_sten[EVO_MAX_LEVELS];
+    LevelMem lv[EVO_MAX_LEVELS];
+    void *slab;
+    size_t slab_bytes;
+    void *krylov[8][EVO_MAX_FIELDS];  // coarsest-level Krylov vectors
+    void *scratch[EVO_MAX_FIELDS];    // finest-level scratch field (Richardson)
+    SolveState *d_state;
+    double *d_hist;
+    int hist_cap;
+    double *d_partials;
+    int n_partials;
+    int *d_cg_iters;
+    SolveState *h_state;  // pinned
+    double *h_hist;       // pinned
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    // captured solver graph (valid for one (tol, max_iters))
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    double graph_tol;
+    int graph_max_iters;
+    int64_t kernels_per_cycle, kernels_prologue;
+    int64_t launch_counter;  // counts kernel launches while enqueueing
+    bool use_while_graph;
+};
+
+template <typename T> static Fields<T> fields_of(void *const *p, int nf)
+{
+    Fields<T> f;
+    for (int i = 0; i < EVO_MAX_FIELDS; ++i) f.p[i] = i < nf ? (T *)p[i] : nullptr;
+    return f;
+}
+
+static dim3 row_grid(const Geom &g, int per_thread = 1)
+{
+    int inner = g.n - 2;
+    int threads = (inner + per_thread - 1) / per_thread;
+    return dim3((threads + BX - 1) / BX, inner, g.dim == 3 ? inner : 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// library
+extern "C" int evo_abi_version(void) { return EVO_ABI_VERSION; }
+extern "C" const char *evo_last_error(void) { return g_err.c_str(); }
+
+extern "C" int evo_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(EVO_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return EVO_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+extern "C" int evo_device_name(int device, char *buf, size_t len, int *sm_count)
+{
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (buf && len) snprintf(buf, len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return EVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem
+extern "C" int evo_problem_create(const evo_problem_desc *d, evo_problem **out)
+{
+    if (!d || !out) return fail(EVO_ERR_INVALID, "null argument");
+    if (d->abi_version != EVO_ABI_VERSION) return fail(EVO_ERR_INVALID, "ABI version mismatch");
+    if (d->dim < 2 || d->dim > 3 || d->n_fields < 1 || d->n_fields > EVO_MAX_FIELDS || d->min_level < 1 ||
+        d->max_level >= EVO_MAX_LEVELS || d->min_level > d->max_level || (d->scalar_words != 1 && d->scalar_words != 2))
+        return fail(EVO_ERR_INVALID, "invalid problem descriptor");
+    if (d->scalar_words == 2 && (d->n_fields != 1 || d->dim != 2))
+        return fail(EVO_ERR_UNSUPPORTED, "complex problems: scalar 2-D only");
+    int ndev = evo_device_count();
+    if (ndev <= 0) return fail(EVO_ERR_NO_DEVICE, "no CUDA device: this backend has no CPU fallback");
+    if (d->device < 0 || d->device >= ndev) return fail(EVO_ERR_INVALID, "device ordinal %d out of range", d->device);
+    CU(cudaSetDevice(d->device));
+    evo_problem *p = new evo_problem();
+    p->desc = *d;
+    p->words = d->scalar_words;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, d->device));
+    p->sm_count = prop.multiProcessorCount;
+    for (int l = d->min_level; l <= d->max_level; ++l) p->geom[l] = make_geom(l, d->dim);
+    p->R = make_transfer(d->restrict_w, d->dim);
+    p->P = make_transfer(d->prolong_w, d->dim);
+    const size_t bytes = (size_t)p->geom[d->max_level].total * sizeof(double) * p->words;
+    for (int i = 0; i < EVO_MAX_FIELDS; ++i) { p->init_sol[i] = nullptr; p->rhs0[i] = nullptr; }
+    for (int i = 0; i < d->n_fields; ++i) {
+        CU(cudaMalloc(&p->init_sol[i], bytes));
+        CU(cudaMalloc(&p->rhs0[i], bytes));
+        CU(cudaMemset(p->init_sol[i], 0, bytes));
+        CU(cudaMemset(p->rhs0[i], 0, bytes));
+    }
+    *out = p;
+    return EVO_OK;
+}
+
+extern "C" int evo_problem_destroy(evo_problem *p)
+{
+    if (!p) return EVO_OK;
+    cudaSetDevice(p->desc.device);
+    for (int i = 0; i < EVO_MAX_FIELDS; ++i) { cudaFree(p->init_sol[i]); cudaFree(p->rhs0[i]); }
+    for (auto &s : p->pool) cudaFree(s.first);
+    delete p;
+    return EVO_OK;
+}
+
+// dense host array (n^dim entries, x fastest) <-> padded device array
+static int copy_field(const Geom &g, int words, void *dev, const void *host_src, void *host_dst, cudaStream_t stream)
+{
+    const size_t esz = sizeof(double) * words;
+    const size_t rows = (size_t)g.n * g.nz;
+    if (host_src) CU(cudaMemcpy2DAsync(dev, g.pitch * esz, host_src, g.n * esz, g.n * esz, rows, cudaMemcpyHostToDevice, stream));
+    if (host_dst) CU(cudaMemcpy2DAsync(host_dst, g.n * esz, dev, g.pitch * esz, g.n * esz, rows, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return EVO_OK;
+}
+
+extern "C" int evo_problem_set_field(evo_problem *p, int level, int buf, int field, const double *host, size_t n_doubles)
+{
+    if (!p || !host) return fail(EVO_ERR_INVALID, "null argument");
+    if (level != p->desc.max_level) return fail(EVO_ERR_UNSUPPORTED, "initial fields are defined on the finest level only");
+    if (field < 0 || field >= p->desc.n_fields || (buf != EVO_BUF_SOL && buf != EVO_BUF_RHS))
+        return fail(EVO_ERR_INVALID, "invalid field/buffer");
+    const Geom &g = p->geom[level];
+    if (n_doubles != (size_t)g.n * g.n * g.nz * p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    CU(cudaSetDevice(p->desc.device));
+    return copy_field(g, p->words, buf == EVO_BUF_SOL ? p->init_sol[field] : p->rhs0[field], host, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cycle: memory
+static bool level_needs_slot(const evo_cycle *c, int level)
+{
+    for (const evo_op &op : c->ops)
+        if (op.level == level && ((op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_JACOBI) || op.code == EVO_OP_RICHARDSON))
+            return true;
+    return false;
+}
+static bool uses_buffer(const evo_cycle *c, int level, int buf)
+{
+    for (const evo_op &op : c->ops) {
+        int dl = op.level, sl = op.level;
+        if (op.code == EVO_OP_RESTRICT) dl = op.level - 1;
+        if (op.code == EVO_OP_PROLONG_ADD || op.code == EVO_OP_PROLONG_SET) sl = op.level - 1;
+        if ((dl == level && op.dst == buf) || (sl == level && op.src == buf)) return true;
+    }
+    return false;
+}
+
+static int allocate_cycle(evo_cycle *c)
+{
+    evo_problem *p = c->p;
+    const int nf = p->desc.n_fields, lo = p->desc.min_level, hi = p->desc.max_level;
+    const size_t esz = sizeof(double) * p->words;
+    auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+    // pass 1: size, pass 2: carve
+    for (int pass = 0; pass < 2; ++pass) {
+        size_t off = 0;
+        char *base = (char *)c->slab;
+        auto take = [&](size_t bytes) -> void * {
+            void *r = pass ? (void *)(base + off) : nullptr;
+            off += align(bytes);
+            return r;
+        };
+        for (int l = lo; l <= hi; ++l) {
+            const size_t fb = (size_t)p->geom[l].total * esz;
+            const bool slot = level_needs_slot(c, l);
+            for (int i = 0; i < nf; ++i) {
+                c->lv[l].buf[EVO_BUF_SOL][i] = take(fb);
+                c->lv[l].buf[EVO_BUF_RHS][i] = l == hi ? (pass ? p->rhs0[i] : nullptr) : take(fb);
+                c->lv[l].buf[EVO_BUF_RES][i] = take(fb);
+                c->lv[l].buf[EVO_BUF_COR][i] = (l == hi && uses_buffer(c, l, EVO_BUF_COR)) ? take(fb) : c->lv[l].buf[EVO_BUF_SOL][i];
+                c->lv[l].buf[EVO_BUF_APX][i] = (p->desc.kind == EVO_PROBLEM_FAS) ? take(fb) : nullptr;
+                c->lv[l].slot[i] = slot ? take(fb) : nullptr;
+                c->lv[l].swapped[i] = false;
+            }
+        }
+        const size_t cb = (size_t)p->geom[lo].total * esz;
+        for (int v = 0; v < 8; ++v)
+            for (int i = 0; i < nf; ++i) c->krylov[v][i] = take(cb);
+        c->d_state = (SolveState *)take(sizeof(SolveState));
+        c->d_cg_iters = (int *)take(256);
+        const Geom &gf = p->geom[hi];
+        dim3 gr = row_grid(gf);
+        c->n_partials = (int)(gr.x * gr.y * gr.z);
+        c->d_partials = (double *)take(sizeof(double) * (size_t)c->n_partials);
+        if (pass == 0) {
+            c->slab_bytes = off;
+            c->slab = nullptr;
+            for (size_t k = 0; k < p->pool.size(); ++k)
+                if (p->pool[k].second == off) {
+                    c->slab = p->pool[k].first;
+                    p->pool.erase(p->pool.begin() + k);
+                    break;
+                }
+            if (!c->slab) CU(cudaMalloc(&c->slab, off));
+        }
+    }
+    return EVO_OK;
+}
+
+static int reset_cycle(evo_cycle *c, cudaStream_t s)
+{
+    evo_problem *p = c->p;
+    const int nf = p->desc.n_fields, hi = p->desc.max_level;
+    const size_t esz = sizeof(double) * p->words;
+    // zero everything we own (boundary layers of the coarse fields must be 0 and are never written)
+    CU(cudaMemsetAsync(c->slab, 0, c->slab_bytes, s));
+    const size_t fb = (size_t)p->geom[hi].total * esz;
+    for (int i = 0; i < nf; ++i) {
+        CU(cudaMemcpyAsync(c->lv[hi].buf[EVO_BUF_SOL][i], p->init_sol[i], fb, cudaMemcpyDeviceToDevice, s));
+        // both jacobi slots carry the Dirichlet boundary values
+        if (c->lv[hi].slot[i]) CU(cudaMemcpyAsync(c->lv[hi].slot[i], p->init_sol[i], fb, cudaMemcpyDeviceToDevice, s));
+    }
+    return EVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cycle: op dispatch (every function only enqueues work on `s`; safe under stream capture)
+template <typename T, int DIM, int NF> struct Launch {
+    static int residual(evo_cycle *c, int l, bool norm, cudaStream_t s)
+    {
+        const Geom &g = c->p->geom[l];
+        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
+             r = fields_of<T>(c->lv[l].buf[EVO_BUF_RES], NF);
+        if (star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, norm ? c->d_partials : nullptr, s)) {
+            c->launch_counter++;
+        } else {
+            if (norm) k_residual<T, DIM, NF, true><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, c->d_partials);
+            else k_residual<T, DIM, NF, false><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, nullptr);
+            c->launch_counter++;
+        }
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    template <int NU> static int smooth_nu(evo_cycle *c, const evo_op &op, cudaStream_t s)
+    {
+        const int l = op.level;
+        const Geom &g = c->p->geom[l];
+        SmoothParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.nu = NU;
+        sp.omega = op.omega;
+        sp.write_all = 0;
+        bool has_own[EVO_MAX_FIELDS] = {false, false}, written[EVO_MAX_FIELDS] = {false, false};
+        for (int a = 0; a < NU; ++a) {
+            sp.field[a] = op.unk_field[a];
+            if (sp.field[a] < 0 || sp.field[a] >= NF) return fail(EVO_ERR_INVALID, "unknown refers to field %d", sp.field[a]);
+            for (int d = 0; d < 3; ++d) sp.off[a][d] = d < DIM ? op.unk_off[a][d] : 0;
+            written[sp.field[a]] = true;
+            if (sp.off[a][0] == 0 && sp.off[a][1] == 0 && sp.off[a][2] == 0) has_own[sp.field[a]] = true;
+        }
+        for (int i = 0; i < NF; ++i)
+            if (written[i] && !has_own[i])
+                return fail(EVO_ERR_UNSUPPORTED, "local system without an unknown at the anchor node for field %d", i);
+        auto rhs = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
+        const int reps = op.count > 1 ? op.count : 1;
+        for (int rep = 0; rep < reps; ++rep) {
+            if (op.mode == EVO_SMOOTH_JACOBI) {
+                // read the current slot, write the next slot, then `advance` (swap) the written fields
+                void *cur[EVO_MAX_FIELDS], *nxt[EVO_MAX_FIELDS];
+                for (int i = 0; i < NF; ++i) {
+                    cur[i] = c->lv[l].buf[EVO_BUF_SOL][i];
+                    nxt[i] = written[i] ? c->lv[l].slot[i] : cur[i];
+                    if (written[i] && !nxt[i]) return fail(EVO_ERR_INVALID, "missing jacobi slot");
+                }
+                sp.color = -1;
+                auto src = fields_of<T>(cur, NF), dst = fields_of<T>(nxt, NF);
+                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, src, dst, rhs, s)))
+                    k_smooth<T, DIM, NF, NU><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], sp, src, dst, rhs);
+                c->launch_counter++;
+                for (int i = 0; i < NF; ++i)
+                    if (written[i]) {
+                        std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
+                        c->lv[l].swapped[i] = !c->lv[l].swapped[i];
+                        if (c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].slot[i]) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
+                    }
+            } else if (op.mode == EVO_SMOOTH_REDBLACK) {
+                auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF);
+                if (color_order_dependent(c->sten[l], sp, NF)) {
+                    if (NU != NF) return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
+                    k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
+                    c->launch_counter++;
+                } else {
+                    for (int color = 0; color < 2; ++color) {
+                        sp.color = color;
+                        if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, u, u, rhs, s)))
+                            k_smooth<T, DIM, NF, NU><<<row_grid(g, 2), BX, 0, s>>>(g, c->sten[l], sp, u, u, rhs);
+                        c->launch_counter++;
+                    }
+                }
+            } else {
+                return fail(EVO_ERR_UNSUPPORTED, "lexicographic in-place smoothing (model-based mode) is not implemented");
+            }
+        }
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    static bool color_order_dependent(const OpSten &st, const SmoothParams &sp, int nf)
+    {
+        for (int a = 0; a < sp.nu; ++a)
+            for (int j = 0; j < nf; ++j) {
+                const Sten &sj = st.s[sp.field[a]][j];
+                for (int q = 0; q < sj.nnz; ++q) {
+                    int ox = sp.off[a][0] + sj.ox[q], oy = sp.off[a][1] + sj.oy[q], oz = sp.off[a][2] + sj.oz[q];
+                    bool is_unknown = false;
+                    for (int m = 0; m < sp.nu; ++m)
+                        if (sp.field[m] == j && sp.off[m][0] == ox && sp.off[m][1] == oy && sp.off[m][2] == oz) is_unknown = true;
+                    if (is_unknown) continue;
+                    for (int m = 0; m < sp.nu; ++m) {
+                        if (sp.field[m] != j) continue;
+                        int sx = ox - sp.off[m][0], sy = oy - sp.off[m][1], sz = oz - sp.off[m][2];
+                        if (((sx + sy + sz) & 1) == 0) return true;
+                    }
+                }
+            }
+        return false;
+    }
+
+    static int smooth(evo_cycle *c, const evo_op &op, cudaStream_t s)
+    {
+        switch (op.n_unknowns) {
+        case 1: return smooth_nu<1>(c, op, s);
+        case 2: return smooth_nu<2>(c, op, s);
+        case 3: return smooth_nu<3>(c, op, s);
+        case 4: return smooth_nu<4>(c, op, s);
+        case 5: return smooth_nu<5>(c, op, s);
+        case 6: return smooth_nu<6>(c, op, s);
+        case 7: return smooth_nu<7>(c, op, s);
+        case 8: return smooth_nu<8>(c, op, s);
+        default: return fail(EVO_ERR_INVALID, "local system size %d", op.n_unknowns);
+        }
+    }
+
+    static int restrict_(evo_cycle *c, const evo_op &op, cudaStream_t s)
+    {
+        const int l = op.level;
+        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        auto src = fields_of<T>(c->lv[l].buf[op.src], NF), dst = fields_of<T>(c->lv[l - 1].buf[op.dst], NF);
+        k_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->p->R, src, dst);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    static int residual_restrict(evo_cycle *c, const evo_op &op, cudaStream_t s)
+    {
+        const int l = op.level;
+        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
+             dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
+        if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s))
+            k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    static int prolong(evo_cycle *c, const evo_op &op, bool add, cudaStream_t s)
+    {
+        const int l = op.level;
+        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        auto src = fields_of<T>(c->lv[l - 1].buf[op.src], NF);
+        auto dst = fields_of<T>(c->lv[l].buf[add ? EVO_BUF_SOL : op.dst], NF);
+        if (add) {
+            if (!star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s))
+                k_prolong<T, DIM, NF, true><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, op.omega);
+        } else {
+            k_prolong<T, DIM, NF, false><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, 1.0);
+        }
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    static int richardson(evo_cycle *c, const evo_op &op, cudaStream_t s)
+    {
+        // field by field: tmp = RHS_i - (A SOL)_i from the current values, then SOL_i += w * tmp
+        const int l = op.level;
+        const Geom &g = c->p->geom[l];
+        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
+        for (int i = 0; i < NF; ++i) {
+            T *tmp = (T *)c->lv[l].slot[i];
+            if (!tmp) return fail(EVO_ERR_INVALID, "missing scratch slot");
+            Fields<T> r = u;  // residual of field i goes to tmp; other entries unused (NF passes write all -> use scratch trick)
+            for (int j = 0; j < NF; ++j) r.p[j] = (T *)c->lv[l].slot[j];
+            k_residual<T, DIM, NF, false><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, nullptr);
+            k_axpy_inner<T, DIM><<<row_grid(g), BX, 0, s>>>(g, (T *)c->lv[l].buf[EVO_BUF_SOL][i], tmp, op.omega);
+            c->launch_counter += 2;
+        }
+        // the slot was used as scratch: restore its boundary invariant (inner values are don't-care)
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
+    static int norm2(evo_cycle *c, int l, int buf, cudaStream_t s)
+    {
+        const Geom &g = c->p->geom[l];
+        auto r = fields_of<T>(c->lv[l].buf[buf], NF);
+        k_norm2<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, r, c->d_partials);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+};
+
+template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, cudaStream_t s)
+{
+    const int l = op.level;
+    const Geom &g = c->p->geom[l];
+    if (l != c->p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
+    auto x = fields_of<double>(c->lv[l].buf[EVO_BUF_SOL], NF), b = fields_of<double>(c->lv[l].buf[EVO_BUF_RHS], NF);
+    auto r = fields_of<double>(c->krylov[0], NF), p = fields_of<double>(c->krylov[1], NF), ap = fields_of<double>(c->krylov[2], NF);
+    k_coarse_cg<DIM, NF><<<1, 1024, 0, s>>>(g, c->sten[l], x, b, r, p, ap, op.count, op.tol, c->d_cg_iters);
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+template <typename T, int DIM, int NF> static int enqueue_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
+{
+    using L = Launch<T, DIM, NF>;
+    evo_problem *p = c->p;
+    const int l = op.level;
+    const size_t esz = sizeof(double) * p->words;
+    switch (op.code) {
+    case EVO_OP_ZERO:
+        for (int i = 0; i < NF; ++i) CU(cudaMemsetAsync(c->lv[l].buf[op.dst][i], 0, (size_t)p->geom[l].total * esz, s));
+        return EVO_OK;
+    case EVO_OP_COPY:
+        for (int i = 0; i < NF; ++i)
+            if (c->lv[l].buf[op.dst][i] != c->lv[l].buf[op.src][i])
+                CU(cudaMemcpyAsync(c->lv[l].buf[op.dst][i], c->lv[l].buf[op.src][i], (size_t)p->geom[l].total * esz,
+                                   cudaMemcpyDeviceToDevice, s));
+        return EVO_OK;
+    case EVO_OP_RESIDUAL: return L::residual(c, l, false, s);
+    case EVO_OP_RICHARDSON: return L::richardson(c, op, s);
+    case EVO_OP_SMOOTH: return L::smooth(c, op, s);
+    case EVO_OP_RESTRICT: return L::restrict_(c, op, s);
+    case EVO_OP_RESIDUAL_RESTRICT: return L::residual_restrict(c, op, s);
+    case EVO_OP_PROLONG_ADD: return L::prolong(c, op, true, s);
+    case EVO_OP_PROLONG_SET: return L::prolong(c, op, false, s);
+    case EVO_OP_COARSE_SOLVE:
+        if (sizeof(T) == sizeof(double)) return coarse_cg<DIM, NF>(c, op, s);
+        return fail(EVO_ERR_UNSUPPORTED, "complex coarse-grid solver not implemented yet");
+    default: return fail(EVO_ERR_UNSUPPORTED, "op code %d not implemented", op.code);
+    }
+}
+
+static int dispatch_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
+{
+    const evo_problem_desc &d = c->p->desc;
+    if (d.scalar_words == 2) return enqueue_op<cplx, 2, 1>(c, op, s);
+    if (d.dim == 2) return d.n_fields == 1 ? enqueue_op<double, 2, 1>(c, op, s) : enqueue_op<double, 2, 2>(c, op, s);
+    return d.n_fields == 1 ? enqueue_op<double, 3, 1>(c, op, s) : enqueue_op<double, 3, 2>(c, op, s);
+}
+
+static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s)
+{
+    const evo_problem_desc &d = c->p->desc;
+    const int l = d.max_level;
+    if (d.scalar_words == 2) EV((Launch<cplx, 2, 1>::residual(c, l, true, s)));
+    else if (d.dim == 2 && d.n_fields == 1) EV((Launch<double, 2, 1>::residual(c, l, true, s)));
+    else if (d.dim == 2) EV((Launch<double, 2, 2>::residual(c, l, true, s)));
+    else if (d.n_fields == 1) EV((Launch<double, 3, 1>::residual(c, l, true, s)));
+    else EV((Launch<double, 3, 2>::residual(c, l, true, s)));
+    k_reduce_partials<<<1, 1024, 0, s>>>(c->d_partials, c->n_partials, c->d_state);
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+// all statements of the cycle function, then restore the canonical jacobi-slot assignment so that a
+// replay (next outer iteration) starts from the same pointers
+static int enqueue_cycle(evo_cycle *c, cudaStream_t s)
+{
+    evo_problem *p = c->p;
+    for (const evo_op &op : c->ops) EV(dispatch_op(c, op, s));
+    const size_t esz = sizeof(double) * p->words;
+    for (int l = p->desc.min_level; l <= p->desc.max_level; ++l)
+        for (int i = 0; i < p->desc.n_fields; ++i)
+            if (c->lv[l].swapped[i]) {
+                // current content lives in the buffer that was the slot at cycle start: copy back
+                CU(cudaMemcpyAsync(c->lv[l].slot[i], c->lv[l].buf[EVO_BUF_SOL][i], (size_t)p->geom[l].total * esz,
+                                   cudaMemcpyDeviceToDevice, s));
+                bool cor_alias = c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].buf[EVO_BUF_SOL][i];
+                std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
+                if (cor_alias) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
+                c->lv[l].swapped[i] = false;
+            }
+    return EVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cycle: validation + build
+static int validate_ops(const evo_cycle *c)
+{
+    const evo_problem_desc &d = c->p->desc;
+    for (size_t t = 0; t < c->ops.size(); ++t) {
+        const evo_op &op = c->ops[t];
+        int lo = d.min_level;
+        if (op.code == EVO_OP_RESTRICT || op.code == EVO_OP_PROLONG_ADD || op.code == EVO_OP_PROLONG_SET ||
+            op.code == EVO_OP_RESIDUAL_RESTRICT || op.code == EVO_OP_FAS_RESTRICT_SOL || op.code == EVO_OP_FAS_COARSE_RHS)
+            lo = d.min_level + 1;
+        if (op.level < lo || op.level > d.max_level) return fail(EVO_ERR_INVALID, "op %zu: level %d out of range", t, op.level);
+        if (op.dst < 0 || op.dst >= EVO_BUF_COUNT || op.src < 0 || op.src >= EVO_BUF_COUNT)
+            return fail(EVO_ERR_INVALID, "op %zu: invalid buffer", t);
+        bool needs_op = op.code == EVO_OP_RESIDUAL || op.code == EVO_OP_RICHARDSON || op.code == EVO_OP_SMOOTH ||
+                        op.code == EVO_OP_COARSE_SOLVE || op.code == EVO_OP_RESIDUAL_RESTRICT;
+        if (needs_op && !c->has_sten[op.level]) return fail(EVO_ERR_INVALID, "op %zu: no operator for level %d", t, op.level);
+        if (op.code == EVO_OP_SMOOTH && (op.n_unknowns < 1 || op.n_unknowns > EVO_MAX_UNKNOWNS))
+            return fail(EVO_ERR_INVALID, "op %zu: local system size %d", t, op.n_unknowns);
+    }
+    if (!c->has_sten[d.max_level]) return fail(EVO_ERR_INVALID, "no operator for the finest level");
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_destroy(evo_cycle *c);
+
+extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, const evo_level_operator *operators,
+                               int n_operators, evo_cycle **out)
+{
+    if (!p || !out || (n_ops > 0 && !ops) || (n_operators > 0 && !operators)) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(p->desc.device));
+    evo_cycle *c = new evo_cycle();
+    c->p = p;
+    c->ops.assign(ops, ops + n_ops);
+    c->slab = nullptr;
+    c->graph = nullptr;
+    c->exec = nullptr;
+    c->stream = nullptr;
+    c->h_state = nullptr;
+    c->h_hist = nullptr;
+    c->d_hist = nullptr;
+    c->hist_cap = 0;
+    c->use_while_graph = true;
+    memset(c->has_sten, 0, sizeof(c->has_sten));
+    memset(c->lv, 0, sizeof(c->lv));
+    for (int t = 0; t < n_operators; ++t) {
+        const int l = operators[t].level;
+        if (l < p->desc.min_level || l > p->desc.max_level) { delete c; return fail(EVO_ERR_INVALID, "operator level %d out of range", l); }
+        OpSten &os = c->sten[l];
+        memset(&os, 0, sizeof(os));
+        for (int i = 0; i < p->desc.n_fields; ++i)
+            for (int j = 0; j < p->desc.n_fields; ++j) {
+                Sten &s = os.s[i][j];
+                for (int q = 0; q < 27; ++q) {
+                    double re = operators[t].coef[i][j][q][0], im = operators[t].coef[i][j][q][1];
+                    if (re == 0.0 && im == 0.0) continue;
+                    int oz = q / 9 - 1;
+                    if (p->desc.dim == 2 && oz != 0) { delete c; return fail(EVO_ERR_INVALID, "3-D stencil entry in a 2-D problem"); }
+                    int k = s.nnz++;
+                    s.ox[k] = (signed char)(q % 3 - 1); s.oy[k] = (signed char)((q / 3) % 3 - 1); s.oz[k] = (signed char)oz;
+                    s.re[k] = re; s.im[k] = im;
+                }
+            }
+        c->has_sten[l] = true;
+    }
+    int rc = validate_ops(c);
+    if (rc == EVO_OK) rc = allocate_cycle(c);
+    if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMallocHost(&c->h_state, sizeof(SolveState)));
+    rc = reset_cycle(c, c->stream);
+    if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_destroy(evo_cycle *c)
+{
+    if (!c) return EVO_OK;
+    cudaSetDevice(c->p->desc.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->exec) cudaGraphExecDestroy(c->exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    if (c->slab) c->p->pool.push_back({c->slab, c->slab_bytes});
+    // keep the pool bounded: free slabs beyond a generous budget
+    size_t pooled = 0;
+    for (auto &s : c->p->pool) pooled += s.second;
+    while (!c->p->pool.empty() && (c->p->pool.size() > 512 || pooled > ((size_t)64 << 30))) {
+        pooled -= c->p->pool.front().second;
+        cudaFree(c->p->pool.front().first);
+        c->p->pool.erase(c->p->pool.begin());
+    }
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_hist) cudaFreeHost(c->h_hist);
+    if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream); }
+    delete c;
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_reset(evo_cycle *c)
+{
+    if (!c) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    EV(reset_cycle(c, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_apply(evo_cycle *c, int repeat)
+{
+    if (!c) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    for (int r = 0; r < repeat; ++r) EV(enqueue_cycle(c, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return EVO_OK;
+}
+
+static int field_ptr(evo_cycle *c, int level, int buf, int field, void **out)
+{
+    const evo_problem_desc &d = c->p->desc;
+    if (level < d.min_level || level > d.max_level || field < 0 || field >= d.n_fields || buf < 0 || buf >= EVO_BUF_COUNT)
+        return fail(EVO_ERR_INVALID, "invalid level/buffer/field");
+    *out = c->lv[level].buf[buf][field];
+    if (!*out) return fail(EVO_ERR_INVALID, "buffer not allocated for this problem kind");
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, double *host, size_t n_doubles)
+{
+    if (!c || !host) return fail(EVO_ERR_INVALID, "null argument");
+    void *dev;
+    EV(field_ptr(c, level, buf, field, &dev));
+    const Geom &g = c->p->geom[level];
+    if (n_doubles != (size_t)g.n * g.n * g.nz * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    CU(cudaSetDevice(c->p->desc.device));
+    return copy_field(g, c->p->words, dev, nullptr, host, c->stream);
+}
+
+extern "C" int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, const double *host, size_t n_doubles)
+{
+    if (!c || !host) return fail(EVO_ERR_INVALID, "null argument");
+    void *dev;
+    EV(field_ptr(c, level, buf, field, &dev));
+    if (level == c->p->desc.max_level && buf == EVO_BUF_RHS)
+        return fail(EVO_ERR_UNSUPPORTED, "the finest right-hand side is shared by all cycles: use evo_problem_set_field");
+    const Geom &g = c->p->geom[level];
+    if (n_doubles != (size_t)g.n * g.n * g.nz * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    CU(cudaSetDevice(c->p->desc.device));
+    EV(copy_field(g, c->p->words, dev, host, nullptr, c->stream));
+    if (buf == EVO_BUF_SOL && c->lv[level].slot[field])  // keep the boundary invariant of the jacobi slot
+        EV(copy_field(g, c->p->words, c->lv[level].slot[field], host, nullptr, c->stream));
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_residual_norm(evo_cycle *c, double *norm)
+{
+    if (!c || !norm) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    EV(dispatch_residual_norm(c, c->stream));
+    CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *norm = sqrt(c->h_state->sum);
+    return EVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve: the generated solver's outer loop
+__global__ void k_set_while_condition(cudaGraphConditionalHandle handle, const SolveState *st)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) cudaGraphSetConditional(handle, st->done ? 0u : 1u);
+}
+
+static int ensure_hist(evo_cycle *c, int max_iters)
+{
+    if (c->hist_cap >= max_iters + 1) return EVO_OK;
+    if (c->d_hist) cudaFree(c->d_hist);
+    if (c->h_hist) cudaFreeHost(c->h_hist);
+    c->hist_cap = max_iters + 1;
+    CU(cudaMalloc(&c->d_hist, sizeof(double) * c->hist_cap));
+    CU(cudaMallocHost(&c->h_hist, sizeof(double) * c->hist_cap));
+    return EVO_OK;
+}
+
+// graph = [res0 + norm + update(0)] -> WHILE(!done) { cycle ops; residual + norm; update(1); set condition }
+static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
+{
+    if (c->exec && c->graph_tol == tol && c->graph_max_iters == max_iters) return EVO_OK;
+    if (c->exec) { cudaGraphExecDestroy(c->exec); c->exec = nullptr; }
+    if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+    cudaStream_t s = c->stream;
+    // prologue captured into the main graph
+    c->launch_counter = 0;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = dispatch_residual_norm(c, s);
+    if (rc == EVO_OK) {
+        k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 0);
+        c->launch_counter++;
+    }
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc != EVO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "prologue capture: %s", cudaGetErrorString(e));
+    c->kernels_prologue = c->launch_counter;
+    // find the leaf of the prologue to hang the while node on
+    size_t n_nodes = 0;
+    CU(cudaGraphGetNodes(g, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    CU(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+    std::vector<cudaGraphNode_t> leaves;
+    for (cudaGraphNode_t nd : nodes) {
+        size_t nd_dep = 0;
+        CU(cudaGraphNodeGetDependentNodes(nd, nullptr, &nd_dep));
+        if (nd_dep == 0) leaves.push_back(nd);
+    }
+    cudaGraphConditionalHandle handle;
+    CU(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    // guard: the while body must not run when the prologue already set done (max_iters == 0 / bad)
+    // -> a tiny kernel node after the prologue sets the condition from the state
+    cudaGraphNode_t cond_init;
+    {
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        void *args[2] = {(void *)&handle, (void *)&c->d_state};
+        kp.func = (void *)k_set_while_condition;
+        kp.gridDim = dim3(1);
+        kp.blockDim = dim3(32);
+        kp.kernelParams = args;
+        CU(cudaGraphAddKernelNode(&cond_init, g, leaves.data(), leaves.size(), &kp));
+        c->kernels_prologue++;
+    }
+    CU(cudaGraphAddNode(&wnode, g, &cond_init, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    c->launch_counter = 0;
+    CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_cycle(c, s);
+    if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
+    if (rc == EVO_OK) {
+        k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 1);
+        k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
+        c->launch_counter += 2;
+    }
+    e = cudaStreamEndCapture(s, nullptr);
+    if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "body capture: %s", cudaGetErrorString(e)); }
+    c->kernels_per_cycle = c->launch_counter;
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    c->graph = g;
+    c->exec = exec;
+    c->graph_tol = tol;
+    c->graph_max_iters = max_iters;
+    return EVO_OK;
+}
+
+// enqueue one complete solve on the cycle's stream (no host synchronisation)
+static int enqueue_solve(evo_cycle *c, const evo_solve_params *prm)
+{
+    cudaStream_t s = c->stream;
+    if (!(prm->flags & EVO_SOLVE_KEEP_STATE)) EV(reset_cycle(c, s));
+    CU(cudaEventRecord(c->ev0, s));
+    if (prm->flags & EVO_SOLVE_NO_GRAPH) {
+        // debugging path: direct launches, host-side loop with one synchronisation per iteration
+        c->launch_counter = 0;
+        EV(dispatch_residual_norm(c, s));
+        k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, prm->tol, prm->max_iters, 0);
+        c->kernels_prologue = c->launch_counter + 1;
+        for (int it = 0; it < prm->max_iters; ++it) {
+            CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if (c->h_state->done) break;
+            c->launch_counter = 0;
+            EV(enqueue_cycle(c, s));
+            EV(dispatch_residual_norm(c, s));
+            k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, prm->tol, prm->max_iters, 1);
+            c->kernels_per_cycle = c->launch_counter + 1;
+        }
+    } else {
+        CU(cudaGraphLaunch(c->exec, s));
+    }
+    CU(cudaEventRecord(c->ev1, s));
+    CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_hist, c->d_hist, sizeof(double) * (prm->max_iters + 1), cudaMemcpyDeviceToHost, s));
+    return EVO_OK;
+}
+
+static int collect_solve(evo_cycle *c, const evo_solve_params *prm, evo_solve_result *res, double *res_hist, float *ms)
+{
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    const SolveState &st = *c->h_state;
+    res->status = st.bad ? 1 : 0;
+    res->iterations = st.it;
+    res->initial_residual = st.res0;
+    res->final_residual = st.res;
+    res->kernel_launches = c->kernels_prologue + c->kernels_per_cycle * (int64_t)st.it;
+    if (res_hist) memcpy(res_hist, c->h_hist, sizeof(double) * (st.it + 1));
+    return EVO_OK;
+}
+
+static int prepare_solve(evo_cycle *c, const evo_solve_params *prm)
+{
+    if (prm->max_iters < 0 || prm->max_iters > 1000000) return fail(EVO_ERR_INVALID, "max_iters out of range");
+    CU(cudaSetDevice(c->p->desc.device));
+    EV(ensure_hist(c, prm->max_iters));
+    if (!(prm->flags & EVO_SOLVE_NO_GRAPH)) EV(build_solver_graph(c, prm->tol, prm->max_iters));
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_solve(evo_cycle *c, const evo_solve_params *prm, evo_solve_result *res, double *res_hist)
+{
+    if (!c || !prm || !res) return fail(EVO_ERR_INVALID, "null argument");
+    EV(prepare_solve(c, prm));
+    const int samples = prm->samples > 0 ? prm->samples : 1;
+    std::vector<float> times;
+    memset(res, 0, sizeof(*res));
+    for (int sidx = 0; sidx < samples; ++sidx) {
+        float ms = 0.f;
+        EV(enqueue_solve(c, prm));
+        EV(collect_solve(c, prm, res, res_hist, &ms));
+        times.push_back(ms);
+    }
+    std::sort(times.begin(), times.end());
+    res->time_ms = times[times.size() / 2];
+    res->time_ms_min = times[0];
+    return EVO_OK;
+}
+
+// population evaluation on one GPU: every individual's complete solve is one graph launch on its own
+// stream, nothing synchronises until all are in flight (reference: the sequential toolbox.map of
+// optimization/program.py:491, one subprocess chain per individual)
+extern "C" int evo_batch_solve(evo_cycle **cycles, int n, const evo_solve_params *prm, evo_solve_result *results,
+                               double *res_hist, double *batch_ms)
+{
+    if (!cycles || !prm || !results || n < 0) return fail(EVO_ERR_INVALID, "null argument");
+    if (n == 0) { if (batch_ms) *batch_ms = 0.0; return EVO_OK; }
+    if (prm->flags & EVO_SOLVE_NO_GRAPH) return fail(EVO_ERR_UNSUPPORTED, "batch solve needs the device-side outer loop");
+    for (int i = 0; i < n; ++i) EV(prepare_solve(cycles[i], prm));
+    const int samples = prm->samples > 0 ? prm->samples : 1;
+    std::vector<std::vector<float>> times(n);
+    std::vector<float> wall;
+    cudaEvent_t b0, b1;
+    CU(cudaEventCreate(&b0));
+    CU(cudaEventCreate(&b1));
+    cudaStream_t s0 = cycles[0]->stream;
+    for (int sidx = 0; sidx < samples; ++sidx) {
+        // fork: all streams wait for b0 on stream 0; join: stream 0 waits for every ev1
+        CU(cudaEventRecord(b0, s0));
+        for (int i = 0; i < n; ++i) {
+            if (i) CU(cudaStreamWaitEvent(cycles[i]->stream, b0, 0));
+            EV(enqueue_solve(cycles[i], prm));
+        }
+        for (int i = 1; i < n; ++i) CU(cudaStreamWaitEvent(s0, cycles[i]->ev1, 0));
+        CU(cudaEventRecord(b1, s0));
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f;
+            EV(collect_solve(cycles[i], prm, &results[i], res_hist ? res_hist + (size_t)i * (prm->max_iters + 1) : nullptr, &ms));
+            times[i].push_back(ms);
+        }
+        CU(cudaEventSynchronize(b1));
+        float w = 0.f;
+        CU(cudaEventElapsedTime(&w, b0, b1));
+        wall.push_back(w);
+    }
+    for (int i = 0; i < n; ++i) {
+        std::sort(times[i].begin(), times[i].end());
+        results[i].time_ms = times[i][times[i].size() / 2];
+        results[i].time_ms_min = times[i][0];
+    }
+    std::sort(wall.begin(), wall.end());
+    if (batch_ms) *batch_ms = wall[wall.size() / 2];
+    cudaEventDestroy(b0);
+    cudaEventDestroy(b1);
+    return EVO_OK;
+}

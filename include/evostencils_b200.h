@@ -1,0 +1,200 @@
+/*
+ * evostencils_b200.h -- C-ABI of the B200-native multigrid fitness-evaluation backend.
+ *
+ * This library replaces everything *below* the method boundary of the reference's
+ * ProgramGenerator (reference: evostencils/code_generation/exastencils.py:39).  In the
+ * reference that boundary is crossed by three subprocesses (java code generator :397-403,
+ * make :413, the generated solver binary :425-429); here it is crossed by the entry points
+ * declared below.  Every entry point cites the reference interface it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types in any signature
+ *   - all functions return 0 on success, a negative evo_status otherwise;
+ *     evo_last_error() returns a thread-local human readable message
+ *   - a "level" l is a node-based grid with (2^l + 1)^dim nodes including the Dirichlet
+ *     boundary layer, spacing h = 2^-l (reference: exastencils.py:97-103)
+ *   - host-side field arrays are dense, x (= i0) fastest, (2^l+1)^dim entries per field,
+ *     `scalar_words` doubles per entry (1 real, 2 complex); the padded device layout is private
+ */
+#ifndef EVOSTENCILS_B200_H
+#define EVOSTENCILS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVO_ABI_VERSION 1
+#define EVO_MAX_FIELDS 2
+#define EVO_MAX_UNKNOWNS 8   /* reference: optimization/program.py:107 (maximum_local_system_size) */
+#define EVO_MAX_DIM 3
+#define EVO_MAX_LEVELS 16
+#define EVO_STENCIL_POINTS 27 /* 3^3; 2-D problems use the 9 entries of the plane dz = 0 */
+
+/* ---------------------------------------------------------------- status codes */
+enum evo_status {
+    EVO_OK = 0,
+    EVO_ERR_INVALID = -1,   /* malformed descriptor / op list                          */
+    EVO_ERR_CUDA = -2,      /* CUDA runtime error (message in evo_last_error)          */
+    EVO_ERR_NO_DEVICE = -3, /* no CUDA device: the product path has NO CPU fallback    */
+    EVO_ERR_UNSUPPORTED = -4,
+    EVO_ERR_OOM = -5
+};
+
+/* ---------------------------------------------------------------- buffers
+ * Field naming of the reference (exastencils.py:14-26, :295-316):
+ *   SOL  = <field>@finest, gen_error_<field> below the finest level
+ *   RHS  = <rhs_name>            RES = gen_residual_<field>
+ *   COR  = gen_error_<field>     (aliases SOL below the finest level; the lowering resolves that)
+ *   APX  = FAS restricted fine solution (exastencils_FAS.py:121-136)                     */
+enum evo_buffer { EVO_BUF_SOL = 0, EVO_BUF_RHS = 1, EVO_BUF_RES = 2, EVO_BUF_COR = 3, EVO_BUF_APX = 4,
+                  EVO_BUF_COUNT = 5 };
+
+/* ---------------------------------------------------------------- op codes
+ * One op == one statement the reference's emitter would print (exastencils.py:684-925);
+ * codes >= 32 are fused forms produced only by the optimiser pass, never by the lowering.   */
+enum evo_opcode {
+    EVO_OP_ZERO = 1,          /* dst@level = 0                                   (:706-709) */
+    EVO_OP_COPY = 2,          /* dst@level = src@level                           (:897-911) */
+    EVO_OP_RESIDUAL = 3,      /* RES = RHS - A*SOL                               (:837-853) */
+    EVO_OP_RICHARDSON = 4,    /* SOL_i += w*(RHS_i - sum_j A_ij SOL_j), i in order (:710-726) */
+    EVO_OP_SMOOTH = 5,        /* one `solve locally` statement                   (:769-822) */
+    EVO_OP_RESTRICT = 6,      /* dst@(level-1) = R@level * src@level             (:855-873) */
+    EVO_OP_PROLONG_ADD = 7,   /* SOL@level += w * (P@(level-1) * src@(level-1))  (:727-743) */
+    EVO_OP_PROLONG_SET = 8,   /* dst@level  = P@(level-1) * src@(level-1)        (:868-873) */
+    EVO_OP_COARSE_SOLVE = 9,  /* gen_mgCycle@min(): Krylov solve, zero guess     (:874-896) */
+    /* FAS (exastencils_FAS.py:99-319) */
+    EVO_OP_FAS_RESTRICT_SOL = 10, /* APX@(level-1) = R*SOL@level ; SOL@(level-1) = APX     (:121-136) */
+    EVO_OP_FAS_COARSE_RHS = 11,   /* RHS@(level-1) = R*RES@level + N(APX)@(level-1)        (:138-147) */
+    EVO_OP_FAS_SUB_APX = 12,      /* SOL@level -= APX@level                                (:173-183) */
+    /* fused forms */
+    EVO_OP_RESIDUAL_RESTRICT = 32, /* RHS@(level-1) = R*(RHS - A*SOL)@level, RES not stored   */
+    EVO_OP_SMOOTH_FUSED = 33       /* `count` identical pointwise sweeps in one pass           */
+};
+
+/* smoother update mode of a `solve locally` statement */
+enum evo_smooth_mode {
+    EVO_SMOOTH_JACOBI = 0,   /* `with jacobi`: read old slot, write new slot, advance (exastencils.py:780-783) */
+    EVO_SMOOTH_REDBLACK = 1, /* `color with {(i0+..)%2}`: colour 0 first, in place    (:659-667, :785-790)    */
+    EVO_SMOOTH_LEX = 2       /* in place, lexicographic (model-based mode, :64-70)                              */
+};
+
+enum evo_smooth_kind {
+    EVO_KIND_LINEAR = 0,
+    EVO_KIND_FAS_PICARD = 1, /* u += w (f - (A u + N(u)u)) / a00           (exastencils_FAS.py:226-232) */
+    EVO_KIND_FAS_NEWTON = 2  /* ... / (a00 + J(u)), `count` inner steps     (:218-231)                   */
+};
+
+typedef struct evo_op {
+    int32_t code;       /* evo_opcode                                                         */
+    int32_t level;      /* level of the written field (fine level for RESTRICT / PROLONG_*)   */
+    int32_t dst;        /* evo_buffer                                                         */
+    int32_t src;        /* evo_buffer                                                         */
+    int32_t mode;       /* evo_smooth_mode                                                    */
+    int32_t kind;       /* evo_smooth_kind                                                    */
+    int32_t n_unknowns; /* size of the local system of a SMOOTH statement (1..8)              */
+    int32_t count;      /* repetitions (fused sweeps / Newton steps) or max Krylov iterations */
+    int32_t unk_field[EVO_MAX_UNKNOWNS];           /* field index of each unknown             */
+    int32_t unk_off[EVO_MAX_UNKNOWNS][EVO_MAX_DIM];/* node offset of each unknown             */
+    double omega;       /* relaxation factor                                                  */
+    double tol;         /* Krylov relative residual target                                    */
+} evo_op;
+
+/* Rediscretised system operator of one level: coef[i][j][p][w], p = (dz+1)*9+(dy+1)*3+(dx+1),
+ * w = 0 real / 1 imaginary part.  A*u at a node = sum_j sum_p coef[i][j][p] * u_j[node+off_p],
+ * accumulated in ascending (j, p) order (the oracle and the kernels use the same order).       */
+typedef struct evo_level_operator {
+    int32_t level;
+    int32_t pad_;
+    double coef[EVO_MAX_FIELDS][EVO_MAX_FIELDS][EVO_STENCIL_POINTS][2];
+} evo_level_operator;
+
+enum evo_problem_kind {
+    EVO_PROBLEM_LINEAR = 0,    /* Poisson 2D/3D, LinearElasticity (example_problems/ *.exa2)        */
+    EVO_PROBLEM_FAS = 1,       /* -Lap u + gamma u e^u = f  (FAS_2D_Basic_template.exa4:19-34)     */
+    EVO_PROBLEM_HELMHOLTZ = 2  /* complex, Robin x-boundaries (Helmholtz/...exa4:25-145)           */
+};
+
+typedef struct evo_problem_desc {
+    int32_t abi_version;  /* EVO_ABI_VERSION                                             */
+    int32_t dim;          /* 2 or 3          (parser.py:114-125, `dimensionality`)       */
+    int32_t n_fields;     /* 1 or 2                                                      */
+    int32_t scalar_words; /* 1 real fp64, 2 complex fp64                                 */
+    int32_t min_level;    /* coarsest level  (knowledge `minLevel`)                      */
+    int32_t max_level;    /* finest level    (knowledge `maxLevel`)                      */
+    int32_t kind;         /* evo_problem_kind                                            */
+    int32_t device;       /* CUDA device ordinal                                         */
+    double gamma;         /* FAS nonlinearity factor                                     */
+    double k_re, k_im;    /* Helmholtz: Robin factor uses wave number k (exa4:43-108)    */
+    double restrict_w[EVO_STENCIL_POINTS]; /* R weights, offset index p as above (reads fine node 2*I+o) */
+    double prolong_w[EVO_STENCIL_POINTS];  /* P weights (fine node x gets w[o]*coarse[(x+o)/2], x+o even) */
+} evo_problem_desc;
+
+typedef struct evo_solve_params {
+    double tol;          /* solver_targetResReduction (Poisson/2D...exa3:3)                     */
+    int32_t max_iters;   /* solver_maxNumIts (:4)                                               */
+    int32_t samples;     /* evaluation_samples (exastencils.py:417-443): timing repeats          */
+    int32_t flags;       /* EVO_SOLVE_* bits                                                    */
+    int32_t reserved;
+} evo_solve_params;
+
+#define EVO_SOLVE_NO_GRAPH 1   /* debugging: launch kernels directly, no CUDA-graph capture */
+#define EVO_SOLVE_KEEP_STATE 2 /* do not reset SOL to the initial guess before solving      */
+
+typedef struct evo_solve_result {
+    int32_t status;       /* 0 ok, 1 non-finite residual encountered                            */
+    int32_t iterations;   /* outer iterations executed                                          */
+    double time_ms;       /* median solve time over `samples` runs, CUDA events (ms)            */
+    double time_ms_min;
+    double initial_residual;
+    double final_residual;
+    int64_t kernel_launches; /* kernels launched by one solve (graph nodes x iterations)         */
+} evo_solve_result;
+
+typedef struct evo_problem evo_problem;
+typedef struct evo_cycle evo_cycle;
+
+/* -- library -------------------------------------------------------------------------------- */
+int evo_abi_version(void);
+const char *evo_last_error(void);
+/* number of visible CUDA devices; <0 on error.  ProgramGenerator.__init__ raises
+ * RuntimeError("Compiler not found") when its toolchain is missing (exastencils.py:104-108);
+ * the drop-in raises the same way when this returns <= 0.                                      */
+int evo_device_count(void);
+int evo_device_name(int device, char *buf, size_t len, int *sm_count);
+
+/* -- problem = discretisation hierarchy + initial guess / rhs (what InitFields and the field
+ *    declarations of the generated program hold; exastencils.py:586-592 generate_storage)      */
+int evo_problem_create(const evo_problem_desc *desc, evo_problem **out);
+int evo_problem_destroy(evo_problem *p);
+/* upload the initial content of buffer `buf` (SOL incl. boundary values, or RHS) of `field` on
+ * `level`; n_doubles must be (2^level+1)^dim * scalar_words                                    */
+int evo_problem_set_field(evo_problem *p, int level, int buf, int field, const double *host, size_t n_doubles);
+
+/* -- cycle = one lowered individual (replaces generate_cycle_function + java + make,
+ *    exastencils.py:318-336, :381-415)                                                          */
+int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, const evo_level_operator *operators,
+                    int n_operators, evo_cycle **out);
+int evo_cycle_destroy(evo_cycle *c);
+/* run the op list `repeat` times on the cycle's working hierarchy (parity testing hook)        */
+int evo_cycle_reset(evo_cycle *c);
+int evo_cycle_apply(evo_cycle *c, int repeat);
+int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, double *host, size_t n_doubles);
+int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, const double *host, size_t n_doubles);
+/* RES@finest = RHS - A*SOL and its L2 norm over inner nodes (gen_resNorm of the generated solver) */
+int evo_cycle_residual_norm(evo_cycle *c, double *norm);
+
+/* -- solve = the generated solver's outer loop (a9) run `samples` times (a7: evaluate,
+ *    exastencils.py:417-443): res0 = ||f - A u0||; repeat { cycle; res = ||f - A u|| } until
+ *    res < tol*res0 or max_iters.  res_hist receives res0, res1, ... (max_iters+1 entries).     */
+int evo_cycle_solve(evo_cycle *c, const evo_solve_params *params, evo_solve_result *result, double *res_hist);
+/* many individuals in flight on one GPU, one stream each (population evaluation, program.py:491) */
+int evo_batch_solve(evo_cycle **cycles, int n_cycles, const evo_solve_params *params, evo_solve_result *results,
+                    double *res_hist /* n_cycles * (max_iters+1) */, double *batch_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVOSTENCILS_B200_H */

@@ -1,0 +1,330 @@
+/*
+ * oracle.c -- TEST INFRASTRUCTURE.  CPU restatement ("port") of the numerics that the
+ * reference delegates to ExaStencils v1.1 generated C++ (lssfau/ExaStencils tag v1.1, commit
+ * 73ba6ee9..., un-vendored third-party dependency; reference call sites
+ * evostencils/code_generation/exastencils.py:397-403, :413, :425-429).
+ *
+ * It interprets the same op list (include/evostencils_b200.h) the CUDA library executes, with
+ * one plain loop nest per statement, fp64, no fusion.  Pinned against the reference's only
+ * numeric known-answer fixture (notebooks/tutorial.ipynb:3373 + :3422-3470) by
+ * tests/test_oracle_kat.py; every other problem class is "parity unpinned" (SURVEY.md 8c).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  Build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off).
+ */
+#include <complex.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/evostencils_b200.h"
+
+typedef struct Sten {
+    int nnz;
+    int off[27][3];
+    ptrdiff_t delta[27];
+    double re[27], im[27];
+} Sten;
+
+typedef struct Level {
+    int n;        /* nodes per dimension = 2^l + 1 */
+    size_t total; /* n^dim */
+    void *buf[EVO_BUF_COUNT][EVO_MAX_FIELDS];
+    void *slot[EVO_MAX_FIELDS]; /* [next] slot of SOL for `with jacobi` statements */
+    Sten sten[EVO_MAX_FIELDS][EVO_MAX_FIELDS];
+    int has_operator;
+} Level;
+
+typedef struct Hier {
+    int dim, nf, words, min_level, max_level, kind;
+    double gamma, k_re, k_im;
+    double R[27], P[27];
+    Level lv[EVO_MAX_LEVELS];
+    void *init[2][EVO_MAX_FIELDS]; /* pristine SOL / RHS of the finest level */
+    void *scratch[8];              /* finest-level sized work arrays (jacobi slots, CG vectors) */
+    int cg_iterations_last;
+    long cg_iterations_total;
+} Hier;
+
+static double wall_ms(void)
+{
+#ifdef _OPENMP
+    return omp_get_wtime() * 1e3;
+#else
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+#endif
+}
+
+/* ------------------------------------------------------------------ real instantiation */
+#define T double
+#define FN(x) x##_r
+#define CO(s, q) ((s)->re[q])
+#define ABS2(x) ((x) * (x))
+#include "mg_ops.inc"
+#include "mg_krylov.inc"
+#undef T
+#undef FN
+#undef CO
+#undef ABS2
+
+/* ------------------------------------------------------------------ complex instantiation */
+#define T double complex
+#define FN(x) x##_c
+#define CO(s, q) ((s)->re[q] + (s)->im[q] * I)
+#define ABS2(x) (creal(x) * creal(x) + cimag(x) * cimag(x))
+#define EVO_COMPLEX 1
+#include "mg_ops.inc"
+#include "mg_krylov.inc"
+#undef EVO_COMPLEX
+#undef T
+#undef FN
+#undef CO
+#undef ABS2
+
+#include "mg_fas.inc"
+
+/* ------------------------------------------------------------------ hierarchy */
+void *orc_create(const evo_problem_desc *d)
+{
+    if (!d || d->dim < 2 || d->dim > 3 || d->n_fields < 1 || d->n_fields > EVO_MAX_FIELDS ||
+        d->min_level < 1 || d->max_level >= EVO_MAX_LEVELS || d->min_level > d->max_level ||
+        (d->scalar_words != 1 && d->scalar_words != 2))
+        return NULL;
+    Hier *H = (Hier *)calloc(1, sizeof(Hier));
+    H->dim = d->dim; H->nf = d->n_fields; H->words = d->scalar_words;
+    H->min_level = d->min_level; H->max_level = d->max_level; H->kind = d->kind;
+    H->gamma = d->gamma; H->k_re = d->k_re; H->k_im = d->k_im;
+    memcpy(H->R, d->restrict_w, sizeof(H->R));
+    memcpy(H->P, d->prolong_w, sizeof(H->P));
+    const size_t esz = sizeof(double) * (size_t)H->words;
+    for (int l = H->min_level; l <= H->max_level; ++l) {
+        Level *L = &H->lv[l];
+        L->n = (1 << l) + 1;
+        L->total = (size_t)L->n * L->n * (H->dim == 3 ? L->n : 1);
+        for (int b = 0; b < EVO_BUF_COUNT; ++b)
+            for (int i = 0; i < H->nf; ++i) L->buf[b][i] = calloc(L->total, esz);
+        for (int i = 0; i < H->nf; ++i) L->slot[i] = calloc(L->total, esz);
+    }
+    Level *F = &H->lv[H->max_level];
+    for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < H->nf; ++i) H->init[b][i] = calloc(F->total, esz);
+    for (int s = 0; s < 8; ++s) H->scratch[s] = calloc(F->total * (size_t)H->nf, esz);
+    return H;
+}
+
+void orc_destroy(void *h)
+{
+    Hier *H = (Hier *)h;
+    if (!H) return;
+    for (int l = H->min_level; l <= H->max_level; ++l)
+        for (int b = 0; b < EVO_BUF_COUNT; ++b)
+            for (int i = 0; i < H->nf; ++i) free(H->lv[l].buf[b][i]);
+    for (int l = H->min_level; l <= H->max_level; ++l)
+        for (int i = 0; i < H->nf; ++i) free(H->lv[l].slot[i]);
+    for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < H->nf; ++i) free(H->init[b][i]);
+    for (int s = 0; s < 8; ++s) free(H->scratch[s]);
+    free(H);
+}
+
+int orc_set_operators(void *h, const evo_level_operator *ops, int n)
+{
+    Hier *H = (Hier *)h;
+    for (int t = 0; t < n; ++t) {
+        int l = ops[t].level;
+        if (l < H->min_level || l > H->max_level) return EVO_ERR_INVALID;
+        Level *L = &H->lv[l];
+        for (int i = 0; i < H->nf; ++i)
+            for (int j = 0; j < H->nf; ++j) {
+                Sten *s = &L->sten[i][j];
+                s->nnz = 0;
+                for (int p = 0; p < 27; ++p) {
+                    double re = ops[t].coef[i][j][p][0], im = ops[t].coef[i][j][p][1];
+                    if (re == 0.0 && im == 0.0) continue;
+                    int ox = p % 3 - 1, oy = (p / 3) % 3 - 1, oz = p / 9 - 1;
+                    if (H->dim == 2 && oz != 0) return EVO_ERR_INVALID;
+                    int q = s->nnz++;
+                    s->off[q][0] = ox; s->off[q][1] = oy; s->off[q][2] = oz;
+                    s->delta[q] = ((ptrdiff_t)oz * L->n + oy) * L->n + ox;
+                    s->re[q] = re; s->im[q] = im;
+                }
+            }
+        L->has_operator = 1;
+    }
+    return EVO_OK;
+}
+
+/* initial content of SOL (with boundary values) or RHS on a level; the finest level's content is
+ * also kept as the pristine state every solve starts from (InitFields of the generated program) */
+int orc_set_field(void *h, int level, int buf, int field, const double *host, size_t n_doubles)
+{
+    Hier *H = (Hier *)h;
+    if (level < H->min_level || level > H->max_level || field < 0 || field >= H->nf || buf < 0 || buf >= EVO_BUF_COUNT)
+        return EVO_ERR_INVALID;
+    Level *L = &H->lv[level];
+    if (n_doubles != L->total * (size_t)H->words) return EVO_ERR_INVALID;
+    memcpy(L->buf[buf][field], host, n_doubles * sizeof(double));
+    if (level == H->max_level && (buf == EVO_BUF_SOL || buf == EVO_BUF_RHS))
+        memcpy(H->init[buf][field], host, n_doubles * sizeof(double));
+    return EVO_OK;
+}
+
+int orc_get_field(void *h, int level, int buf, int field, double *host, size_t n_doubles)
+{
+    Hier *H = (Hier *)h;
+    if (level < H->min_level || level > H->max_level || field < 0 || field >= H->nf || buf < 0 || buf >= EVO_BUF_COUNT)
+        return EVO_ERR_INVALID;
+    Level *L = &H->lv[level];
+    if (n_doubles != L->total * (size_t)H->words) return EVO_ERR_INVALID;
+    memcpy(host, L->buf[buf][field], n_doubles * sizeof(double));
+    return EVO_OK;
+}
+
+int orc_reset(void *h)
+{
+    Hier *H = (Hier *)h;
+    const size_t esz = sizeof(double) * (size_t)H->words;
+    for (int l = H->min_level; l <= H->max_level; ++l)
+        for (int b = 0; b < EVO_BUF_COUNT; ++b)
+            for (int i = 0; i < H->nf; ++i) {
+                if (l == H->max_level && b < 2) memcpy(H->lv[l].buf[b][i], H->init[b][i], H->lv[l].total * esz);
+                else memset(H->lv[l].buf[b][i], 0, H->lv[l].total * esz);
+            }
+    H->cg_iterations_total = 0;
+    return EVO_OK;
+}
+
+/* ------------------------------------------------------------------ interpreter */
+static int run_op(Hier *H, const evo_op *op)
+{
+    const int l = op->level;
+    if (l < H->min_level || l > H->max_level) return EVO_ERR_INVALID;
+    const int cplx = H->words == 2;
+    if (H->kind == EVO_PROBLEM_FAS) {
+        int rc = fas_run_op(H, op);
+        if (rc != 1) return rc; /* 1 = not a FAS-specific op, fall through */
+    }
+    switch (op->code) {
+    case EVO_OP_ZERO: cplx ? op_zero_c(H, l, op->dst) : op_zero_r(H, l, op->dst); break;
+    case EVO_OP_COPY: cplx ? op_copy_c(H, l, op->dst, op->src) : op_copy_r(H, l, op->dst, op->src); break;
+    case EVO_OP_RESIDUAL: cplx ? op_residual_c(H, l) : op_residual_r(H, l); break;
+    case EVO_OP_RICHARDSON: cplx ? op_richardson_c(H, l, op->omega) : op_richardson_r(H, l, op->omega); break;
+    case EVO_OP_SMOOTH:
+        if (op->n_unknowns < 1 || op->n_unknowns > EVO_MAX_UNKNOWNS) return EVO_ERR_INVALID;
+        for (int r = 0; r < (op->count > 1 ? op->count : 1); ++r) cplx ? op_smooth_c(H, op) : op_smooth_r(H, op);
+        break;
+    case EVO_OP_RESTRICT:
+        if (l <= H->min_level) return EVO_ERR_INVALID;
+        cplx ? op_restrict_c(H, l, op->dst, op->src) : op_restrict_r(H, l, op->dst, op->src);
+        break;
+    case EVO_OP_PROLONG_ADD:
+        if (l <= H->min_level) return EVO_ERR_INVALID;
+        cplx ? op_prolong_c(H, l, EVO_BUF_SOL, op->src, 1, op->omega) : op_prolong_r(H, l, EVO_BUF_SOL, op->src, 1, op->omega);
+        break;
+    case EVO_OP_PROLONG_SET:
+        if (l <= H->min_level) return EVO_ERR_INVALID;
+        cplx ? op_prolong_c(H, l, op->dst, op->src, 0, 1.0) : op_prolong_r(H, l, op->dst, op->src, 0, 1.0);
+        break;
+    case EVO_OP_COARSE_SOLVE:
+        H->cg_iterations_last = cplx ? coarse_solve_c(H, l, op->count, op->tol) : coarse_solve_r(H, l, op->count, op->tol);
+        H->cg_iterations_total += H->cg_iterations_last;
+        break;
+    case EVO_OP_RESIDUAL_RESTRICT: /* fused form == the two statements in sequence */
+        cplx ? op_residual_c(H, l) : op_residual_r(H, l);
+        cplx ? op_restrict_c(H, l, EVO_BUF_RHS, EVO_BUF_RES) : op_restrict_r(H, l, EVO_BUF_RHS, EVO_BUF_RES);
+        break;
+    default: return EVO_ERR_UNSUPPORTED;
+    }
+    return EVO_OK;
+}
+
+int orc_run_ops(void *h, const evo_op *ops, int n_ops, int repeat)
+{
+    Hier *H = (Hier *)h;
+    for (int r = 0; r < repeat; ++r)
+        for (int t = 0; t < n_ops; ++t) {
+            int rc = run_op(H, &ops[t]);
+            if (rc) return rc;
+        }
+    return EVO_OK;
+}
+
+static double finest_residual_norm(Hier *H)
+{
+    if (H->kind == EVO_PROBLEM_FAS) return fas_residual_norm(H, H->max_level);
+    if (H->words == 2) { op_residual_c(H, H->max_level); return sqrt(norm2_inner_c(H, H->max_level, EVO_BUF_RES)); }
+    op_residual_r(H, H->max_level);
+    return sqrt(norm2_inner_r(H, H->max_level, EVO_BUF_RES));
+}
+
+int orc_residual_norm(void *h, double *norm) { *norm = finest_residual_norm((Hier *)h); return EVO_OK; }
+
+/* The generated solver's outer loop (`generate solver` block, example_problems/Poisson/
+ * 2D_FD_Poisson_fromL2.exa3:2-15): res0; repeat { gen_mgCycle@finest; res = resNorm } until
+ * res < tol*res0 or it >= maxIts.  res_hist[0..iters] = res0, res1, ...                        */
+int orc_solve(void *h, const evo_op *ops, int n_ops, const evo_solve_params *prm, evo_solve_result *out, double *res_hist)
+{
+    Hier *H = (Hier *)h;
+    const int samples = prm->samples > 0 ? prm->samples : 1;
+    double best = 1e300, times[64];
+    memset(out, 0, sizeof(*out));
+    for (int s = 0; s < samples; ++s) {
+        if (!(prm->flags & EVO_SOLVE_KEEP_STATE)) orc_reset(H);
+        double t0 = wall_ms();
+        double res0 = finest_residual_norm(H), res = res0;
+        res_hist[0] = res0;
+        int it = 0, bad = 0;
+        while (it < prm->max_iters) {
+            int rc = orc_run_ops(H, ops, n_ops, 1);
+            if (rc) return rc;
+            res = finest_residual_norm(H);
+            ++it;
+            res_hist[it] = res;
+            if (!isfinite(res)) { bad = 1; break; }
+            if (res < prm->tol * res0) break;
+        }
+        double t1 = wall_ms();
+        times[s < 64 ? s : 63] = t1 - t0;
+        if (t1 - t0 < best) best = t1 - t0;
+        out->status = bad;
+        out->iterations = it;
+        out->initial_residual = res0;
+        out->final_residual = res;
+    }
+    /* median */
+    int m = samples < 64 ? samples : 64;
+    for (int a = 0; a < m; ++a)
+        for (int b = a + 1; b < m; ++b)
+            if (times[b] < times[a]) { double t = times[a]; times[a] = times[b]; times[b] = t; }
+    out->time_ms = times[m / 2];
+    out->time_ms_min = best;
+    out->kernel_launches = 0;
+    return EVO_OK;
+}
+
+long orc_cg_iterations(void *h) { return ((Hier *)h)->cg_iterations_total; }
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
