@@ -42,43 +42,52 @@ __device__ __forceinline__ T apply_row(const Geom &g, const OpSten &st, const Fi
 
 // ------------------------------------------------------------------------------------------------
 // gen_residual_<f>@l = RHS@l - (A@l * SOL@l)                          (exastencils.py:837-853)
-// optional fused partial sums of |r|^2 (one double per block, fixed order -> deterministic norm)
-template <typename T, int DIM, int NF, bool NORM>
+template <typename T, int DIM, int NF>
 __global__ void __launch_bounds__(BX) k_residual(const Geom g, const __grid_constant__ OpSten st, Fields<T> u,
-                                                 Fields<T> f, Fields<T> r, double *partials)
+                                                 Fields<T> f, Fields<T> r)
 {
-    __shared__ double red[32];
     const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
-    double sq = 0.0;
-    if (x <= g.n - 2) {
-        const long long idx = node_index(g, x, y, z);
+    if (x > g.n - 2) return;
+    const long long idx = node_index(g, x, y, z);
 #pragma unroll
-        for (int i = 0; i < NF; ++i) {
-            T v = f.p[i][idx] - apply_row<T, NF>(g, st, u, i, idx);
-            r.p[i][idx] = v;
-            if (NORM) sq += abs2(v);
-        }
-    }
-    if (NORM) {
-        double s = block_sum(sq, red);
-        if (threadIdx.x == 0) partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
-    }
+    for (int i = 0; i < NF; ++i) r.p[i][idx] = f.p[i][idx] - apply_row<T, NF>(g, st, u, i, idx);
 }
 
-// |r|^2 partial sums over inner nodes of an existing field (norm of a stored residual)
-template <typename T, int DIM, int NF>
-__global__ void __launch_bounds__(BX) k_norm2(const Geom g, Fields<T> r, double *partials)
+// ---- canonical reduction order (shared with oracle/mg_ops.inc, which documents it) ---------------
+//   vecsum(v[0..m)): lane (i mod 32) adds v[i] in ascending i, then xor butterfly 16,8,4,2,1
+//   field sum      : vecsum_z( vecsum_y( vecsum_x(row) ) );  total: field sums added in field order
+// A warp IS this order: lane-strided loop + __shfl_xor tree.  Every reduction of a solve (residual
+// norm, Krylov dot products) uses it, which makes GPU and oracle residual histories bit-identical.
+__device__ __forceinline__ double shfl_xor(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ cplx shfl_xor(cplx v, int o)
 {
-    __shared__ double red[32];
-    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
-    double sq = 0.0;
-    if (x <= g.n - 2) {
-        const long long idx = node_index(g, x, y, z);
+    return cplx(__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o));
+}
+template <typename T> __device__ __forceinline__ T warp_butterfly(T v)
+{
 #pragma unroll
-        for (int i = 0; i < NF; ++i) sq += abs2(r.p[i][idx]);
+    for (int o = 16; o > 0; o >>= 1) v = v + shfl_xor(v, o);
+    return v;
+}
+// canonical vecsum of v[0..m) by one full warp (all lanes return the sum)
+template <typename T> __device__ __forceinline__ T warp_vecsum(const T *v, int m)
+{
+    const int lane = threadIdx.x & 31;
+    T acc = T(0.0);
+    for (int i = lane; i < m; i += 32) acc = acc + v[i];
+    return warp_butterfly(acc);
+}
+// canonical sum over one row of inner nodes of a*b (b == nullptr: |a|^2 as a real number)
+template <typename T, typename R>
+__device__ __forceinline__ R warp_row_dot(const T *a, const T *b, long long row_base /* index of x = 1 */, int ni)
+{
+    const int lane = threadIdx.x & 31;
+    R acc = R(0.0);
+    for (int i = lane; i < ni; i += 32) {
+        if constexpr (sizeof(R) == sizeof(T)) acc = acc + (b ? a[row_base + i] * b[row_base + i] : R(abs2(a[row_base + i])));
+        else acc = acc + abs2(a[row_base + i]);
     }
-    double s = block_sum(sq, red);
-    if (threadIdx.x == 0) partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    return warp_butterfly(acc);
 }
 
 // state of the generated solver's outer loop, resident on the device (one per cycle)
@@ -91,14 +100,58 @@ struct SolveState {
     int pad;
 };
 
-// final, order-fixed reduction of the per-block partial sums (single block)
-__global__ void __launch_bounds__(1024) k_reduce_partials(const double *partials, int n, SolveState *st)
+// |r|^2 row sums of every field: one warp per row; rows[(field * nzi + (z - z0)) * ni + (y - 1)]
+template <typename T, int DIM, int NF>
+__global__ void __launch_bounds__(128) k_row_sumsq(const Geom g, Fields<T> r, double *rows)
 {
-    __shared__ double red[32];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) acc += partials[i];
-    double s = block_sum(acc, red);
-    if (threadIdx.x == 0) st->sum = s;
+    const int ni = g.n - 2, nzi = DIM == 3 ? ni : 1;
+    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= (long long)ni * nzi) return;
+    const int y = 1 + (int)(row % ni), z = DIM == 3 ? 1 + (int)(row / ni) : 0;
+    const long long base = node_index(g, 1, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        double s = warp_row_dot<T, double>(r.p[i], nullptr, base, ni);
+        if ((threadIdx.x & 31) == 0) rows[(long long)i * ni * nzi + row] = s;
+    }
+}
+
+// rows -> planes -> field sums -> total (single block of 32 warps)
+template <int DIM>
+__global__ void __launch_bounds__(1024) k_reduce_rows(const double *rows, int nf, int ni, SolveState *st)
+{
+    __shared__ double planes[1024];
+    __shared__ double fsum[EVO_MAX_FIELDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nzi = DIM == 3 ? ni : 1;
+    for (int i = 0; i < nf; ++i) {
+        const double *fr = rows + (long long)i * ni * nzi;
+        if (DIM == 3) {
+            for (int base = 0; base < nzi; base += 1024) {  // nzi <= 1023 for every supported level
+                for (int zz = base + warp; zz < min(nzi, base + 1024); zz += 32) {
+                    double s = warp_vecsum(fr + (long long)zz * ni, ni);
+                    if (lane == 0) planes[zz - base] = s;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double s = warp_vecsum(planes, nzi);
+                if (lane == 0) fsum[i] = s;
+            }
+            __syncthreads();
+        } else {
+            if (warp == 0) {
+                double s = warp_vecsum(fr, ni);
+                if (lane == 0) fsum[i] = s;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int i = 0; i < nf; ++i) total = total + fsum[i];
+        st->sum = total;
+    }
 }
 
 // bookkeeping of the outer loop: `until res < tol*res0 or it >= maxIts`
@@ -378,27 +431,44 @@ __global__ void __launch_bounds__(BX) k_axpy_inner(const Geom g, T *y_, const T 
 template <int DIM, int NF>
 __global__ void __launch_bounds__(1024) k_coarse_cg(const Geom g, const __grid_constant__ OpSten st, Fields<double> x,
                                                     Fields<double> b, Fields<double> r, Fields<double> p,
-                                                    Fields<double> ap, int max_it, double tol, int *iters_out)
+                                                    Fields<double> ap, double *rows, int max_it, double tol,
+                                                    int *iters_out)
 {
-    __shared__ double red[32];
+    __shared__ double planes[1024];
     __shared__ double bc;
-    const int ni = g.n - 2;
+    const int ni = g.n - 2, nzi = DIM == 3 ? ni : 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long count = (long long)ni * ni * (DIM == 3 ? ni : 1);
     auto idx_of = [&](long long t) {
         int ix = (int)(t % ni), iy = (int)((t / ni) % ni), iz = DIM == 3 ? (int)(t / ((long long)ni * ni)) : -1;
         return node_index(g, ix + 1, iy + 1, iz + 1);
     };
+    // canonical dot product (see warp_vecsum): rows by warps, then planes, then fields in order
     auto dot = [&](const Fields<double> &a_, const Fields<double> &b_) {
-        double acc = 0.0;
-        for (int i = 0; i < NF; ++i)
-            for (long long t = threadIdx.x; t < count; t += blockDim.x) {
-                long long id = idx_of(t);
-                acc += a_.p[i][id] * b_.p[i][id];
+        double total = 0.0;
+        for (int i = 0; i < NF; ++i) {
+            for (int row = warp; row < ni * nzi; row += 32) {
+                const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+                double s = warp_row_dot<double, double>(a_.p[i], b_.p[i], node_index(g, 1, y, z), ni);
+                if (lane == 0) rows[row] = s;
             }
-        double s = block_sum(acc, red);
-        if (threadIdx.x == 0) bc = s;
-        __syncthreads();
-        return bc;
+            __syncthreads();
+            if (DIM == 3) {
+                for (int zz = warp; zz < nzi; zz += 32) {
+                    double s = warp_vecsum(rows + (long long)zz * ni, ni);
+                    if (lane == 0) planes[zz] = s;
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
+                double s = DIM == 3 ? warp_vecsum(planes, nzi) : warp_vecsum(rows, ni);
+                if (lane == 0) bc = s;
+            }
+            __syncthreads();
+            total = total + bc;
+            __syncthreads();
+        }
+        return total;
     };
     for (int i = 0; i < NF; ++i)
         for (long long t = threadIdx.x; t < g.total; t += blockDim.x) {

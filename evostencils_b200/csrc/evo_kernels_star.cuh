@@ -9,7 +9,7 @@ namespace evo {
 namespace star {
 
 template <typename T, int DIM, int NF>
-static bool try_residual(int, const Geom &, const OpSten &, Fields<T>, Fields<T>, Fields<T>, double *, cudaStream_t)
+static bool try_residual(int, const Geom &, const OpSten &, Fields<T>, Fields<T>, Fields<T>, cudaStream_t)
 {
     return false;
 }

@@ -282,8 +282,7 @@ static int allocate_cycle(evo_cycle *c)
         c->d_state = (SolveState *)take(sizeof(SolveState));
         c->d_cg_iters = (int *)take(256);
         const Geom &gf = p->geom[hi];
-        dim3 gr = row_grid(gf);
-        c->n_partials = (int)(gr.x * gr.y * gr.z);
+        c->n_partials = nf * (gf.n - 2) * (gf.dim == 3 ? gf.n - 2 : 1);
         c->d_partials = (double *)take(sizeof(double) * (size_t)c->n_partials);
         if (pass == 0) {
             c->slab_bytes = off;
@@ -324,12 +323,15 @@ template <typename T, int DIM, int NF> struct Launch {
         const Geom &g = c->p->geom[l];
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              r = fields_of<T>(c->lv[l].buf[EVO_BUF_RES], NF);
-        if (star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, norm ? c->d_partials : nullptr, s)) {
-            c->launch_counter++;
-        } else {
-            if (norm) k_residual<T, DIM, NF, true><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, c->d_partials);
-            else k_residual<T, DIM, NF, false><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, nullptr);
-            c->launch_counter++;
+        if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s))
+            k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
+        c->launch_counter++;
+        if (norm) {
+            const int ni = g.n - 2;
+            const long long nrows = (long long)ni * (DIM == 3 ? ni : 1);
+            k_row_sumsq<T, DIM, NF><<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
+            k_reduce_rows<DIM><<<1, 1024, 0, s>>>(c->d_partials, NF, ni, c->d_state);
+            c->launch_counter += 2;
         }
         CU(cudaGetLastError());
         return EVO_OK;
@@ -380,9 +382,12 @@ template <typename T, int DIM, int NF> struct Launch {
             } else if (op.mode == EVO_SMOOTH_REDBLACK) {
                 auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF);
                 if (color_order_dependent(c->sten[l], sp, NF)) {
-                    if (NU != NF) return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
-                    k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
-                    c->launch_counter++;
+                    if constexpr (NU == NF) {
+                        k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
+                        c->launch_counter++;
+                    } else {
+                        return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
+                    }
                 } else {
                     for (int color = 0; color < 2; ++color) {
                         sp.color = color;
@@ -487,7 +492,7 @@ template <typename T, int DIM, int NF> struct Launch {
             if (!tmp) return fail(EVO_ERR_INVALID, "missing scratch slot");
             Fields<T> r = u;  // residual of field i goes to tmp; other entries unused (NF passes write all -> use scratch trick)
             for (int j = 0; j < NF; ++j) r.p[j] = (T *)c->lv[l].slot[j];
-            k_residual<T, DIM, NF, false><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r, nullptr);
+            k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
             k_axpy_inner<T, DIM><<<row_grid(g), BX, 0, s>>>(g, (T *)c->lv[l].buf[EVO_BUF_SOL][i], tmp, op.omega);
             c->launch_counter += 2;
         }
@@ -496,15 +501,6 @@ template <typename T, int DIM, int NF> struct Launch {
         return EVO_OK;
     }
 
-    static int norm2(evo_cycle *c, int l, int buf, cudaStream_t s)
-    {
-        const Geom &g = c->p->geom[l];
-        auto r = fields_of<T>(c->lv[l].buf[buf], NF);
-        k_norm2<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, r, c->d_partials);
-        c->launch_counter++;
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
 };
 
 template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, cudaStream_t s)
@@ -514,7 +510,8 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
     if (l != c->p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
     auto x = fields_of<double>(c->lv[l].buf[EVO_BUF_SOL], NF), b = fields_of<double>(c->lv[l].buf[EVO_BUF_RHS], NF);
     auto r = fields_of<double>(c->krylov[0], NF), p = fields_of<double>(c->krylov[1], NF), ap = fields_of<double>(c->krylov[2], NF);
-    k_coarse_cg<DIM, NF><<<1, 1024, 0, s>>>(g, c->sten[l], x, b, r, p, ap, op.count, op.tol, c->d_cg_iters);
+    k_coarse_cg<DIM, NF><<<1, 1024, 0, s>>>(g, c->sten[l], x, b, r, p, ap, (double *)c->krylov[3][0], op.count, op.tol,
+                                            c->d_cg_iters);
     c->launch_counter++;
     CU(cudaGetLastError());
     return EVO_OK;
@@ -567,9 +564,6 @@ static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s)
     else if (d.dim == 2) EV((Launch<double, 2, 2>::residual(c, l, true, s)));
     else if (d.n_fields == 1) EV((Launch<double, 3, 1>::residual(c, l, true, s)));
     else EV((Launch<double, 3, 2>::residual(c, l, true, s)));
-    k_reduce_partials<<<1, 1024, 0, s>>>(c->d_partials, c->n_partials, c->d_state);
-    c->launch_counter++;
-    CU(cudaGetLastError());
     return EVO_OK;
 }
 

@@ -67,18 +67,21 @@ static double wall_ms(void)
 #define FN(x) x##_r
 #define CO(s, q) ((s)->re[q])
 #define ABS2(x) ((x) * (x))
+#define REAL(x) (x)
 #include "mg_ops.inc"
 #include "mg_krylov.inc"
 #undef T
 #undef FN
 #undef CO
 #undef ABS2
+#undef REAL
 
 /* ------------------------------------------------------------------ complex instantiation */
 #define T double complex
 #define FN(x) x##_c
 #define CO(s, q) ((s)->re[q] + (s)->im[q] * I)
 #define ABS2(x) (creal(x) * creal(x) + cimag(x) * cimag(x))
+#define REAL(x) creal(x)
 #define EVO_COMPLEX 1
 #include "mg_ops.inc"
 #include "mg_krylov.inc"
@@ -87,6 +90,7 @@ static double wall_ms(void)
 #undef FN
 #undef CO
 #undef ABS2
+#undef REAL
 
 #include "mg_fas.inc"
 

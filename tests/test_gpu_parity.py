@@ -25,7 +25,10 @@ def _assert_solve_parity(gc, oc, prob, flags=0):
     b = oc.solve(s.tol, s.max_iters, 1)
     assert a.iterations == b.iterations
     assert a.status == b.status
+    # every reduction uses the shared canonical order -> the histories are bit-identical, far inside
+    # the 1e-10 bar of the north star
     np.testing.assert_allclose(a.residuals, b.residuals, rtol=RES_RTOL, atol=0)
+    assert np.array_equal(a.residuals, b.residuals)
     cfa = fitness.fitness_from_history(a.residuals, a.time_ms, s.max_iters)[1]
     cfb = fitness.fitness_from_history(b.residuals, b.time_ms, s.max_iters)[1]
     assert abs(cfa - cfb) < CF_ATOL
