@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "evo_abi_version", "evo_last_error", "evo_device_count", "evo_device_name",
     "evo_problem_create", "evo_problem_destroy", "evo_problem_set_field",
     "evo_cycle_build", "evo_cycle_destroy", "evo_cycle_reset", "evo_cycle_apply",
-    "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm",
+    "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm", "evo_cycle_profile_op",
     "evo_cycle_solve", "evo_batch_solve",
 )
 
@@ -62,6 +62,8 @@ def load_library(path: Optional[str] = None):
     lib.evo_cycle_get_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.evo_cycle_set_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.evo_cycle_residual_norm.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.evo_cycle_profile_op.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64)]
     lib.evo_cycle_solve.argtypes = [C.c_void_p, C.POINTER(ol.CEvoSolveParams), C.POINTER(ol.CEvoSolveResult),
                                     C.POINTER(C.c_double)]
     lib.evo_batch_solve.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(ol.CEvoSolveParams),
@@ -166,6 +168,14 @@ class DeviceCycle:
         v = C.c_double()
         _check(self._lib, self._lib.evo_cycle_residual_norm(self._h, C.byref(v)), "evo_cycle_residual_norm")
         return float(v.value)
+
+    def profile_op(self, op: ol.Op, repeat: int = 10):
+        """(average ms per execution, kernel launches per execution) of one statement."""
+        ms, n = C.c_double(), C.c_int64()
+        cop = op.to_c()
+        _check(self._lib, self._lib.evo_cycle_profile_op(self._h, C.byref(cop), repeat, C.byref(ms), C.byref(n)),
+               "evo_cycle_profile_op")
+        return float(ms.value), int(n.value)
 
     def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0) -> SolveOutcome:
         prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)

@@ -757,6 +757,42 @@ extern "C" int evo_cycle_residual_norm(evo_cycle *c, double *norm)
     return EVO_OK;
 }
 
+extern "C" int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, double *ms_per_exec, int64_t *launches_per_exec)
+{
+    if (!c || !op || repeat < 1) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    // validate like evo_cycle_build does
+    std::vector<evo_op> saved = c->ops;
+    c->ops.assign(1, *op);
+    int rc = validate_ops(c);
+    c->ops = saved;
+    EV(rc);
+    if (op->code == EVO_OP_SMOOTH && op->mode == EVO_SMOOTH_JACOBI && !c->lv[op->level].slot[0])
+        return fail(EVO_ERR_INVALID, "the cycle was built without a jacobi slot on level %d", op->level);
+    cudaStream_t s = c->stream;
+    EV(dispatch_op(c, *op, s));  // warm-up
+    CU(cudaStreamSynchronize(s));
+    c->launch_counter = 0;
+    CU(cudaEventRecord(c->ev0, s));
+    for (int r = 0; r < repeat; ++r) EV(dispatch_op(c, *op, s));
+    CU(cudaEventRecord(c->ev1, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms_per_exec) *ms_per_exec = (double)ms / repeat;
+    if (launches_per_exec) *launches_per_exec = c->launch_counter / repeat;
+    // restore the canonical jacobi slot assignment
+    for (int l = c->p->desc.min_level; l <= c->p->desc.max_level; ++l)
+        for (int i = 0; i < c->p->desc.n_fields; ++i)
+            if (c->lv[l].swapped[i]) {
+                bool cor_alias = c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].buf[EVO_BUF_SOL][i];
+                std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
+                if (cor_alias) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
+                c->lv[l].swapped[i] = false;
+            }
+    return EVO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // solve: the generated solver's outer loop
 __global__ void k_set_while_condition(cudaGraphConditionalHandle handle, const SolveState *st)

@@ -185,6 +185,11 @@ int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, double *hos
 int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, const double *host, size_t n_doubles);
 /* RES@finest = RHS - A*SOL and its L2 norm over inner nodes (gen_resNorm of the generated solver) */
 int evo_cycle_residual_norm(evo_cycle *c, double *norm);
+/* measurement hook (bench.py roofline): launch the kernels of ONE statement `repeat` times on the
+ * cycle's stream, bracketed by CUDA events; returns the average milliseconds per execution and the
+ * number of kernel launches one execution makes.  The reference's counterpart is the per-function
+ * timer output of the generated binary (printAllTimers, Helmholtz/...exa4:13-19).                 */
+int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, double *ms_per_exec, int64_t *launches_per_exec);
 
 /* -- solve = the generated solver's outer loop (a9) run `samples` times (a7: evaluate,
  *    exastencils.py:417-443): res0 = ||f - A u0||; repeat { cycle; res = ||f - A u|| } until

@@ -46,7 +46,8 @@ typedef struct Hier {
     double R[27], P[27];
     Level lv[EVO_MAX_LEVELS];
     void *init[2][EVO_MAX_FIELDS]; /* pristine SOL / RHS of the finest level */
-    void *scratch[8];              /* finest-level sized work arrays (jacobi slots, CG vectors) */
+    void *scratch[8];              /* work arrays (Richardson temporary, Krylov vectors), sized on demand */
+    size_t scratch_total[8];
     int cg_iterations_last;
     long cg_iterations_total;
 } Hier;
@@ -112,14 +113,15 @@ void *orc_create(const evo_problem_desc *d)
         Level *L = &H->lv[l];
         L->n = (1 << l) + 1;
         L->total = (size_t)L->n * L->n * (H->dim == 3 ? L->n : 1);
-        for (int b = 0; b < EVO_BUF_COUNT; ++b)
+        for (int b = 0; b < EVO_BUF_COUNT; ++b) {
+            if (b == EVO_BUF_APX && H->kind != EVO_PROBLEM_FAS) continue;
+            if (b == EVO_BUF_COR) continue; /* allocated on first use (ensure_level_buffers) */
             for (int i = 0; i < H->nf; ++i) L->buf[b][i] = calloc(L->total, esz);
-        for (int i = 0; i < H->nf; ++i) L->slot[i] = calloc(L->total, esz);
+        }
     }
     Level *F = &H->lv[H->max_level];
     for (int b = 0; b < 2; ++b)
         for (int i = 0; i < H->nf; ++i) H->init[b][i] = calloc(F->total, esz);
-    for (int s = 0; s < 8; ++s) H->scratch[s] = calloc(F->total * (size_t)H->nf, esz);
     return H;
 }
 
@@ -174,6 +176,7 @@ int orc_set_field(void *h, int level, int buf, int field, const double *host, si
         return EVO_ERR_INVALID;
     Level *L = &H->lv[level];
     if (n_doubles != L->total * (size_t)H->words) return EVO_ERR_INVALID;
+    if (!L->buf[buf][field]) L->buf[buf][field] = calloc(L->total, sizeof(double) * (size_t)H->words);
     memcpy(L->buf[buf][field], host, n_doubles * sizeof(double));
     if (level == H->max_level && (buf == EVO_BUF_SOL || buf == EVO_BUF_RHS))
         memcpy(H->init[buf][field], host, n_doubles * sizeof(double));
@@ -187,6 +190,7 @@ int orc_get_field(void *h, int level, int buf, int field, double *host, size_t n
         return EVO_ERR_INVALID;
     Level *L = &H->lv[level];
     if (n_doubles != L->total * (size_t)H->words) return EVO_ERR_INVALID;
+    if (!L->buf[buf][field]) return EVO_ERR_INVALID;
     memcpy(host, L->buf[buf][field], n_doubles * sizeof(double));
     return EVO_OK;
 }
@@ -198,11 +202,50 @@ int orc_reset(void *h)
     for (int l = H->min_level; l <= H->max_level; ++l)
         for (int b = 0; b < EVO_BUF_COUNT; ++b)
             for (int i = 0; i < H->nf; ++i) {
+                if (!H->lv[l].buf[b][i]) continue;
                 if (l == H->max_level && b < 2) memcpy(H->lv[l].buf[b][i], H->init[b][i], H->lv[l].total * esz);
                 else memset(H->lv[l].buf[b][i], 0, H->lv[l].total * esz);
             }
+    for (int l = H->min_level; l <= H->max_level; ++l)
+        for (int i = 0; i < H->nf; ++i)
+            if (H->lv[l].slot[i]) memcpy(H->lv[l].slot[i], H->lv[l].buf[EVO_BUF_SOL][i], H->lv[l].total * esz);
     H->cg_iterations_total = 0;
     return EVO_OK;
+}
+
+/* buffers that only some statements need are allocated when a statement first touches them */
+static void ensure_for_op(Hier *H, const evo_op *op)
+{
+    const size_t esz = sizeof(double) * (size_t)H->words;
+    Level *L = &H->lv[op->level];
+    int lv[2] = {op->level, op->level - 1};
+    for (int t = 0; t < 2; ++t) {
+        if (lv[t] < H->min_level) continue;
+        Level *Q = &H->lv[lv[t]];
+        for (int i = 0; i < H->nf; ++i) {
+            if ((op->dst == EVO_BUF_COR || op->src == EVO_BUF_COR) && !Q->buf[EVO_BUF_COR][i])
+                Q->buf[EVO_BUF_COR][i] = calloc(Q->total, esz);
+        }
+    }
+    if ((op->code == EVO_OP_SMOOTH && op->mode == EVO_SMOOTH_JACOBI) ||
+        (op->code == EVO_OP_COARSE_SOLVE && H->kind == EVO_PROBLEM_FAS))
+        for (int i = 0; i < H->nf; ++i)
+            if (!L->slot[i]) {
+                L->slot[i] = calloc(L->total, esz);
+                memcpy(L->slot[i], L->buf[EVO_BUF_SOL][i], L->total * esz);
+            }
+    if (op->code == EVO_OP_RICHARDSON && (!H->scratch[0] || H->scratch_total[0] < L->total)) {
+        free(H->scratch[0]);
+        H->scratch[0] = calloc(L->total, esz);
+        H->scratch_total[0] = L->total;
+    }
+    if (op->code == EVO_OP_COARSE_SOLVE)
+        for (int s = 2; s < 8; ++s)
+            if (!H->scratch[s] || H->scratch_total[s] < L->total * (size_t)H->nf) {
+                free(H->scratch[s]);
+                H->scratch[s] = calloc(L->total * (size_t)H->nf, esz);
+                H->scratch_total[s] = L->total * (size_t)H->nf;
+            }
 }
 
 /* ------------------------------------------------------------------ interpreter */
@@ -211,6 +254,7 @@ static int run_op(Hier *H, const evo_op *op)
     const int l = op->level;
     if (l < H->min_level || l > H->max_level) return EVO_ERR_INVALID;
     const int cplx = H->words == 2;
+    ensure_for_op(H, op);
     if (H->kind == EVO_PROBLEM_FAS) {
         int rc = fas_run_op(H, op);
         if (rc != 1) return rc; /* 1 = not a FAS-specific op, fall through */
