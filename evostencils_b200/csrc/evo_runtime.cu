@@ -230,10 +230,18 @@ extern "C" int evo_problem_set_field(evo_problem *p, int level, int buf, int fie
 
 // ------------------------------------------------------------------------------------------------
 // cycle: memory
+// pointwise RB-GS on a 3-D scalar real problem runs as the out-of-place streaming kernel
+static bool rb_stream_candidate(const evo_cycle *c, const evo_op &op)
+{
+    const evo_problem_desc &d = c->p->desc;
+    return op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_REDBLACK && op.kind == EVO_KIND_LINEAR && op.n_unknowns == 1 &&
+           d.dim == 3 && d.n_fields == 1 && d.scalar_words == 1 && c->p->geom[op.level].n >= 33;
+}
 static bool level_needs_slot(const evo_cycle *c, int level)
 {
     for (const evo_op &op : c->ops)
-        if (op.level == level && ((op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_JACOBI) || op.code == EVO_OP_RICHARDSON))
+        if (op.level == level && ((op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_JACOBI) || op.code == EVO_OP_RICHARDSON ||
+                                  rb_stream_candidate(c, op)))
             return true;
     return false;
 }
@@ -358,7 +366,22 @@ template <typename T, int DIM, int NF> struct Launch {
             if (written[i] && !has_own[i])
                 return fail(EVO_ERR_UNSUPPORTED, "local system without an unknown at the anchor node for field %d", i);
         auto rhs = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
-        const int reps = op.count > 1 ? op.count : 1;
+        int reps = op.count > 1 ? op.count : 1;
+        if (NU == 1 && op.mode == EVO_SMOOTH_REDBLACK && c->lv[l].slot[0] && star::rbgs_stream_applicable<T, DIM, NF>(g, c->sten[l])) {
+            // fused streaming kernel: up to 2 sweeps per pass, out of place into the [next] slot
+            while (reps > 0) {
+                const int k = reps >= 2 ? 2 : 1;
+                auto src = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), dst = fields_of<T>(c->lv[l].slot, NF);
+                if (!star::try_rbgs_stream<T, DIM, NF>(c->p->sm_count, g, c->sten[l], src, rhs, dst, op.omega, k, s)) break;
+                c->launch_counter++;
+                bool cor_alias = c->lv[l].buf[EVO_BUF_COR][0] == c->lv[l].buf[EVO_BUF_SOL][0];
+                std::swap(c->lv[l].buf[EVO_BUF_SOL][0], c->lv[l].slot[0]);
+                if (cor_alias) c->lv[l].buf[EVO_BUF_COR][0] = c->lv[l].buf[EVO_BUF_SOL][0];
+                c->lv[l].swapped[0] = !c->lv[l].swapped[0];
+                reps -= k;
+            }
+            if (reps == 0) { CU(cudaGetLastError()); return EVO_OK; }
+        }
         for (int rep = 0; rep < reps; ++rep) {
             if (op.mode == EVO_SMOOTH_JACOBI) {
                 // read the current slot, write the next slot, then `advance` (swap) the written fields
@@ -375,9 +398,10 @@ template <typename T, int DIM, int NF> struct Launch {
                 c->launch_counter++;
                 for (int i = 0; i < NF; ++i)
                     if (written[i]) {
+                        bool cor_alias = c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].buf[EVO_BUF_SOL][i];
                         std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
                         c->lv[l].swapped[i] = !c->lv[l].swapped[i];
-                        if (c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].slot[i]) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
+                        if (cor_alias) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
                     }
             } else if (op.mode == EVO_SMOOTH_REDBLACK) {
                 auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF);
@@ -621,7 +645,19 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
     CU(cudaSetDevice(p->desc.device));
     evo_cycle *c = new evo_cycle();
     c->p = p;
-    c->ops.assign(ops, ops + n_ops);
+    // consecutive identical `solve locally` statements become one op with a repeat count (the kernels
+    // fuse repeated sweeps; semantics are unchanged)
+    for (int t = 0; t < n_ops; ++t) {
+        evo_op op = ops[t];
+        if (op.code == EVO_OP_SMOOTH && op.count < 1) op.count = 1;
+        if (!c->ops.empty() && op.code == EVO_OP_SMOOTH && op.kind == EVO_KIND_LINEAR) {
+            evo_op &prev = c->ops.back();
+            evo_op a = prev, b = op;
+            a.count = b.count = 0;
+            if (prev.code == EVO_OP_SMOOTH && memcmp(&a, &b, sizeof(evo_op)) == 0) { prev.count += op.count; continue; }
+        }
+        c->ops.push_back(op);
+    }
     c->slab = nullptr;
     c->graph = nullptr;
     c->exec = nullptr;
