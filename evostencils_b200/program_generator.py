@@ -1,0 +1,398 @@
+"""Drop-in replacement for the evaluate path of the reference's ``ProgramGenerator``.
+
+Reference: evostencils/code_generation/exastencils.py:39 (class), :485 ``generate_and_evaluate``, :318
+``generate_cycle_function``, :586 ``generate_storage``, :445 ``initialize_code_generation``, :196
+``reinitialize``.  ``Optimizer`` (optimization/program.py:68-72) accepts an instance of this class as
+``program_generator`` unchanged: same attributes, same method names, same argument meaning, same
+sentinel behaviour (``(infinity,)*3`` on failure, early un-averaged return on divergence).
+
+What changes is what happens inside ``generate_and_evaluate``: instead of ExaSlang text -> Java code
+generator (twice) -> ``make`` -> running the binary ``evaluation_samples`` times -> parsing stdout, the
+tree is lowered to an op list and executed by the CUDA library (one CUDA-graph launch per sample).
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+import time
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import backend, exaslang, fitness, lowering, oplist as ol, problems
+from .problems import Problem
+
+JACOBI_COMPAT_MODES = ("intended", "exastencils_v1_1_noop")
+
+
+def _problem_from_paths(settings_path: Optional[str], knowledge_path: Optional[str], base_path: Optional[str]) -> Problem:
+    """Map the reference's configuration files to a problem descriptor.  Levels/dimension come from the
+    .knowledge file when it exists (same keys as parser.extract_knowledge_information, parser.py:114-125)."""
+    text = f"{settings_path or ''} {knowledge_path or ''}"
+    if "Helmholtz" in text:
+        prob: Problem = problems.Helmholtz2D()
+    elif "LinearElasticity" in text:
+        prob = problems.LinearElasticity2D()
+    elif "FAS" in text:
+        prob = problems.FAS2D()
+    elif "3D_FD_Poisson" in text:
+        prob = problems.Poisson3D()
+    elif "Poisson" in text:
+        prob = problems.Poisson2D()
+    else:
+        raise RuntimeError(f"no problem descriptor for settings '{settings_path}' / knowledge '{knowledge_path}'")
+    if knowledge_path and base_path and os.path.exists(os.path.join(base_path, knowledge_path)):
+        from .frontend import read_knowledge
+        dim, lo, hi = read_knowledge(os.path.join(base_path, knowledge_path))
+        if dim != prob.dim:
+            raise RuntimeError("dimensionality of the knowledge file does not match the problem")
+        prob = prob.with_levels(lo, hi)
+    return prob
+
+
+class B200ProgramGenerator:
+    def __init__(self, absolute_compiler_path: Optional[str] = None, base_path: Optional[str] = None,
+                 settings_path: Optional[str] = None, knowledge_path: Optional[str] = None,
+                 platform_path: Optional[str] = None, mpi_rank: int = 0, solution_equations=None,
+                 cycle_name: str = "gen_mgCycle", model_based_estimation: bool = False, evaluation_timeout=300,
+                 code_generation_timeout=300, c_compiler_timeout=120, solver_iteration_limit=None, *,
+                 problem: Optional[Problem] = None, device: Optional[int] = None,
+                 jacobi_compat: str = "intended", fuse: bool = True):
+        if jacobi_compat not in JACOBI_COMPAT_MODES:
+            raise ValueError(f"jacobi_compat must be one of {JACOBI_COMPAT_MODES}")
+        self._average_generation_time = 0          # written by Optimizer (program.py:850-851)
+        self._counter = 0
+        self.timeout_evaluate = evaluation_timeout
+        self.timeout_exastencils_compiler = code_generation_timeout
+        self.timeout_c_compiler = c_compiler_timeout
+        self._solver_iteration_limit = solver_iteration_limit
+        self._absolute_compiler_path = absolute_compiler_path
+        self._base_path = base_path
+        self._settings_path, self._knowledge_path, self._platform_path = settings_path, knowledge_path, platform_path
+        self._mpi_rank = mpi_rank
+        self._cycle_name = cycle_name
+        self._use_jacobi_prefix = not model_based_estimation      # exastencils.py:64-70
+        self._solution_equations = solution_equations
+        self.jacobi_compat = jacobi_compat
+        self.fuse = fuse
+        self._problem = problem if problem is not None else _problem_from_paths(settings_path, knowledge_path, base_path)
+        self._original_min_level, self._original_max_level = self._problem.min_level, self._problem.max_level
+        # the reference raises RuntimeError("Compiler not found. Aborting.") when its tool chain is missing
+        # (exastencils.py:104-108); ours is the CUDA library + a device.  No CPU fallback.
+        try:
+            lib = backend.load_library()
+            ndev = lib.evo_device_count()
+        except backend.BackendError as e:
+            raise RuntimeError(f"Compiler not found. Aborting. ({e})")
+        if ndev <= 0:
+            raise RuntimeError("Compiler not found. Aborting. (no CUDA device visible; the B200 backend has no CPU fallback)")
+        self._device = (mpi_rank % ndev) if device is None else device
+        self._compiler_available = True
+        self._device_problems: Dict[Tuple, backend.DeviceProblem] = {}
+        self._cycle_registry: Dict[int, dict] = {}
+        self._l2_cache = None
+        self.last_outcome = None
+        self.total_kernel_launches = 0
+
+    # ---- attributes read by Optimizer / scripts (scripts/optimize.py:60-68, program.py:116-124, :808) ----
+    @property
+    def uses_FAS(self):
+        return False
+
+    @property
+    def absolute_compiler_path(self):
+        return self._absolute_compiler_path
+
+    @property
+    def knowledge_path(self):
+        return self._knowledge_path
+
+    @property
+    def settings_path(self):
+        return self._settings_path
+
+    @property
+    def problem_name(self):
+        return self._problem.name
+
+    @property
+    def compiler_available(self):
+        return self._compiler_available
+
+    @property
+    def base_path(self):
+        return self._base_path
+
+    @property
+    def platform_path(self):
+        return self._platform_path
+
+    @property
+    def dimension(self):
+        return self._problem.dim
+
+    @property
+    def min_level(self):
+        return self._problem.min_level
+
+    @property
+    def max_level(self):
+        return self._problem.max_level
+
+    @property
+    def mpi_rank(self):
+        return self._mpi_rank
+
+    @property
+    def solution_equations(self):
+        return self._solution_equations
+
+    @property
+    def solver_iteration_limit(self):
+        return self._solver_iteration_limit
+
+    @property
+    def problem(self) -> Problem:
+        return self._problem
+
+    @property
+    def coarsening_factor(self):
+        return [tuple([2] * self.dimension) for _ in self._problem.fields]
+
+    def _l2(self):
+        """equations / operators / fields / finest_grid in the classes ``generate_primitive_set`` expects
+        (grammar/multigrid.py:15-71): the reference's own classes when the package is importable."""
+        key = (self._problem.min_level, self._problem.max_level, tuple(sorted(self._problem.parameters.items())))
+        if self._l2_cache is not None and self._l2_cache[0] == key:
+            return self._l2_cache[1]
+        p = self._problem
+        try:
+            import sympy
+            from evostencils.grammar import multigrid as mg      # needs DEAP (grammar/gp.py:3)
+            from evostencils.ir import base
+            from evostencils.stencils import constant
+            fields = [sympy.Symbol(f) for f in p.fields]
+            mk_op = lambda name, level, ent, typ: mg.OperatorInfo(name, level, constant.Stencil(ent, p.dim), typ)
+            types = (base.Operator, base.Restriction, base.Prolongation)
+            mk_eq = mg.EquationInfo
+            mk_grid = base.Grid
+        except Exception:
+            fields = [SimpleNamespace(name=f) for f in p.fields]
+            mk_op = lambda name, level, ent, typ: SimpleNamespace(name=name, level=level, operator_type=typ,
+                                                                  stencil=SimpleNamespace(entries=tuple(ent), dimension=p.dim))
+            types = ("Operator", "Restriction", "Prolongation")
+            mk_eq = lambda name, level, expr: SimpleNamespace(name=name, level=level, rhs_name=expr.split("==")[1].strip().split("@")[0],
+                                                              _associated_field=None)
+            mk_grid = lambda size, spacing, level: SimpleNamespace(size=size, spacing=spacing, level=level, dimension=len(size))
+        equations, operators = [], []
+        for level in range(p.min_level, p.max_level + 1):
+            table = p.operator(level)
+            for i, (eq, rhs) in enumerate(zip(p.equation_names, p.rhs_names)):
+                terms = []
+                for j, fld in enumerate(p.fields):
+                    ent = [(ol.stencil_offset(q, p.dim), complex(table[i, j, q]) if np.iscomplexobj(table) else float(table[i, j, q]))
+                           for q in range(ol.STENCIL_POINTS) if table[i, j, q] != 0]
+                    if not ent:
+                        continue
+                    name = f"A{i}{j}"
+                    operators.append(mk_op(name, level, ent, types[0]))
+                    terms.append(f"( {name}@{level} * {fld}@{level} )")
+                e = mk_eq(eq, level, " + ".join(terms) + f" == {rhs}@{level}")
+                e._associated_field = fields[i]
+                equations.append(e)
+            rw, pw = p.restrict_weights(), p.prolong_weights()
+            for fld in p.fields:
+                operators.append(mk_op(f"gen_restrictionForRes_{fld}", level,
+                                       [(ol.stencil_offset(q, p.dim), float(rw[q])) for q in range(27) if rw[q] != 0], types[1]))
+                operators.append(mk_op(f"gen_prolongationForSol_{fld}", level,
+                                       [(ol.stencil_offset(q, p.dim), float(pw[q])) for q in range(27) if pw[q] != 0], types[2]))
+        size = 2 ** p.max_level
+        finest = [mk_grid(tuple([size] * p.dim), tuple([1.0 / size] * p.dim), p.max_level) for _ in p.fields]
+        self._l2_cache = (key, (equations, operators, fields, finest))
+        return self._l2_cache[1]
+
+    @property
+    def equations(self):
+        return self._l2()[0]
+
+    @property
+    def operators(self):
+        return self._l2()[1]
+
+    @property
+    def fields(self):
+        return self._l2()[2]
+
+    @property
+    def finest_grid(self):
+        return self._l2()[3]
+
+    # ---- methods called by Optimizer -------------------------------------------------------------------
+    def generate_storage(self, min_level: int, max_level: int, finest_grids=None) -> list:
+        """Opaque per-level handles (the reference returns CycleStorage objects, exastencils.py:586-592;
+        callers only pass them back)."""
+        return [SimpleNamespace(level=l) for l in range(max_level, min_level - 1, -1)]
+
+    def _device_problem(self, min_level: int, max_level: int, problem: Optional[Problem] = None) -> backend.DeviceProblem:
+        p = (problem or self._problem).with_levels(min_level, max_level)
+        key = (min_level, max_level, tuple(sorted(p.parameters.items())))
+        if key not in self._device_problems:
+            if len(self._device_problems) >= 4:                 # keep HBM use bounded across generalisation steps
+                k0 = next(iter(self._device_problems))
+                self._device_problems.pop(k0).close()
+            self._device_problems[key] = backend.DeviceProblem(p, device=self._device)
+        return self._device_problems[key]
+
+    def initialize_code_generation(self, min_level: int, max_level: int):
+        """One-time set-up per level range (the reference runs the Java generator here, :445-466)."""
+        start = time.time()
+        self._device_problem(min_level, max_level)
+        if self._counter == 0:
+            self._counter += 1
+            self._average_generation_time += (time.time() - start - self._average_generation_time) / self._counter
+        return f"b200://{self.problem_name}/{min_level}-{max_level}"
+
+    def reinitialize(self, min_level, max_level, global_expressions=None):
+        """New level range / PDE parameters (generalisation step, program.py:110-146 -> exastencils.py:196-215)."""
+        import copy
+        p = copy.copy(self._problem).with_levels(min_level, max_level)
+        if global_expressions:
+            p.parameters = dict(p.parameters)
+            for k, v in global_expressions.items():
+                if k in p.parameters:
+                    p.parameters[k] = float(v)
+            if "k" in global_expressions and hasattr(p, "wave_number"):
+                p.wave_number = complex(float(global_expressions["k"]))
+        self._problem = p
+        self._l2_cache = None
+
+    def lower(self, expression, min_level: int, max_level: Optional[int] = None) -> ol.Program:
+        p = self._problem
+        prog = lowering.lower_cycle(expression, min_level, self.max_level if max_level is None else max_level,
+                                    p.n_fields, p.dim, use_jacobi_prefix=self._use_jacobi_prefix,
+                                    cgs_max_iters=p.settings.cgs_max_iters, cgs_tol=p.settings.cgs_tol,
+                                    cycle_registry=self._cycle_registry,
+                                    default_restrict=p.restrict_weights(), default_prolong=p.prolong_weights())
+        return prog
+
+    def _finalise(self, prog: ol.Program) -> ol.Program:
+        prog = lowering.apply_jacobi_compat(prog, self.jacobi_compat)
+        if self.fuse:
+            prog = lowering.optimise(prog)
+        return prog
+
+    def generate_cycle_function(self, expression, storages, min_level: int, level: int, max_level: int,
+                                use_global_weights: bool = False) -> str:
+        prog = self.lower(expression, min_level, max_level)
+        # a later run on finer levels may call this cycle as its coarse-grid solver (multi-run mode,
+        # exastencils.py:893-896): remember the statements under the level it was generated for
+        self._cycle_registry[level] = {"ops": list(prog.ops), "operators": dict(prog.operators)}
+        return exaslang.program_to_exaslang(prog, self._problem.fields, self._problem.rhs_names, level, self._cycle_name)
+
+    def _apply_sentinels(self, time_ms, cf, iters, infinity):
+        """evaluate(), exastencils.py:435-443, for identical samples (cf / iterations are deterministic)."""
+        if iters >= infinity or cf > 1:
+            return time_ms, cf, iters
+        if math.isinf(cf) or math.isnan(cf):
+            return infinity, infinity, infinity
+        return time_ms, cf, iters
+
+    def _evaluate_program(self, prog: ol.Program, min_level, problem, infinity, evaluation_samples):
+        dev = self._device_problem(min_level, self.max_level, problem)
+        s = dev.problem.settings
+        cyc = dev.build(prog)
+        try:
+            out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
+        finally:
+            cyc.close()
+        self.last_outcome = out
+        self.total_kernel_launches += out.kernel_launches * max(1, int(evaluation_samples))
+        t, cf, its = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters, infinity,
+                                                  self._solver_iteration_limit)
+        return self._apply_sentinels(t, cf, its, infinity)
+
+    def generate_and_evaluate(self, expression, storages, min_level: int, max_level: int, solver_program: str,
+                              infinity=1e100, evaluation_samples=3, global_variable_values=None):
+        if global_variable_values is None:
+            global_variable_values = {}
+        start = time.time()
+        try:
+            prog = self._finalise(self.lower(expression, min_level))
+        except Exception:
+            return infinity, infinity, infinity                 # "Code generation failed" (:499-510)
+        self._counter += 1
+        self._average_generation_time += (time.time() - start - self._average_generation_time) / self._counter
+        mapping = dict(global_variable_values)
+        n = 3 if "k" in mapping else 1                          # :518-521
+        avg = [0.0, 0.0, 0.0]
+        for _ in range(n):
+            problem = None
+            if mapping:
+                import copy
+                problem = copy.copy(self._problem)
+                problem.parameters = dict(problem.parameters)
+                for k, v in mapping.items():
+                    if k in problem.parameters:
+                        problem.parameters[k] = float(v)
+                if "k" in mapping:
+                    problem.wave_number = complex(float(mapping["k"]))
+            try:
+                t, cf, its = self._evaluate_program(prog, min_level, problem, infinity, evaluation_samples)
+            except backend.BackendError:
+                t, cf, its = infinity, infinity, infinity
+            avg[0] += t; avg[1] += cf; avg[2] += its
+            if its >= infinity or cf > 1:                       # :529-530
+                return tuple(avg)
+            if n > 1:
+                mapping["k"] *= 2
+        return avg[0] / n, avg[1] / n, avg[2] / n
+
+    # ---- beyond the reference surface: a whole generation in one call -----------------------------------
+    def evaluate_population(self, expressions: Sequence, min_level: Optional[int] = None, infinity=1e100,
+                            evaluation_samples: int = 1, max_in_flight: int = 64, programs: Optional[Sequence[ol.Program]] = None):
+        """Fitness tuples of many individuals; up to ``max_in_flight`` solves run concurrently on the GPU,
+        one CUDA stream and one device-side solver loop each (the reference evaluates one after the other,
+        program.py:491).  Returns (list of tuples, device milliseconds)."""
+        min_level = self.min_level if min_level is None else min_level
+        dev = self._device_problem(min_level, self.max_level)
+        s = dev.problem.settings
+        results: List[Tuple[float, float, float]] = []
+        total_ms = 0.0
+        progs: List[Optional[ol.Program]] = []
+        if programs is not None:
+            progs = [self._finalise(p) for p in programs]
+        else:
+            for e in expressions:
+                try:
+                    progs.append(self._finalise(self.lower(e, min_level)))
+                except Exception:
+                    progs.append(None)
+        for a in range(0, len(progs), max_in_flight):
+            chunk = progs[a:a + max_in_flight]
+            cycles = [dev.build(p) if p is not None else None for p in chunk]
+            live = [c for c in cycles if c is not None]
+            outs, ms = dev.batch_solve(live, s.tol, s.max_iters, samples=max(1, evaluation_samples)) if live else ([], 0.0)
+            total_ms += ms
+            it = iter(outs)
+            for c in cycles:
+                if c is None:
+                    results.append((infinity, infinity, infinity))
+                    continue
+                o = next(it)
+                self.total_kernel_launches += o.kernel_launches * max(1, evaluation_samples)
+                t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
+                                                          self._solver_iteration_limit)
+                results.append(self._apply_sentinels(t, cf, its, infinity))
+                c.close()
+        return results, total_ms
+
+    def close(self):
+        for d in self._device_problems.values():
+            d.close()
+        self._device_problems.clear()
+
+
+# the name a user of the reference would look for
+ProgramGenerator = B200ProgramGenerator

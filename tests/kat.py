@@ -38,3 +38,21 @@ def tutorial_ops():
 def drop_jacobi(ops):
     """jacobi_compat = 'exastencils_v1_1_noop' (SURVEY.md 0.5): `with jacobi` statements do nothing."""
     return [o for o in ops if not (o.code == ol.OP_SMOOTH and o.mode == ol.MODE_JACOBI)]
+
+
+# Grammar string that lowers to the cycle above (reconstructed from the printed ExaSlang; weight index i
+# means omega = linspace(0.1, 1.9, 37)[i], grammar/multigrid.py:428): the whole stack
+# string -> tree -> lowering -> kernels can then be checked against notebooks/tutorial.ipynb:3373.
+TUTORIAL_INDIVIDUAL = (
+    "collective_jacobi_0(28, red_black, residual_0("
+    "collective_jacobi_0(31, single, residual_0("
+    "update_with_coarse_grid_correction_0(18, P_1, "
+    "collective_jacobi_1(13, single, residual_1("
+    "update_with_coarse_grid_correction_1(33, P_2, "
+    "update_with_coarse_grid_correction_2(31, P_3, "
+    "correct_with_coarse_grid_solver_3(0, P_4, CGS_4, R_3, residual_3("
+    "collective_block_jacobi_3(0, ((1, 6),), residual_3("
+    "collective_block_jacobi_3(5, ((3, 2),), "
+    "coarsening_2(A_3, zero_3, R_2, coarsening_1(A_2, zero_2, R_1, coarsening_0(A_1, zero_1, R_0, "
+    "residual_0(u_and_f))))))))))))))))))"
+)
