@@ -5,7 +5,7 @@
 //
 // Arithmetic contract shared with the CPU oracle (oracle/mg_ops.inc):
 //   A*u at a node   = sum_j sum_q c[i][j][q] * u_j[node + off_q], q ascending, acc = acc + c*u
-//   pointwise solve = s = sum of the non-unknown terms (same order); x = (f - s) / a; u += w (x - u)
+//   pointwise solve = s = sum of the non-unknown terms (same order); x = (f - s) * (1/a); u += w (x - u)
 #pragma once
 #include "evo_common.cuh"
 
@@ -282,7 +282,7 @@ __device__ __forceinline__ void local_solve(const Geom &g, const OpSten &st, con
         }
         b[a] = rhs.p[fi][uidx[a]] - s;
     }
-    if (NU == 1) b[0] = b[0] / M[0][0];
+    if (NU == 1) b[0] = b[0] * (T(1.0) / M[0][0]);  // pointwise: multiply by the reciprocal diagonal
     else solve_dense<T, NU>(M, b);
 #pragma unroll
     for (int a = 0; a < NU; ++a) {

@@ -112,18 +112,122 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // k consecutive pointwise RB-GS sweeps (S = 2k half-sweeps) in one pass, 3-D 7-point.
 constexpr int RB_TX = 64, RB_TY = 16, RB_NT = 256;
 
+// compile-time geometry of pipeline stage s of S: it covers the tile plus a halo of E nodes
+template <int S, int s> struct StageCfg {
+    static constexpr int E = S - 1 - s;
+    static constexpr int W = RB_TX + 2 * E, ROWS = RB_TY + 2 * E, NPX = W / 2;
+    static constexpr int ITEMS = NPX * ROWS, ROUNDS = (ITEMS + RB_NT - 1) / RB_NT;
+};
+template <int S, int s> __host__ __device__ constexpr int stage_base()
+{
+    if constexpr (s == 0) return 0;
+    else return stage_base<S, s - 1>() + StageCfg<S, s - 1>::ROUNDS;
+}
+template <int S> struct RbCfg {
+    static constexpr int H = S;
+    // TMA needs a 16-byte aligned start address: with fp64 the x start coordinate must be even, so the
+    // window starts one node further left (tiles start at odd x = 1 + 64*bx) and is 2 nodes wider
+    static constexpr int LX = RB_TX + 2 * H + 2, LY = RB_TY + 2 * H;
+    static constexpr int NP = S + 3;  // ring: planes t-S .. t+2 (one plane of TMA prefetch)
+    static constexpr int PSTRIDE = (LX * LY + 15) / 16 * 16;  // slot stride in doubles (128-byte aligned)
+    static constexpr int TOT = stage_base<S, S>();             // work items per thread over all stages
+};
+
+// per-thread work items: fixed (row, x-pair) positions for every stage, set up once before the z loop
+template <int S> struct RbItems {
+    int loff[RbCfg<S>::TOT];   // shared-memory offset of the pair's left node
+    int goff[RbCfg<S>::TOT];   // in-plane global offset of the pair's left node
+    unsigned v0, v1, par;      // bit i: item i valid when the active node is the left / right one; parity bit
+};
+
+template <int S, int s>
+__device__ __forceinline__ void rb_setup(RbItems<S> &it, int tid, int x0, int y0, int xb, int yb, const Geom &g)
+{
+    using C = StageCfg<S, s>;
+    constexpr int base = stage_base<S, s>();
+#pragma unroll
+    for (int j = 0; j < C::ROUNDS; ++j) {
+        const int i = tid + RB_NT * j;
+        const int ry = i / C::NPX, kx = i - ry * C::NPX;
+        const int y = y0 - C::E + ry, xw = x0 - C::E + 2 * kx;
+        const bool ok = i < C::ITEMS && y >= 1 && y <= g.n - 2;
+        it.loff[base + j] = (y - yb) * RbCfg<S>::LX + (xw - xb);
+        it.goff[base + j] = y * g.pitch + xw;
+        if (ok && xw >= 1 && xw <= g.n - 2) it.v0 |= 1u << (base + j);
+        if (ok && xw + 1 >= 1 && xw + 1 <= g.n - 2) it.v1 |= 1u << (base + j);
+        if ((xw + y + (s & 1)) & 1) it.par |= 1u << (base + j);   // parity of the left node for z even
+    }
+    if constexpr (s + 1 < S) rb_setup<S, s + 1>(it, tid, x0, y0, xb, yb, g);
+}
+
+// f values of the active nodes of every stage for the step whose stage-0 plane is t
+template <int S, int s>
+__device__ __forceinline__ void rb_load_f(const RbItems<S> &it, double (&fv)[RbCfg<S>::TOT], const double *__restrict__ f,
+                                          const Geom &g, int t, int za, int zb)
+{
+    using C = StageCfg<S, s>;
+    constexpr int base = stage_base<S, s>();
+    const int z = t - s;
+    if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
+        const double *fp = f + (long long)z * g.plane;
+#pragma unroll
+        for (int j = 0; j < C::ROUNDS; ++j) {
+            const int idx = base + j;
+            // active node = left node iff its colour (x+y+z+c) is even
+            const unsigned p = ((it.par >> idx) ^ (unsigned)z) & 1u;
+            const bool ok = ((p ? it.v1 : it.v0) >> idx) & 1u;
+            if (ok) fv[idx] = __ldg(fp + it.goff[idx] + p);
+        }
+    }
+    if constexpr (s + 1 < S) rb_load_f<S, s + 1>(it, fv, f, g, t, za, zb);
+}
+
+template <int S, int s>
+__device__ __forceinline__ void rb_stages(const RbItems<S> &it, const double (&fv)[RbCfg<S>::TOT], double *ring, int pbase,
+                                          const Geom &g, const Star7 &c, double inv_c, double omega, int t, int za, int zb)
+{
+    using C = StageCfg<S, s>;
+    using R = RbCfg<S>;
+    constexpr int base = stage_base<S, s>();
+    const int z = t - s;
+    if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
+        double *pc = ring + (size_t)((z - pbase) % R::NP) * R::PSTRIDE;
+        const double *pm = ring + (size_t)((z - 1 - pbase) % R::NP) * R::PSTRIDE;
+        const double *pp = ring + (size_t)((z + 1 - pbase) % R::NP) * R::PSTRIDE;
+#pragma unroll
+        for (int j = 0; j < C::ROUNDS; ++j) {
+            const int idx = base + j;
+            const unsigned p = ((it.par >> idx) ^ (unsigned)z) & 1u;
+            const bool ok = ((p ? it.v1 : it.v0) >> idx) & 1u;
+            if (ok) {
+                const int li = it.loff[idx] + (int)p;
+                double sum = 0.0;
+                sum = sum + c.zm * pm[li];
+                sum = sum + c.ym * pc[li - R::LX];
+                sum = sum + c.xm * pc[li - 1];
+                sum = sum + c.xp * pc[li + 1];
+                sum = sum + c.yp * pc[li + R::LX];
+                sum = sum + c.zp * pp[li];
+                const double xs = (fv[idx] - sum) * inv_c;
+                const double old = pc[li];
+                pc[li] = old + omega * (xs - old);
+            }
+        }
+    }
+    __syncthreads();
+    if constexpr (s + 1 < S) rb_stages<S, s + 1>(it, fv, ring, pbase, g, c, inv_c, omega, t, za, zb);
+}
+
 template <int S>
 __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ CUtensorMap umap,
                                                         const double *__restrict__ f, double *__restrict__ uout,
-                                                        const Geom g, const Star7 c, const double omega, const int tz)
+                                                        const Geom g, const Star7 c, const double inv_c,
+                                                        const double omega, const int tz)
 {
-    constexpr int H = S;                 // load halo
-    // TMA needs a 16-byte aligned start address: with fp64 the x start coordinate must be even, so the
-    // window starts one node further left (tiles start at odd x = 1 + 64*bx) and is 2 nodes wider
-    constexpr int LX = RB_TX + 2 * H + 2, LY = RB_TY + 2 * H;
-    constexpr int NP = S + 3;            // ring: planes t-S .. t+2 (one plane of TMA prefetch)
+    using R = RbCfg<S>;
+    constexpr int H = R::H, LX = R::LX, LY = R::LY, NP = R::NP, PSTRIDE = R::PSTRIDE, TOT = R::TOT;
     constexpr uint32_t PLANE_BYTES = LX * LY * 8;
-    constexpr int PSTRIDE = (LX * LY + 15) / 16 * 16;  // slot stride in doubles (128-byte aligned slots)
+    static_assert(TOT <= 32, "validity bit masks are 32 bits wide");
     extern __shared__ __align__(128) double ring[];
     __shared__ __align__(8) uint64_t bars[NP];
 
@@ -131,13 +235,16 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
     const int x0 = 1 + blockIdx.x * RB_TX, y0 = 1 + blockIdx.y * RB_TY;
     const int za = 1 + blockIdx.z * tz, zb = min(za + tz - 1, n - 2);
     const int xb = x0 - H - 1, yb = y0 - H;  // global coordinates of local (0, 0); xb is even
-    const int pbase = za - H;            // first plane ever loaded (may be < 0: zero filled, never used)
+    const int pbase = za - H;                // first plane ever loaded (may be < 0: zero filled, never used)
     const int tid = threadIdx.x;
 
     if (tid == 0) {
         for (int i = 0; i < NP; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
+    RbItems<S> it;
+    it.v0 = it.v1 = it.par = 0u;
+    rb_setup<S, 0>(it, tid, x0, y0, xb, yb, g);
     __syncthreads();
 
     auto slot_of = [&](int p) { return (p - pbase) % NP; };
@@ -154,59 +261,37 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
     if (tid == 0) {
         for (int p = pbase; p <= min(t0 + 1, pmax); ++p) issue(p);
     }
+    double fcur[TOT], fnext[TOT];
+#pragma unroll
+    for (int i = 0; i < TOT; ++i) { fcur[i] = 0.0; fnext[i] = 0.0; }
+    rb_load_f<S, 0>(it, fcur, f, g, t0, za, zb);
     for (int p = pbase; p <= min(t0, pmax); ++p) wait_plane(p);
 
     for (int t = t0; t <= t1; ++t) {
+        // right-hand sides of the next step: issued now, consumed one step later (latency hidden)
+        if (t < t1) rb_load_f<S, 0>(it, fnext, f, g, t + 1, za, zb);
         if (t + 1 <= pmax) wait_plane(t + 1);
         if (tid == 0 && t + 2 <= pmax) {
-            fence_proxy_async();         // generic-proxy accesses of the recycled slot are complete (barrier below)
+            fence_proxy_async();         // generic-proxy accesses of the recycled slot completed before the last barrier
             issue(t + 2);
         }
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int z = t - s;
-            const int e = S - 1 - s;     // halo this stage still has to cover
-            if (z >= max(za - e, 1) && z <= min(zb + e, n - 2)) {
-                const int xlo = max(x0 - e, 1), xhi = min(x0 + RB_TX - 1 + e, n - 2);
-                const int ylo = max(y0 - e, 1), yhi = min(y0 + RB_TY - 1 + e, n - 2);
-                const int color = s & 1;
-                const int npx = ((xhi - xlo) >> 1) + 1, nrow = yhi - ylo + 1;
-                double *pc = ring + (size_t)slot_of(z) * PSTRIDE;
-                const double *pm = ring + (size_t)slot_of(z - 1) * PSTRIDE;
-                const double *pp = ring + (size_t)slot_of(z + 1) * PSTRIDE;
-                for (int i = tid; i < npx * nrow; i += RB_NT) {
-                    const int ry = i / npx, k = i - ry * npx;
-                    const int y = ylo + ry;
-                    const int x = xlo + ((xlo + y + z + color) & 1) + 2 * k;
-                    if (x > xhi) continue;
-                    const int li = (y - yb) * LX + (x - xb);
-                    const double fv = __ldg(f + node_index(g, x, y, z));
-                    double sum = 0.0;
-                    sum = sum + c.zm * pm[li];
-                    sum = sum + c.ym * pc[li - LX];
-                    sum = sum + c.xm * pc[li - 1];
-                    sum = sum + c.xp * pc[li + 1];
-                    sum = sum + c.yp * pc[li + LX];
-                    sum = sum + c.zp * pp[li];
-                    const double xs = (fv - sum) / c.c;
-                    const double old = pc[li];
-                    pc[li] = old + omega * (xs - old);
-                }
-            }
-            __syncthreads();
-        }
+        rb_stages<S, 0>(it, fcur, ring, pbase, g, c, inv_c, omega, t, za, zb);
         const int zf = t - (S - 1);
         if (zf >= za && zf <= zb) {
             const double *pc = ring + (size_t)slot_of(zf) * PSTRIDE;
             const int xhi = min(x0 + RB_TX - 1, n - 2), yhi = min(y0 + RB_TY - 1, n - 2);
+            double *op = uout + (long long)zf * g.plane;
+#pragma unroll
             for (int i = tid; i < RB_TX * RB_TY; i += RB_NT) {
                 const int ry = i / RB_TX, rx = i - ry * RB_TX;
                 const int x = x0 + rx, y = y0 + ry;
-                if (x <= xhi && y <= yhi) uout[node_index(g, x, y, zf)] = pc[(y - yb) * LX + (x - xb)];
+                if (x <= xhi && y <= yhi) op[y * g.pitch + x] = pc[(y - yb) * LX + (x - xb)];
             }
         }
         // no barrier needed here: the slot the next step's TMA recycles (plane t-S) was last read by stage
         // S-1 above, i.e. before that stage's barrier; the store loop reads a different slot
+#pragma unroll
+        for (int i = 0; i < TOT; ++i) fcur[i] = fnext[i];
     }
 }
 
@@ -214,23 +299,31 @@ template <int S>
 static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout,
                                double omega, cudaStream_t s)
 {
-    constexpr int H = S, LX = RB_TX + 2 * H + 2, LY = RB_TY + 2 * H, NP = S + 3;
-    constexpr int PSTRIDE = (LX * LY + 15) / 16 * 16;
+    using R = RbCfg<S>;
     CUtensorMap map;
-    if (!make_plane_map(&map, g, u, LX, LY)) return false;
-    const size_t smem = (size_t)NP * PSTRIDE * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!make_plane_map(&map, g, u, R::LX, R::LY)) return false;
+    const size_t smem = (size_t)R::NP * R::PSTRIDE * 8;
+    static int occ = 0;
+    if (occ == 0) {
         if (cudaFuncSetAttribute(k3_rbgs_stream<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        attr_set = true;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_stream<S>, RB_NT, smem) != cudaSuccess || occ < 1) occ = 1;
     }
     const int inner = g.n - 2;
     const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + RB_TY - 1) / RB_TY;
-    // z slabs: enough CTAs for ~4 per SM, but slabs of at least 32 planes (pipeline fill = S-1 planes)
-    int slabs = std::max(1, std::min(inner / 32, (4 * sm_count + tx * ty - 1) / (tx * ty)));
-    const int tz = (inner + slabs - 1) / slabs;
-    slabs = (inner + tz - 1) / tz;
-    k3_rbgs_stream<S><<<dim3(tx, ty, slabs), RB_NT, smem, s>>>(map, f, uout, g, c, omega, tz);
+    // z slabs: minimise (waves) x (planes per slab + pipeline fill) over 1..16 slabs
+    const long long slots = (long long)occ * sm_count;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int slabs = 1; slabs <= 16 && slabs * 8 <= inner; ++slabs) {
+        const int tzc = (inner + slabs - 1) / slabs;
+        const long long ctas = (long long)tx * ty * ((inner + tzc - 1) / tzc);
+        const double waves = (double)((ctas + slots - 1) / slots);
+        const double cost = waves * (tzc + 2 * S + 2);
+        if (cost < best_cost) { best_cost = cost; best = slabs; }
+    }
+    const int tz = (inner + best - 1) / best;
+    const int slabs = (inner + tz - 1) / tz;
+    k3_rbgs_stream<S><<<dim3(tx, ty, slabs), RB_NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
     return cudaGetLastError() == cudaSuccess;
 }
 
@@ -262,11 +355,140 @@ static bool rbgs_stream_applicable(const Geom &g, const OpSten &st)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int DIM, int NF>
-static bool try_residual(int, const Geom &, const OpSten &, Fields<T>, Fields<T>, Fields<T>, cudaStream_t)
+// 3-D residual r = f - A u, 7-point star, one warp per row (lane-strided over x).  A CTA of 8 warps
+// takes 8 consecutive rows of one plane so that the y-neighbour rows hit L1.  With NORM the squared
+// residual is reduced per row in the canonical order (lane (x-1) mod 32 accumulates ascending x, then
+// the xor butterfly) and written to rows[]; with !STORE the residual itself is never written
+// (16 B/DOF: the residual that only feeds the solver's convergence test).
+template <bool STORE, bool NORM>
+__global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star7 c, const double *__restrict__ u,
+                                                        const double *__restrict__ f, double *__restrict__ r,
+                                                        double *__restrict__ rows)
 {
-    return false;
+    const int ni = g.n - 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = 1 + blockIdx.x * 8 + warp, z = 1 + blockIdx.y;
+    if (y > ni) return;
+    const long long base = (long long)z * g.plane + (long long)y * g.pitch;
+    const double *uc = u + base, *fc = f + base;
+    const double *uym = uc - g.pitch, *uyp = uc + g.pitch, *uzm = uc - g.plane, *uzp = uc + g.plane;
+    double acc = 0.0;
+    for (int x = 1 + lane; x <= ni; x += 32) {
+        double sum = 0.0;
+        sum = sum + c.zm * uzm[x];
+        sum = sum + c.ym * uym[x];
+        sum = sum + c.xm * uc[x - 1];
+        sum = sum + c.c * uc[x];
+        sum = sum + c.xp * uc[x + 1];
+        sum = sum + c.yp * uyp[x];
+        sum = sum + c.zp * uzp[x];
+        const double rv = fc[x] - sum;
+        if (STORE) r[base + x] = rv;
+        if (NORM) acc = acc + rv * rv;
+    }
+    if (NORM) {
+        acc = warp_butterfly(acc);
+        if (lane == 0) rows[(long long)(z - 1) * ni + (y - 1)] = acc;
+    }
 }
+
+// 3-D trilinear prolongation + correction u += w * P e, one thread per coarse cell: the 8 coarse corner
+// values give the 8 fine nodes (2X..2X+1, 2Y..2Y+1, 2Z..2Z+1); fine rows are updated with coalesced
+// 16-byte read-modify-writes.  Per fine node the terms are added in ascending stencil-table order of
+// the offsets o with x+o even (the order of the generic kernel and of the oracle).
+struct DenseW { double w[27]; };
+
+template <int PX, int PY, int PZ>
+__device__ __forceinline__ double prolong_node(const DenseW &P, const double (&e)[2][2][2])
+{
+    // node parity (PX,PY,PZ): an even coordinate takes o = 0 from corner index 0, an odd one o = -1 (corner 0)
+    // then o = +1 (corner 1)
+    double acc = 0.0;
+#pragma unroll
+    for (int oz = -1; oz <= 1; ++oz) {
+        if ((PZ == 0) != (oz == 0)) continue;
+#pragma unroll
+        for (int oy = -1; oy <= 1; ++oy) {
+            if ((PY == 0) != (oy == 0)) continue;
+#pragma unroll
+            for (int ox = -1; ox <= 1; ++ox) {
+                if ((PX == 0) != (ox == 0)) continue;
+                acc = acc + P.w[(oz + 1) * 9 + (oy + 1) * 3 + (ox + 1)] * e[oz > 0][oy > 0][ox > 0];
+            }
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(128) k3_prolong_add(const Geom gf, const Geom gc, const DenseW P,
+                                                      const double *__restrict__ ec, double *__restrict__ u,
+                                                      const double weight)
+{
+    const int X = blockIdx.x * 128 + threadIdx.x, Y = blockIdx.y, Z = blockIdx.z;
+    if (X > gc.n - 2) return;
+    double e[2][2][2];
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const double *row = ec + (long long)(Z + dz) * gc.plane + (long long)(Y + dy) * gc.pitch + X;
+            e[dz][dy][0] = row[0];
+            e[dz][dy][1] = row[1];
+        }
+    const int n2 = gf.n - 2;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+        const int z = 2 * Z + dz;
+        if (z < 1 || z > n2) continue;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int y = 2 * Y + dy;
+            if (y < 1 || y > n2) continue;
+            double2 *up = reinterpret_cast<double2 *>(u + (long long)z * gf.plane + (long long)y * gf.pitch + 2 * X);
+            double2 v = *up;
+            double p0, p1;
+            if (dz == 0 && dy == 0) { p0 = prolong_node<0, 0, 0>(P, e); p1 = prolong_node<1, 0, 0>(P, e); }
+            else if (dz == 0 && dy == 1) { p0 = prolong_node<0, 1, 0>(P, e); p1 = prolong_node<1, 1, 0>(P, e); }
+            else if (dz == 1 && dy == 0) { p0 = prolong_node<0, 0, 1>(P, e); p1 = prolong_node<1, 0, 1>(P, e); }
+            else { p0 = prolong_node<0, 1, 1>(P, e); p1 = prolong_node<1, 1, 1>(P, e); }
+            if (X > 0) v.x = v.x + weight * p0;   // fine x = 0 is the boundary layer
+            v.y = v.y + weight * p1;              // fine x = 2X+1 <= n-2 always
+            *up = v;
+        }
+    }
+}
+
+template <typename T, int DIM, int NF>
+static bool try_residual(int, const Geom &g, const OpSten &st, Fields<T> u, Fields<T> f, Fields<T> r, cudaStream_t s)
+{
+    if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
+        Star7 c;
+        if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
+        const int ni = g.n - 2;
+        k3_residual_rows<true, false><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], nullptr);
+        return cudaGetLastError() == cudaSuccess;
+    } else {
+        return false;
+    }
+}
+
+// residual + canonical row sums of |r|^2 (rows[(z-1)*ni + (y-1)]); store = also write the residual field
+template <typename T, int DIM, int NF>
+static bool try_residual_norm(const Geom &g, const OpSten &st, Fields<T> u, Fields<T> f, Fields<T> r, double *rows,
+                              bool store, cudaStream_t s)
+{
+    if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
+        Star7 c;
+        if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
+        const int ni = g.n - 2;
+        if (store) k3_residual_rows<true, true><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
+        else k3_residual_rows<false, true><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
+        return cudaGetLastError() == cudaSuccess;
+    } else {
+        return false;
+    }
+}
+
 template <typename T, int DIM, int NF>
 static bool try_smooth_point(int, const Geom &, const OpSten &, const SmoothParams &, Fields<T>, Fields<T>, Fields<T>,
                              cudaStream_t)
@@ -280,9 +502,20 @@ static bool try_residual_restrict(int, const Geom &, const Geom &, const OpSten 
     return false;
 }
 template <typename T, int DIM, int NF>
-static bool try_prolong_add(int, const Geom &, const Geom &, const TransferW &, Fields<T>, Fields<T>, double, cudaStream_t)
+static bool try_prolong_add(int, const Geom &gf, const Geom &gc, const TransferW &P, Fields<T> src, Fields<T> dst, double weight,
+                            cudaStream_t s)
 {
-    return false;
+    if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
+        if (gf.n < 33) return false;
+        DenseW W;
+        for (int i = 0; i < 27; ++i) W.w[i] = 0.0;
+        for (int q = 0; q < P.nnz; ++q) W.w[(P.oz[q] + 1) * 9 + (P.oy[q] + 1) * 3 + (P.ox[q] + 1)] = P.w[q];
+        const int cells = gc.n - 1;
+        k3_prolong_add<<<dim3((cells + 127) / 128, cells, cells), 128, 0, s>>>(gf, gc, W, src.p[0], dst.p[0], weight);
+        return cudaGetLastError() == cudaSuccess;
+    } else {
+        return false;
+    }
 }
 
 }  // namespace star

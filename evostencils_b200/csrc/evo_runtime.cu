@@ -117,6 +117,8 @@ struct evo_cycle {
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
     bool use_while_graph;
+    bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
+                             // (convergence test) need not be stored
 };
 
 template <typename T> static Fields<T> fields_of(void *const *p, int nf)
@@ -331,11 +333,19 @@ template <typename T, int DIM, int NF> struct Launch {
         const Geom &g = c->p->geom[l];
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              r = fields_of<T>(c->lv[l].buf[EVO_BUF_RES], NF);
+        const int ni = g.n - 2;
+        if (norm && star::try_residual_norm<T, DIM, NF>(g, c->sten[l], u, f, r, c->d_partials, !c->res_dead_on_entry, s)) {
+            // residual and canonical row sums in one pass; the field itself is only stored if a later
+            // statement may read it
+            k_reduce_rows<DIM><<<1, 1024, 0, s>>>(c->d_partials, NF, ni, c->d_state);
+            c->launch_counter += 2;
+            CU(cudaGetLastError());
+            return EVO_OK;
+        }
         if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s))
             k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
         c->launch_counter++;
         if (norm) {
-            const int ni = g.n - 2;
             const long long nrows = (long long)ni * (DIM == 3 ? ni : 1);
             k_row_sumsq<T, DIM, NF><<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
             k_reduce_rows<DIM><<<1, 1024, 0, s>>>(c->d_partials, NF, ni, c->d_state);
@@ -579,8 +589,11 @@ static int dispatch_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
     return d.n_fields == 1 ? enqueue_op<double, 3, 1>(c, op, s) : enqueue_op<double, 3, 2>(c, op, s);
 }
 
-static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s)
+static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store = false)
 {
+    const bool saved_dead = c->res_dead_on_entry;
+    if (force_store) c->res_dead_on_entry = false;
+    struct Restore { evo_cycle *c; bool v; ~Restore() { c->res_dead_on_entry = v; } } restore{c, saved_dead};
     const evo_problem_desc &d = c->p->desc;
     const int l = d.max_level;
     if (d.scalar_words == 2) EV((Launch<cplx, 2, 1>::residual(c, l, true, s)));
@@ -689,6 +702,18 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
             }
         c->has_sten[l] = true;
     }
+    // is RES@finest written before it is read by the cycle's statements?
+    c->res_dead_on_entry = true;
+    for (const evo_op &op : c->ops) {
+        const int hi = p->desc.max_level;
+        bool reads = ((op.code == EVO_OP_RESTRICT || op.code == EVO_OP_COPY) && op.level == hi && op.src == EVO_BUF_RES) ||
+                     ((op.code == EVO_OP_PROLONG_ADD || op.code == EVO_OP_PROLONG_SET) && op.level - 1 == hi && op.src == EVO_BUF_RES) ||
+                     (op.code == EVO_OP_FAS_COARSE_RHS && op.level == hi);
+        bool writes = (op.code == EVO_OP_RESIDUAL && op.level == hi) ||
+                      ((op.code == EVO_OP_COPY || op.code == EVO_OP_ZERO || op.code == EVO_OP_PROLONG_SET) && op.level == hi && op.dst == EVO_BUF_RES);
+        if (reads) { c->res_dead_on_entry = false; break; }
+        if (writes) break;
+    }
     int rc = validate_ops(c);
     if (rc == EVO_OK) rc = allocate_cycle(c);
     if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
@@ -786,7 +811,7 @@ extern "C" int evo_cycle_residual_norm(evo_cycle *c, double *norm)
 {
     if (!c || !norm) return fail(EVO_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->p->desc.device));
-    EV(dispatch_residual_norm(c, c->stream));
+    EV(dispatch_residual_norm(c, c->stream, true));
     CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *norm = sqrt(c->h_state->sum);
