@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "evo_kernels.cuh"
@@ -110,63 +111,70 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 
 // ---------------------------------------------------------------------------------------------
 // k consecutive pointwise RB-GS sweeps (S = 2k half-sweeps) in one pass, 3-D 7-point.
-constexpr int RB_TX = 64, RB_TY = 16, RB_NT = 256;
+constexpr int RB_TX = 64;  // tile width (x); tile height TY and thread count NT are template parameters
 
 // compile-time geometry of pipeline stage s of S: it covers the tile plus a halo of E nodes
-template <int S, int s> struct StageCfg {
+template <int S, int TY, int NT, int s> struct StageCfg {
     static constexpr int E = S - 1 - s;
-    static constexpr int W = RB_TX + 2 * E, ROWS = RB_TY + 2 * E, NPX = W / 2;
-    static constexpr int ITEMS = NPX * ROWS, ROUNDS = (ITEMS + RB_NT - 1) / RB_NT;
+    static constexpr int W = RB_TX + 2 * E, ROWS = TY + 2 * E, NPX = W / 2;
+    // Bank-conflict-free lane mapping: the active nodes of one row all have the same x parity and would
+    // only hit every other 8-byte bank; a group of 16 lanes (one shared-memory wavefront of 64-bit
+    // accesses) therefore takes 8 consecutive active nodes of row y and 8 of row y+1 -- the two rows'
+    // active colours have opposite x parity and together cover all 16 banks.
+    static constexpr int CH = (NPX + 7) / 8, ROWP = (ROWS + 1) / 2;
+    static constexpr int ITEMS = ROWP * CH * 16, ROUNDS = (ITEMS + NT - 1) / NT;
 };
-template <int S, int s> __host__ __device__ constexpr int stage_base()
+template <int S, int TY, int NT, int s> __host__ __device__ constexpr int stage_base()
 {
     if constexpr (s == 0) return 0;
-    else return stage_base<S, s - 1>() + StageCfg<S, s - 1>::ROUNDS;
+    else return stage_base<S, TY, NT, s - 1>() + StageCfg<S, TY, NT, s - 1>::ROUNDS;
 }
-template <int S> struct RbCfg {
+template <int S, int TY, int NT> struct RbCfg {
     static constexpr int H = S;
     // TMA needs a 16-byte aligned start address: with fp64 the x start coordinate must be even, so the
     // window starts one node further left (tiles start at odd x = 1 + 64*bx) and is 2 nodes wider
-    static constexpr int LX = RB_TX + 2 * H + 2, LY = RB_TY + 2 * H;
+    static constexpr int LX = RB_TX + 2 * H + 2, LY = TY + 2 * H;
     static constexpr int NP = S + 3;  // ring: planes t-S .. t+2 (one plane of TMA prefetch)
     static constexpr int PSTRIDE = (LX * LY + 15) / 16 * 16;  // slot stride in doubles (128-byte aligned)
-    static constexpr int TOT = stage_base<S, S>();             // work items per thread over all stages
+    static constexpr int TOT = stage_base<S, TY, NT, S>();             // work items per thread over all stages
 };
 
 // per-thread work items: fixed (row, x-pair) positions for every stage, set up once before the z loop
-template <int S> struct RbItems {
-    int loff[RbCfg<S>::TOT];   // shared-memory offset of the pair's left node
-    int goff[RbCfg<S>::TOT];   // in-plane global offset of the pair's left node
+template <int S, int TY, int NT> struct RbItems {
+    int loff[RbCfg<S, TY, NT>::TOT];   // shared-memory offset of the pair's left node
+    int goff[RbCfg<S, TY, NT>::TOT];   // in-plane global offset of the pair's left node
     unsigned v0, v1, par;      // bit i: item i valid when the active node is the left / right one; parity bit
 };
 
-template <int S, int s>
-__device__ __forceinline__ void rb_setup(RbItems<S> &it, int tid, int x0, int y0, int xb, int yb, const Geom &g)
+template <int S, int TY, int NT, int s>
+__device__ __forceinline__ void rb_setup(RbItems<S, TY, NT> &it, int tid, int x0, int y0, int xb, int yb, const Geom &g)
 {
-    using C = StageCfg<S, s>;
-    constexpr int base = stage_base<S, s>();
+    using C = StageCfg<S, TY, NT, s>;
+    constexpr int base = stage_base<S, TY, NT, s>();
 #pragma unroll
     for (int j = 0; j < C::ROUNDS; ++j) {
-        const int i = tid + RB_NT * j;
-        const int ry = i / C::NPX, kx = i - ry * C::NPX;
+        const int i = tid + NT * j;
+        const int grp = i >> 4, l16 = i & 15;
+        const int rp = grp / C::CH, ch = grp - rp * C::CH;
+        const int ry = 2 * rp + (l16 >> 3), kx = ch * 8 + (l16 & 7);
         const int y = y0 - C::E + ry, xw = x0 - C::E + 2 * kx;
-        const bool ok = i < C::ITEMS && y >= 1 && y <= g.n - 2;
-        it.loff[base + j] = (y - yb) * RbCfg<S>::LX + (xw - xb);
+        const bool ok = i < C::ITEMS && kx < C::NPX && ry < C::ROWS && y >= 1 && y <= g.n - 2;
+        it.loff[base + j] = (y - yb) * RbCfg<S, TY, NT>::LX + (xw - xb);
         it.goff[base + j] = y * g.pitch + xw;
         if (ok && xw >= 1 && xw <= g.n - 2) it.v0 |= 1u << (base + j);
         if (ok && xw + 1 >= 1 && xw + 1 <= g.n - 2) it.v1 |= 1u << (base + j);
         if ((xw + y + (s & 1)) & 1) it.par |= 1u << (base + j);   // parity of the left node for z even
     }
-    if constexpr (s + 1 < S) rb_setup<S, s + 1>(it, tid, x0, y0, xb, yb, g);
+    if constexpr (s + 1 < S) rb_setup<S, TY, NT, s + 1>(it, tid, x0, y0, xb, yb, g);
 }
 
 // f values of the active nodes of every stage for the step whose stage-0 plane is t
-template <int S, int s>
-__device__ __forceinline__ void rb_load_f(const RbItems<S> &it, double (&fv)[RbCfg<S>::TOT], const double *__restrict__ f,
+template <int S, int TY, int NT, int s>
+__device__ __forceinline__ void rb_load_f(const RbItems<S, TY, NT> &it, double (&fv)[RbCfg<S, TY, NT>::TOT], const double *__restrict__ f,
                                           const Geom &g, int t, int za, int zb)
 {
-    using C = StageCfg<S, s>;
-    constexpr int base = stage_base<S, s>();
+    using C = StageCfg<S, TY, NT, s>;
+    constexpr int base = stage_base<S, TY, NT, s>();
     const int z = t - s;
     if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
         const double *fp = f + (long long)z * g.plane;
@@ -179,16 +187,16 @@ __device__ __forceinline__ void rb_load_f(const RbItems<S> &it, double (&fv)[RbC
             if (ok) fv[idx] = __ldg(fp + it.goff[idx] + p);
         }
     }
-    if constexpr (s + 1 < S) rb_load_f<S, s + 1>(it, fv, f, g, t, za, zb);
+    if constexpr (s + 1 < S) rb_load_f<S, TY, NT, s + 1>(it, fv, f, g, t, za, zb);
 }
 
-template <int S, int s>
-__device__ __forceinline__ void rb_stages(const RbItems<S> &it, const double (&fv)[RbCfg<S>::TOT], double *ring, int pbase,
+template <int S, int TY, int NT, int s>
+__device__ __forceinline__ void rb_stages(const RbItems<S, TY, NT> &it, const double (&fv)[RbCfg<S, TY, NT>::TOT], double *ring, int pbase,
                                           const Geom &g, const Star7 &c, double inv_c, double omega, int t, int za, int zb)
 {
-    using C = StageCfg<S, s>;
-    using R = RbCfg<S>;
-    constexpr int base = stage_base<S, s>();
+    using C = StageCfg<S, TY, NT, s>;
+    using R = RbCfg<S, TY, NT>;
+    constexpr int base = stage_base<S, TY, NT, s>();
     const int z = t - s;
     if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
         double *pc = ring + (size_t)((z - pbase) % R::NP) * R::PSTRIDE;
@@ -215,16 +223,16 @@ __device__ __forceinline__ void rb_stages(const RbItems<S> &it, const double (&f
         }
     }
     __syncthreads();
-    if constexpr (s + 1 < S) rb_stages<S, s + 1>(it, fv, ring, pbase, g, c, inv_c, omega, t, za, zb);
+    if constexpr (s + 1 < S) rb_stages<S, TY, NT, s + 1>(it, fv, ring, pbase, g, c, inv_c, omega, t, za, zb);
 }
 
-template <int S>
-__global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ CUtensorMap umap,
+template <int S, int TY, int NT>
+__global__ void __launch_bounds__(NT) k3_rbgs_stream(const __grid_constant__ CUtensorMap umap,
                                                         const double *__restrict__ f, double *__restrict__ uout,
                                                         const Geom g, const Star7 c, const double inv_c,
                                                         const double omega, const int tz)
 {
-    using R = RbCfg<S>;
+    using R = RbCfg<S, TY, NT>;
     constexpr int H = R::H, LX = R::LX, LY = R::LY, NP = R::NP, PSTRIDE = R::PSTRIDE, TOT = R::TOT;
     constexpr uint32_t PLANE_BYTES = LX * LY * 8;
     static_assert(TOT <= 32, "validity bit masks are 32 bits wide");
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
     __shared__ __align__(8) uint64_t bars[NP];
 
     const int n = g.n;
-    const int x0 = 1 + blockIdx.x * RB_TX, y0 = 1 + blockIdx.y * RB_TY;
+    const int x0 = 1 + blockIdx.x * RB_TX, y0 = 1 + blockIdx.y * TY;
     const int za = 1 + blockIdx.z * tz, zb = min(za + tz - 1, n - 2);
     const int xb = x0 - H - 1, yb = y0 - H;  // global coordinates of local (0, 0); xb is even
     const int pbase = za - H;                // first plane ever loaded (may be < 0: zero filled, never used)
@@ -242,9 +250,9 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
         for (int i = 0; i < NP; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
-    RbItems<S> it;
+    RbItems<S, TY, NT> it;
     it.v0 = it.v1 = it.par = 0u;
-    rb_setup<S, 0>(it, tid, x0, y0, xb, yb, g);
+    rb_setup<S, TY, NT, 0>(it, tid, x0, y0, xb, yb, g);
     __syncthreads();
 
     auto slot_of = [&](int p) { return (p - pbase) % NP; };
@@ -264,25 +272,25 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
     double fcur[TOT], fnext[TOT];
 #pragma unroll
     for (int i = 0; i < TOT; ++i) { fcur[i] = 0.0; fnext[i] = 0.0; }
-    rb_load_f<S, 0>(it, fcur, f, g, t0, za, zb);
+    rb_load_f<S, TY, NT, 0>(it, fcur, f, g, t0, za, zb);
     for (int p = pbase; p <= min(t0, pmax); ++p) wait_plane(p);
 
     for (int t = t0; t <= t1; ++t) {
         // right-hand sides of the next step: issued now, consumed one step later (latency hidden)
-        if (t < t1) rb_load_f<S, 0>(it, fnext, f, g, t + 1, za, zb);
+        if (t < t1) rb_load_f<S, TY, NT, 0>(it, fnext, f, g, t + 1, za, zb);
         if (t + 1 <= pmax) wait_plane(t + 1);
         if (tid == 0 && t + 2 <= pmax) {
             fence_proxy_async();         // generic-proxy accesses of the recycled slot completed before the last barrier
             issue(t + 2);
         }
-        rb_stages<S, 0>(it, fcur, ring, pbase, g, c, inv_c, omega, t, za, zb);
+        rb_stages<S, TY, NT, 0>(it, fcur, ring, pbase, g, c, inv_c, omega, t, za, zb);
         const int zf = t - (S - 1);
         if (zf >= za && zf <= zb) {
             const double *pc = ring + (size_t)slot_of(zf) * PSTRIDE;
-            const int xhi = min(x0 + RB_TX - 1, n - 2), yhi = min(y0 + RB_TY - 1, n - 2);
+            const int xhi = min(x0 + RB_TX - 1, n - 2), yhi = min(y0 + TY - 1, n - 2);
             double *op = uout + (long long)zf * g.plane;
 #pragma unroll
-            for (int i = tid; i < RB_TX * RB_TY; i += RB_NT) {
+            for (int i = tid; i < RB_TX * TY; i += NT) {
                 const int ry = i / RB_TX, rx = i - ry * RB_TX;
                 const int x = x0 + rx, y = y0 + ry;
                 if (x <= xhi && y <= yhi) op[y * g.pitch + x] = pc[(y - yb) * LX + (x - xb)];
@@ -295,21 +303,21 @@ __global__ void __launch_bounds__(RB_NT) k3_rbgs_stream(const __grid_constant__ 
     }
 }
 
-template <int S>
+template <int S, int TY, int NT>
 static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout,
                                double omega, cudaStream_t s)
 {
-    using R = RbCfg<S>;
+    using R = RbCfg<S, TY, NT>;
     CUtensorMap map;
     if (!make_plane_map(&map, g, u, R::LX, R::LY)) return false;
     const size_t smem = (size_t)R::NP * R::PSTRIDE * 8;
     static int occ = 0;
     if (occ == 0) {
-        if (cudaFuncSetAttribute(k3_rbgs_stream<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_stream<S>, RB_NT, smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaFuncSetAttribute(k3_rbgs_stream<S, TY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_stream<S, TY, NT>, NT, smem) != cudaSuccess || occ < 1) occ = 1;
     }
     const int inner = g.n - 2;
-    const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + RB_TY - 1) / RB_TY;
+    const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + TY - 1) / TY;
     // z slabs: minimise (waves) x (planes per slab + pipeline fill) over 1..16 slabs
     const long long slots = (long long)occ * sm_count;
     int best = 1;
@@ -323,7 +331,7 @@ static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, cons
     }
     const int tz = (inner + best - 1) / best;
     const int slabs = (inner + tz - 1) / tz;
-    k3_rbgs_stream<S><<<dim3(tx, ty, slabs), RB_NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
+    k3_rbgs_stream<S, TY, NT><<<dim3(tx, ty, slabs), NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
     return cudaGetLastError() == cudaSuccess;
 }
 
@@ -335,8 +343,26 @@ static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Field
     if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
         Star7 c;
         if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
-        if (sweeps == 1) return launch_rbgs_stream<2>(sm_count, g, c, u.p[0], f.p[0], uout.p[0], omega, s);
-        if (sweeps == 2) return launch_rbgs_stream<4>(sm_count, g, c, u.p[0], f.p[0], uout.p[0], omega, s);
+        static int variant = -1;   // EVO_RB_VARIANT: tile-shape experiments (0 = default)
+        if (variant < 0) { const char *e = getenv("EVO_RB_VARIANT"); variant = e ? atoi(e) : 0; }
+        const double *up = u.p[0], *fp = f.p[0];
+        double *op = uout.p[0];
+        if (sweeps == 1) {
+            if (variant == 1) return launch_rbgs_stream<2, 32, 512>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 2) return launch_rbgs_stream<2, 32, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 3) return launch_rbgs_stream<2, 16, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 4) return launch_rbgs_stream<2, 8, 128>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 5) return launch_rbgs_stream<2, 12, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 6) return launch_rbgs_stream<2, 6, 128>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 7) return launch_rbgs_stream<2, 4, 128>(sm_count, g, c, up, fp, op, omega, s);
+            return launch_rbgs_stream<2, 8, 256>(sm_count, g, c, up, fp, op, omega, s);   // best measured: 68 % of HBM peak
+        }
+        if (sweeps == 2) {
+            if (variant == 1) return launch_rbgs_stream<4, 32, 512>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 2) return launch_rbgs_stream<4, 32, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 3) return launch_rbgs_stream<4, 24, 512>(sm_count, g, c, up, fp, op, omega, s);
+            return launch_rbgs_stream<4, 16, 256>(sm_count, g, c, up, fp, op, omega, s);
+        }
         return false;
     } else {
         return false;

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -380,7 +381,9 @@ template <typename T, int DIM, int NF> struct Launch {
         if (NU == 1 && op.mode == EVO_SMOOTH_REDBLACK && c->lv[l].slot[0] && star::rbgs_stream_applicable<T, DIM, NF>(g, c->sten[l])) {
             // fused streaming kernel: up to 2 sweeps per pass, out of place into the [next] slot
             while (reps > 0) {
-                const int k = reps >= 2 ? 2 : 1;
+                // one launch per sweep: the 2-sweep variant (S = 4) is currently slower than two S = 2 launches
+                static const bool fuse2 = getenv("EVO_RB_FUSE2") != nullptr;
+                const int k = (fuse2 && reps >= 2) ? 2 : 1;
                 auto src = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), dst = fields_of<T>(c->lv[l].slot, NF);
                 if (!star::try_rbgs_stream<T, DIM, NF>(c->p->sm_count, g, c->sten[l], src, rhs, dst, op.omega, k, s)) break;
                 c->launch_counter++;
