@@ -116,42 +116,23 @@ __global__ void __launch_bounds__(128) k_row_sumsq(const Geom g, Fields<T> r, do
     }
 }
 
-// rows -> planes -> field sums -> total (single block of 32 warps)
-template <int DIM>
-__global__ void __launch_bounds__(1024) k_reduce_rows(const double *rows, int nf, int ni, SolveState *st)
+// canonical reduction, second and third level: row sums -> plane sums (3-D: one warp per plane, many
+// blocks) -> field sums -> total (one warp)
+__global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int nf, int ni, double *planes)
 {
-    __shared__ double planes[1024];
-    __shared__ double fsum[EVO_MAX_FIELDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nzi = DIM == 3 ? ni : 1;
-    for (int i = 0; i < nf; ++i) {
-        const double *fr = rows + (long long)i * ni * nzi;
-        if (DIM == 3) {
-            for (int base = 0; base < nzi; base += 1024) {  // nzi <= 1023 for every supported level
-                for (int zz = base + warp; zz < min(nzi, base + 1024); zz += 32) {
-                    double s = warp_vecsum(fr + (long long)zz * ni, ni);
-                    if (lane == 0) planes[zz - base] = s;
-                }
-            }
-            __syncthreads();
-            if (warp == 0) {
-                double s = warp_vecsum(planes, nzi);
-                if (lane == 0) fsum[i] = s;
-            }
-            __syncthreads();
-        } else {
-            if (warp == 0) {
-                double s = warp_vecsum(fr, ni);
-                if (lane == 0) fsum[i] = s;
-            }
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x == 0) {
-        double total = 0.0;
-        for (int i = 0; i < nf; ++i) total = total + fsum[i];
-        st->sum = total;
-    }
+    const long long id = (long long)blockIdx.x * 8 + warp;   // (field, plane)
+    if (id >= (long long)nf * ni) return;
+    double s = warp_vecsum(rows + id * ni, ni);
+    if (lane == 0) planes[id] = s;
+}
+
+// vals: per field `m` partial sums (plane sums in 3-D, row sums in 2-D)
+__global__ void __launch_bounds__(32) k_reduce_final(const double *vals, int nf, int m, SolveState *st)
+{
+    double total = 0.0;
+    for (int i = 0; i < nf; ++i) total = total + warp_vecsum(vals + (long long)i * m, m);
+    if (threadIdx.x == 0) st->sum = total;
 }
 
 // bookkeeping of the outer loop: `until res < tol*res0 or it >= maxIts`

@@ -418,6 +418,34 @@ __global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star
     }
 }
 
+// 3-D pointwise weighted Jacobi sweep (`solve locally ... with jacobi`), same row mapping: reads the
+// current slot, writes the next slot; per node s = sum of the off-diagonal terms in table order,
+// x = (f - s) * (1/a), u_new = u + w (x - u)
+__global__ void __launch_bounds__(256) k3_jacobi_rows(const Geom g, const Star7 c, const double inv_c, const double omega,
+                                                      const double *__restrict__ u, const double *__restrict__ f,
+                                                      double *__restrict__ unew)
+{
+    const int ni = g.n - 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = 1 + blockIdx.x * 8 + warp, z = 1 + blockIdx.y;
+    if (y > ni) return;
+    const long long base = (long long)z * g.plane + (long long)y * g.pitch;
+    const double *uc = u + base, *fc = f + base;
+    const double *uym = uc - g.pitch, *uyp = uc + g.pitch, *uzm = uc - g.plane, *uzp = uc + g.plane;
+    for (int x = 1 + lane; x <= ni; x += 32) {
+        double sum = 0.0;
+        sum = sum + c.zm * uzm[x];
+        sum = sum + c.ym * uym[x];
+        sum = sum + c.xm * uc[x - 1];
+        sum = sum + c.xp * uc[x + 1];
+        sum = sum + c.yp * uyp[x];
+        sum = sum + c.zp * uzp[x];
+        const double xs = (fc[x] - sum) * inv_c;
+        const double old = uc[x];
+        unew[base + x] = old + omega * (xs - old);
+    }
+}
+
 // 3-D trilinear prolongation + correction u += w * P e, one thread per coarse cell: the 8 coarse corner
 // values give the 8 fine nodes (2X..2X+1, 2Y..2Y+1, 2Z..2Z+1); fine rows are updated with coalesced
 // 16-byte read-modify-writes.  Per fine node the terms are added in ascending stencil-table order of
@@ -516,10 +544,19 @@ static bool try_residual_norm(const Geom &g, const OpSten &st, Fields<T> u, Fiel
 }
 
 template <typename T, int DIM, int NF>
-static bool try_smooth_point(int, const Geom &, const OpSten &, const SmoothParams &, Fields<T>, Fields<T>, Fields<T>,
-                             cudaStream_t)
+static bool try_smooth_point(int, const Geom &g, const OpSten &st, const SmoothParams &sp, Fields<T> src, Fields<T> dst,
+                             Fields<T> rhs, cudaStream_t s)
 {
-    return false;
+    if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
+        Star7 c;
+        // only the out-of-place Jacobi sweep (colour passes of RB-GS go through the streaming kernel)
+        if (sp.color >= 0 || src.p[0] == dst.p[0] || g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
+        const int ni = g.n - 2;
+        k3_jacobi_rows<<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, 1.0 / c.c, sp.omega, src.p[0], rhs.p[0], dst.p[0]);
+        return cudaGetLastError() == cudaSuccess;
+    } else {
+        return false;
+    }
 }
 template <typename T, int DIM, int NF>
 static bool try_residual_restrict(int, const Geom &, const Geom &, const OpSten &, const TransferW &, Fields<T>, Fields<T>,

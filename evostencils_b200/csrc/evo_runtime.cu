@@ -17,6 +17,7 @@
 
 #include "evo_kernels.cuh"
 #include "evo_kernels_star.cuh"
+#include "evo_kernels_fas.cuh"
 
 using namespace evo;
 
@@ -244,7 +245,8 @@ static bool level_needs_slot(const evo_cycle *c, int level)
 {
     for (const evo_op &op : c->ops)
         if (op.level == level && ((op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_JACOBI) || op.code == EVO_OP_RICHARDSON ||
-                                  rb_stream_candidate(c, op)))
+                                  rb_stream_candidate(c, op) ||
+                                  (op.code == EVO_OP_COARSE_SOLVE && c->p->desc.kind == EVO_PROBLEM_FAS)))
             return true;
     return false;
 }
@@ -294,7 +296,7 @@ static int allocate_cycle(evo_cycle *c)
         c->d_cg_iters = (int *)take(256);
         const Geom &gf = p->geom[hi];
         c->n_partials = nf * (gf.n - 2) * (gf.dim == 3 ? gf.n - 2 : 1);
-        c->d_partials = (double *)take(sizeof(double) * (size_t)c->n_partials);
+        c->d_partials = (double *)take(sizeof(double) * ((size_t)c->n_partials + (size_t)nf * gf.n));
         if (pass == 0) {
             c->slab_bytes = off;
             c->slab = nullptr;
@@ -329,6 +331,22 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // cycle: op dispatch (every function only enqueues work on `s`; safe under stream capture)
 template <typename T, int DIM, int NF> struct Launch {
+    // d_partials holds the canonical row sums [NF][nzi][ni]; reduce them to SolveState::sum
+    static int reduce_rows(evo_cycle *c, int ni, cudaStream_t s)
+    {
+        if (DIM == 3) {
+            double *planes = c->d_partials + (size_t)NF * ni * ni;
+            k_reduce_planes<<<(unsigned)((NF * ni + 7) / 8), 256, 0, s>>>(c->d_partials, NF, ni, planes);
+            k_reduce_final<<<1, 32, 0, s>>>(planes, NF, ni, c->d_state);
+            c->launch_counter += 2;
+        } else {
+            k_reduce_final<<<1, 32, 0, s>>>(c->d_partials, NF, ni, c->d_state);
+            c->launch_counter += 1;
+        }
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+
     static int residual(evo_cycle *c, int l, bool norm, cudaStream_t s)
     {
         const Geom &g = c->p->geom[l];
@@ -338,9 +356,8 @@ template <typename T, int DIM, int NF> struct Launch {
         if (norm && star::try_residual_norm<T, DIM, NF>(g, c->sten[l], u, f, r, c->d_partials, !c->res_dead_on_entry, s)) {
             // residual and canonical row sums in one pass; the field itself is only stored if a later
             // statement may read it
-            k_reduce_rows<DIM><<<1, 1024, 0, s>>>(c->d_partials, NF, ni, c->d_state);
-            c->launch_counter += 2;
-            CU(cudaGetLastError());
+            c->launch_counter += 1;
+            EV(reduce_rows(c, ni, s));
             return EVO_OK;
         }
         if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s))
@@ -349,8 +366,8 @@ template <typename T, int DIM, int NF> struct Launch {
         if (norm) {
             const long long nrows = (long long)ni * (DIM == 3 ? ni : 1);
             k_row_sumsq<T, DIM, NF><<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
-            k_reduce_rows<DIM><<<1, 1024, 0, s>>>(c->d_partials, NF, ni, c->d_state);
-            c->launch_counter += 2;
+            c->launch_counter += 1;
+            EV(reduce_rows(c, ni, s));
         }
         CU(cudaGetLastError());
         return EVO_OK;
@@ -584,9 +601,109 @@ template <typename T, int DIM, int NF> static int enqueue_op(evo_cycle *c, const
     }
 }
 
+// ---- FAS problems (real scalar 2-D) -----------------------------------------------------------------
+static int fas_residual(evo_cycle *c, int l, cudaStream_t s)
+{
+    fas::Lin2 L;
+    if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
+    const Geom &g = c->p->geom[l];
+    fas::k2_fas_residual<<<row_grid(g), BX, 0, s>>>(g, L, c->p->desc.gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                                   (const double *)c->lv[l].buf[EVO_BUF_RHS][0], (double *)c->lv[l].buf[EVO_BUF_RES][0]);
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+// returns 1 when the op is not FAS specific
+static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
+{
+    const evo_problem_desc &d = c->p->desc;
+    const int l = op.level;
+    const double gamma = d.gamma;
+    auto swap_slot = [&](int lev) {
+        bool cor_alias = c->lv[lev].buf[EVO_BUF_COR][0] == c->lv[lev].buf[EVO_BUF_SOL][0];
+        std::swap(c->lv[lev].buf[EVO_BUF_SOL][0], c->lv[lev].slot[0]);
+        if (cor_alias) c->lv[lev].buf[EVO_BUF_COR][0] = c->lv[lev].buf[EVO_BUF_SOL][0];
+        c->lv[lev].swapped[0] = !c->lv[lev].swapped[0];
+    };
+    switch (op.code) {
+    case EVO_OP_SMOOTH: {
+        if (op.kind == EVO_KIND_LINEAR) return 1;
+        fas::Lin2 L;
+        if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
+        const Geom &g = c->p->geom[l];
+        const int newton = op.kind == EVO_KIND_FAS_NEWTON, steps = op.count > 0 ? op.count : 1;
+        const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
+        if (op.mode == EVO_SMOOTH_JACOBI) {
+            if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing jacobi slot");
+            fas::k2_fas_smooth<<<row_grid(g), BX, 0, s>>>(g, L, gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                                         (double *)c->lv[l].slot[0], f, newton, steps, op.omega, -1);
+            c->launch_counter++;
+            swap_slot(l);
+        } else if (op.mode == EVO_SMOOTH_REDBLACK) {
+            double *u = (double *)c->lv[l].buf[EVO_BUF_SOL][0];
+            for (int color = 0; color < 2; ++color) {
+                fas::k2_fas_smooth<<<row_grid(g, 2), BX, 0, s>>>(g, L, gamma, u, u, f, newton, steps, op.omega, color);
+                c->launch_counter++;
+            }
+        } else {
+            return fail(EVO_ERR_UNSUPPORTED, "FAS: lexicographic smoothing is not implemented");
+        }
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+    case EVO_OP_RESIDUAL: return fas_residual(c, l, s);
+    case EVO_OP_FAS_RESTRICT_SOL: {
+        evo_op r = op;
+        r.code = EVO_OP_RESTRICT; r.dst = EVO_BUF_APX; r.src = EVO_BUF_SOL;
+        EV((Launch<double, 2, 1>::restrict_(c, r, s)));
+        const size_t bytes = (size_t)c->p->geom[l - 1].total * sizeof(double);
+        CU(cudaMemcpyAsync(c->lv[l - 1].buf[EVO_BUF_SOL][0], c->lv[l - 1].buf[EVO_BUF_APX][0], bytes, cudaMemcpyDeviceToDevice, s));
+        return EVO_OK;
+    }
+    case EVO_OP_FAS_COARSE_RHS: {
+        evo_op r = op;
+        r.code = EVO_OP_RESTRICT; r.dst = EVO_BUF_RHS; r.src = EVO_BUF_RES;
+        EV((Launch<double, 2, 1>::restrict_(c, r, s)));
+        fas::Lin2 L;
+        if (!c->has_sten[l - 1] || !fas::make_lin2(c->sten[l - 1].s[0][0], &L)) return fail(EVO_ERR_INVALID, "FAS: no operator on level %d", l - 1);
+        const Geom &gc = c->p->geom[l - 1];
+        fas::k2_fas_add_operator<<<row_grid(gc), BX, 0, s>>>(gc, L, gamma, (const double *)c->lv[l - 1].buf[EVO_BUF_APX][0],
+                                                            (double *)c->lv[l - 1].buf[EVO_BUF_RHS][0]);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+    case EVO_OP_FAS_SUB_APX: {
+        const long long n = c->p->geom[l].total;
+        fas::k_sub_inplace<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, s>>>(
+            (double *)c->lv[l].buf[EVO_BUF_SOL][0], (const double *)c->lv[l].buf[EVO_BUF_APX][0], n);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+    case EVO_OP_COARSE_SOLVE: {
+        fas::Lin2 L;
+        if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
+        if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing slot for the FAS coarse solver");
+        fas::k2_fas_coarse<<<1, 1024, 0, s>>>(c->p->geom[l], L, gamma, (double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                              (double *)c->lv[l].slot[0], (const double *)c->lv[l].buf[EVO_BUF_RHS][0], op.count, op.omega);
+        c->launch_counter++;
+        CU(cudaGetLastError());
+        return EVO_OK;
+    }
+    default: return 1;
+    }
+}
+
 static int dispatch_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
 {
     const evo_problem_desc &d = c->p->desc;
+    if (d.kind == EVO_PROBLEM_FAS) {
+        if (d.dim != 2 || d.n_fields != 1 || d.scalar_words != 1) return fail(EVO_ERR_UNSUPPORTED, "FAS: real scalar 2-D only");
+        int rc = fas_dispatch(c, op, s);
+        if (rc != 1) return rc;
+    }
     if (d.scalar_words == 2) return enqueue_op<cplx, 2, 1>(c, op, s);
     if (d.dim == 2) return d.n_fields == 1 ? enqueue_op<double, 2, 1>(c, op, s) : enqueue_op<double, 2, 2>(c, op, s);
     return d.n_fields == 1 ? enqueue_op<double, 3, 1>(c, op, s) : enqueue_op<double, 3, 2>(c, op, s);
@@ -599,6 +716,15 @@ static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store
     struct Restore { evo_cycle *c; bool v; ~Restore() { c->res_dead_on_entry = v; } } restore{c, saved_dead};
     const evo_problem_desc &d = c->p->desc;
     const int l = d.max_level;
+    if (d.kind == EVO_PROBLEM_FAS) {
+        EV(fas_residual(c, l, s));
+        const Geom &g = c->p->geom[l];
+        const int ni = g.n - 2;
+        auto r = fields_of<double>(c->lv[l].buf[EVO_BUF_RES], 1);
+        k_row_sumsq<double, 2, 1><<<(unsigned)((ni + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
+        c->launch_counter++;
+        return Launch<double, 2, 1>::reduce_rows(c, ni, s);
+    }
     if (d.scalar_words == 2) EV((Launch<cplx, 2, 1>::residual(c, l, true, s)));
     else if (d.dim == 2 && d.n_fields == 1) EV((Launch<double, 2, 1>::residual(c, l, true, s)));
     else if (d.dim == 2) EV((Launch<double, 2, 2>::residual(c, l, true, s)));
@@ -644,6 +770,9 @@ static int validate_ops(const evo_cycle *c)
             return fail(EVO_ERR_INVALID, "op %zu: invalid buffer", t);
         bool needs_op = op.code == EVO_OP_RESIDUAL || op.code == EVO_OP_RICHARDSON || op.code == EVO_OP_SMOOTH ||
                         op.code == EVO_OP_COARSE_SOLVE || op.code == EVO_OP_RESIDUAL_RESTRICT;
+        if ((op.code == EVO_OP_FAS_RESTRICT_SOL || op.code == EVO_OP_FAS_COARSE_RHS || op.code == EVO_OP_FAS_SUB_APX) &&
+            d.kind != EVO_PROBLEM_FAS)
+            return fail(EVO_ERR_INVALID, "op %zu: FAS statement in a linear problem", t);
         if (needs_op && !c->has_sten[op.level]) return fail(EVO_ERR_INVALID, "op %zu: no operator for level %d", t, op.level);
         if (op.code == EVO_OP_SMOOTH && (op.n_unknowns < 1 || op.n_unknowns > EVO_MAX_UNKNOWNS))
             return fail(EVO_ERR_INVALID, "op %zu: local system size %d", t, op.n_unknowns);

@@ -78,3 +78,37 @@ def default_solver_cycle(problem: Problem) -> ol.Program:
     """The cycle of the problem's own `generate solver` block (config C1a of SURVEY.md 8d)."""
     s = problem.settings
     return v_cycle(problem, s.num_pre, s.num_post, s.damping, s.red_black)
+
+
+# ------------------------------------------------------------------------------------------------
+def _fas_cycle(problem: Problem, level: int, pre: int, post: int, omega: float, newton_steps: int, red_black: bool,
+               cgc_weight: float) -> List[ol.Op]:
+    """FAS V-cycle in the statement order of the reference's FAS emitter (exastencils_FAS.py:99-319;
+    golden text example_problems/FAS_2D_Basic/FAS_2D_Basic.exa4:213-269)."""
+    s = problem.settings
+    zero = (0,) * problem.dim
+    kind = ol.KIND_FAS_NEWTON if newton_steps > 0 else ol.KIND_FAS_PICARD
+    mode = ol.MODE_REDBLACK if red_black else ol.MODE_JACOBI
+
+    def smooth(n):
+        return [ol.Op(ol.OP_SMOOTH, level, mode=mode, kind=kind, count=max(1, newton_steps), omega=omega,
+                      unknowns=((0, zero),)) for _ in range(n)]
+
+    if level == problem.min_level:
+        return [ol.Op(ol.OP_COARSE_SOLVE, level, count=s.cgs_max_iters, omega=s.damping)]
+    ops = smooth(pre)
+    ops.append(ol.Op(ol.OP_RESIDUAL, level, dst=ol.BUF_RES))
+    ops.append(ol.Op(ol.OP_FAS_RESTRICT_SOL, level, dst=ol.BUF_APX, src=ol.BUF_SOL))
+    ops.append(ol.Op(ol.OP_FAS_COARSE_RHS, level, dst=ol.BUF_RHS, src=ol.BUF_RES))
+    ops.extend(_fas_cycle(problem, level - 1, pre, post, omega, newton_steps, red_black, cgc_weight))
+    ops.append(ol.Op(ol.OP_FAS_SUB_APX, level - 1, dst=ol.BUF_SOL, src=ol.BUF_APX))
+    ops.append(ol.Op(ol.OP_PROLONG_ADD, level, src=ol.BUF_SOL, omega=cgc_weight))
+    ops.extend(smooth(post))
+    return ops
+
+
+def fas_v_cycle(problem: Problem, pre: int = 2, post: int = 2, omega: float = 0.8, newton_steps: int = 1,
+                red_black: bool = False, cgc_weight: float = 1.0) -> ol.Program:
+    """The template's own FAS cycle: V(2,2), damped Newton-Jacobi omega = 0.8 (template.exa4:65-73)."""
+    return build_program(problem, _fas_cycle(problem, problem.max_level, pre, post, omega, newton_steps, red_black,
+                                             cgc_weight))

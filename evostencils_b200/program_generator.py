@@ -396,3 +396,152 @@ class B200ProgramGenerator:
 
 # the name a user of the reference would look for
 ProgramGenerator = B200ProgramGenerator
+
+
+class B200ProgramGeneratorFAS:
+    """Drop-in for ``ProgramGeneratorFAS`` (reference: code_generation/exastencils_FAS.py:11-445): same
+    constructor arguments, ``uses_FAS``, ``generate_and_evaluate(*args, **kwargs)`` picking the ``Cycle`` out
+    of its positional arguments (:396-404), ``generate_cycle_function(*args)``, the dummy
+    ``generate_storage`` / ``initialize_code_generation`` (:441-445).
+
+    Fitness follows the FAS ``parse_output`` (:370-394): ``c = (res_final/res_initial)^(1/n)`` from the
+    4-digit prints of the template's Solve loop, ``n`` = iterations, ``(1e100,)*3`` on abort / non-finite c.
+    ``cumulative_timer=True`` reproduces the template's time accounting (``t_sol +=
+    getTotalFromTimer('cycle')`` after every iteration, FAS_2D_Basic_template.exa4:148-151: the timer is
+    cumulative, so t_sol = sum_k k * t_cycle); set it to False for the plain solve time."""
+
+    def __init__(self, problem_name="FAS_2D_Basic", solution="Solution", rhs="RHS", residual="Residual",
+                 FASApproximation="Approximation", restriction="RestrictionNode", prolongation="CorrectionNode",
+                 op_linear="Laplace", op_nonlinear="gamSten", fct_name_mgcycle="gen_mgCycle", fct_cgs="CGS",
+                 fct_smoother=None, mpi_rank=0, platform_file=None, build_path=None, exastencils_compiler=None, *,
+                 problem: Optional[Problem] = None, device: Optional[int] = None, cumulative_timer: bool = True):
+        self.problem_name = problem_name
+        self.mpi_rank = mpi_rank
+        self.build_path = build_path
+        self.cumulative_timer = cumulative_timer
+        self._cycle_name = fct_name_mgcycle
+        if problem is None:
+            problem = problems.FAS2D()
+            if build_path:
+                kpath = os.path.join(build_path, problem_name, f"{problem_name}.knowledge")
+                if os.path.exists(kpath):
+                    from .frontend import read_knowledge
+                    dim, lo, hi = read_knowledge(kpath)
+                    problem = problem.with_levels(lo, hi)
+        self._problem = problem
+        self.min_level, self.max_level, self.dimension = problem.min_level, problem.max_level, problem.dim
+        try:
+            lib = backend.load_library()
+            ndev = lib.evo_device_count()
+        except backend.BackendError as e:
+            raise RuntimeError(f"Compiler not found. Aborting. ({e})")
+        if ndev <= 0:
+            raise RuntimeError("Compiler not found. Aborting. (no CUDA device visible; the B200 backend has no CPU fallback)")
+        self._device = (mpi_rank % ndev) if device is None else device
+        self._device_problems: Dict[Tuple, backend.DeviceProblem] = {}
+        self._average_generation_time = 0
+        self._counter = 0
+        self.last_outcome = None
+        self.total_kernel_launches = 0
+        # what generate_primitive_set needs (exastencils_FAS.py:76-93)
+        try:
+            import sympy
+            from evostencils.grammar import multigrid as mg
+            from evostencils.ir import base
+            self.fields = [sympy.Symbol("u")]
+            self.equations, self.operators = [], []
+            for i in range(self.min_level, self.max_level + 1):
+                self.equations.append(mg.EquationInfo("solEq", i, f"( Laplace@{i} * u@{i} ) == RHS_u@{i}"))
+                self.operators.append(mg.OperatorInfo("RestrictionNode", i, None, base.Restriction))
+                self.operators.append(mg.OperatorInfo("ProlongationNode", i, None, base.Prolongation))
+                self.operators.append(mg.OperatorInfo("Laplace", i, None, base.Operator))
+            size = 2 ** self.max_level
+            self.finest_grid = [base.Grid((size,) * self.dimension, (1.0 / size,) * self.dimension, self.max_level)]
+        except Exception:
+            self.fields = [SimpleNamespace(name="u")]
+            self.equations, self.operators = [], []
+            size = 2 ** self.max_level
+            self.finest_grid = [SimpleNamespace(size=(size,) * self.dimension, spacing=(1.0 / size,) * self.dimension,
+                                                level=self.max_level)]
+        self.coarsening_factor = [tuple([2] * self.dimension)]
+
+    @property
+    def uses_FAS(self):
+        return True
+
+    @property
+    def problem(self):
+        return self._problem
+
+    def _dev(self, min_level, max_level):
+        key = (min_level, max_level)
+        if key not in self._device_problems:
+            self._device_problems[key] = backend.DeviceProblem(self._problem.with_levels(min_level, max_level), self._device)
+        return self._device_problems[key]
+
+    @staticmethod
+    def _find_cycle(args):
+        expression = None
+        for arg in args:
+            if type(arg).__name__ == "Cycle":
+                expression = arg
+        return expression
+
+    def lower(self, expression) -> ol.Program:
+        from . import lowering_fas
+        p = self._problem
+        lo = lowering_fas.FASLowering(0, p.max_level, p.dim, p.settings.cgs_max_iters, p.settings.damping)
+        # the coarsest level of the individual is whatever its tree reaches
+        lo.update_rhs = {l: True for l in range(0, p.max_level + 1)}
+        lo._traverse(expression)
+        levels = [o.level for o in lo.ops] + [o.level - 1 for o in lo.ops if o.code in (
+            ol.OP_FAS_RESTRICT_SOL, ol.OP_FAS_COARSE_RHS, ol.OP_PROLONG_ADD)]
+        lo_level = min(levels)
+        prog = ol.Program(dim=p.dim, n_fields=1, min_level=lo_level, max_level=p.max_level, ops=lo.ops,
+                          operators={l: p.operator(l) for l in range(lo_level, p.max_level + 1)})
+        prog.restrict_w, prog.prolong_w = p.restrict_weights(), p.prolong_weights()
+        return prog
+
+    def generate_and_evaluate(self, *args, **kwargs):
+        infinity = 1e100
+        expression = self._find_cycle(args)
+        samples = kwargs.get("evaluation_samples", 1)
+        start = time.time()
+        try:
+            prog = self.lower(expression)
+            dev = self._dev(prog.min_level, prog.max_level)
+            s = dev.problem.settings
+            cyc = dev.build(prog)
+            try:
+                out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(samples)))
+            finally:
+                cyc.close()
+        except Exception:
+            return infinity, infinity, infinity
+        self._counter += 1
+        self._average_generation_time += (time.time() - start - self._average_generation_time) / self._counter
+        self.last_outcome = out
+        self.total_kernel_launches += out.kernel_launches * max(1, int(samples))
+        t, c, n = fitness.fas_fitness(out.residuals, out.time_ms, infinity)
+        if self.cumulative_timer and n < infinity:
+            t = t * (n + 1) / 2.0
+        return t, c, n
+
+    def generate_cycle_function(self, *args):
+        expression = self._find_cycle(args)
+        prog = self.lower(expression)
+        return exaslang.program_to_exaslang(prog, ("Solution",), ("RHS",), self.max_level, self._cycle_name)
+
+    def generate_storage(self, *args):
+        return []
+
+    def initialize_code_generation(self, *args):
+        return None
+
+    def close(self):
+        for d in self._device_problems.values():
+            d.close()
+        self._device_problems.clear()
+
+
+ProgramGeneratorFAS = B200ProgramGeneratorFAS

@@ -151,23 +151,25 @@ class ZeroApproximation(Approximation):
         super().__init__("0", grids)
 
 
-class Diagonal:               # decoupled Jacobi (reference: ir/smoother.py:5-6)
-    def __init__(self, operand):
-        self.operand = operand
-
-
-class ElementwiseDiagonal:    # collective Jacobi (ir/smoother.py:9-10)
-    def __init__(self, operand):
-        self.operand = operand
-
-
-class Inverse:
+class _Unary:
     def __init__(self, operand):
         self.operand = operand
 
     @property
     def grid(self):
-        return self.operand.grid if hasattr(self.operand, "grid") else self.operand.operand.grid
+        return self.operand.grid
+
+
+class Diagonal(_Unary):               # decoupled Jacobi (reference: ir/smoother.py:5-6)
+    pass
+
+
+class ElementwiseDiagonal(_Unary):    # collective Jacobi (ir/smoother.py:9-10)
+    pass
+
+
+class Inverse(_Unary):
+    pass
 
 
 class CoarseGridSolver:
@@ -195,6 +197,25 @@ class Multiplication:
     @property
     def grid(self):
         return self.operand1.grid
+
+
+class Addition:
+    def __init__(self, operand1, operand2):
+        self.operand1, self.operand2 = operand1, operand2
+
+    @property
+    def grid(self):
+        return self.operand1.grid
+
+
+class Subtraction(Addition):
+    pass
+
+
+class Jacobian(_Unary):       # Newton linearisation marker of the FAS smoother (reference: ir/system.py:132-138)
+    def __init__(self, operand, n_newton_steps):
+        super().__init__(operand)
+        self.n_newton_steps = n_newton_steps
 
 
 class Cycle:
@@ -284,7 +305,7 @@ RELAXATION_FACTORS = np.linspace(0.1, 1.9, 37)      # grammar/multigrid.py:428
 
 # ------------------------------------------------------------------------------------------------
 def grammar_context(problem: Problem, min_level: Optional[int] = None, max_level: Optional[int] = None,
-                    relaxation_factors=RELAXATION_FACTORS) -> Dict[str, object]:
+                    relaxation_factors=RELAXATION_FACTORS, fas: Optional[bool] = None) -> Dict[str, object]:
     """Name -> production function / terminal, for ``eval(individual_string, context)``.
 
     Fresh terminals on every call: the productions mutate and alias nodes (like the reference's
@@ -293,6 +314,8 @@ def grammar_context(problem: Problem, min_level: Optional[int] = None, max_level
     max_level = problem.max_level if max_level is None else max_level
     depth_total = max_level - min_level
     assert depth_total >= 1
+    if fas is None:
+        fas = problem.kind == ol.PROBLEM_FAS
     ctx: Dict[str, object] = {"single": Single, "red_black": RedBlack}
     approximation = Approximation("x", _grids(problem, max_level))
     rhs = RightHandSide("b", _grids(problem, max_level))
@@ -331,29 +354,58 @@ def grammar_context(problem: Problem, min_level: Optional[int] = None, max_level
         def collective_block_jacobi(weight_index, block_shape, cycle):
             return smoothing(weight_index, Single, lambda op: block_jacobi_operator(op, block_shape, problem.dim), cycle)
 
+        def restrict(restriction, cycle):
+            if fas:   # coarse rhs = R r + A_c (R u): grammar/multigrid.py:287-293
+                cycle.correction = Addition(Multiplication(restriction, cycle.correction),
+                                            Multiplication(A_c, Multiplication(restriction, cycle.approximation)))
+            else:
+                cycle.correction = Multiplication(restriction, cycle.correction)
+            return cycle
+
+        def jacobi_picard(weight_index, partitioning, cycle):
+            return smoothing(weight_index, partitioning, ElementwiseDiagonal, cycle)
+
+        def jacobi_newton(weight_index, partitioning, n_newton_steps, cycle):
+            return smoothing(weight_index, partitioning,
+                             lambda op: Addition(ElementwiseDiagonal(op), Jacobian(op, n_newton_steps)), cycle)
+
         def coarsening(coarse_operator, coarse_approximation, restriction, cycle):
-            cycle.correction = Multiplication(restriction, cycle.correction)
+            cycle = restrict(restriction, cycle)
             new_cycle = Cycle(coarse_approximation, cycle.correction,
                               Residual(coarse_operator, coarse_approximation, cycle.correction))
             new_cycle.predecessor = cycle
             return new_cycle
 
-        def update_with_coarse_grid_correction(weight_index, prolongation, state):
+        def update_with_coarse_grid_correction(weight_index, prolongation, state, restriction=None):
             cycle = state[0]
-            cycle.predecessor.correction = Multiplication(prolongation, cycle)
+            if fas:   # e_c = u_c - R u_f  (grammar/multigrid.py:275-284)
+                correction = Multiplication(prolongation, Subtraction(
+                    cycle, Multiplication(restriction, cycle.predecessor.approximation)))
+            else:
+                correction = Multiplication(prolongation, cycle)
+            cycle.predecessor.correction = correction
             return update(weight_index, Single, cycle.predecessor)
 
         def correct_with_coarse_grid_solver(weight_index, prolongation, coarse_grid_solver, restriction, cycle):
-            cycle.correction = Multiplication(restriction, cycle.correction)
-            cycle.correction = Multiplication(coarse_grid_solver, cycle.correction)
-            cycle.correction = Multiplication(prolongation, cycle.correction)
+            cycle = restrict(restriction, cycle)
+            if fas:   # grammar/multigrid.py:335-340
+                approximation_c = Multiplication(coarse_grid_solver, cycle.correction)
+                cycle.correction = Multiplication(prolongation, Subtraction(
+                    approximation_c, Multiplication(restriction, cycle.approximation)))
+            else:
+                cycle.correction = Multiplication(coarse_grid_solver, cycle.correction)
+                cycle.correction = Multiplication(prolongation, cycle.correction)
             return update(weight_index, Single, cycle)
 
         ctx[f"residual_{d}"] = residual
         if problem.n_fields > 1:
             ctx[f"decoupled_jacobi_{d}"] = decoupled_jacobi
-        ctx[f"collective_jacobi_{d}"] = collective_jacobi
-        ctx[f"collective_block_jacobi_{d}"] = collective_block_jacobi
+        if fas:   # grammar/multigrid.py:356-364
+            ctx[f"jacobi_picard_{d}"] = jacobi_picard
+            ctx[f"jacobi_newton_{d}"] = jacobi_newton
+        else:
+            ctx[f"collective_jacobi_{d}"] = collective_jacobi
+            ctx[f"collective_block_jacobi_{d}"] = collective_block_jacobi
         if not coarsest:
             ctx[f"update_with_coarse_grid_correction_{d}"] = update_with_coarse_grid_correction
             ctx[f"coarsening_{d}"] = coarsening
@@ -408,6 +460,42 @@ def _v_cycle_tail(levels, pre, post, w, smoother, part, cw, d, presmoothed, fres
             return s_state
         d -= 1
         s_state = f"update_with_coarse_grid_correction_{d}({cw}, P_{d + 1}, {s_state})"
+
+
+def fas_v_cycle_individual(levels: int, pre: int = 2, post: int = 2, weight_index: int = 14, newton_steps: int = 1,
+                           partitioning: str = "single", cgc_weight_index: int = 18) -> str:
+    """FAS V(pre, post) cycle as a grammar string (productions of grammar/multigrid.py:360-375)."""
+    def sm(d, arg_is_c, arg):
+        inner = arg if arg_is_c else f"residual_{d}({arg})"
+        if newton_steps > 0:
+            return f"jacobi_newton_{d}({weight_index}, {partitioning}, {newton_steps}, {inner})"
+        return f"jacobi_picard_{d}({weight_index}, {partitioning}, {inner})"
+
+    s_state, c_state, d = "u_and_f", None, 0
+    for _ in range(pre):
+        s_state = sm(0, False, s_state)
+    while True:
+        c = c_state if s_state is None else f"residual_{d}({s_state})"
+        if d < levels - 1:
+            c_next = f"coarsening_{d}(A_{d + 1}, zero_{d + 1}, R_{d}, {c})"
+            d += 1
+            if pre > 0:
+                s_state = sm(d, True, c_next)
+                for _ in range(pre - 1):
+                    s_state = sm(d, False, s_state)
+                c_state = None
+            else:
+                s_state, c_state = None, c_next
+        else:
+            s_state = f"correct_with_coarse_grid_solver_{d}({cgc_weight_index}, P_{d + 1}, CGS_{d + 1}, R_{d}, {c})"
+            break
+    while True:
+        for _ in range(post):
+            s_state = sm(d, False, s_state)
+        if d == 0:
+            return s_state
+        d -= 1
+        s_state = f"update_with_coarse_grid_correction_{d}({cgc_weight_index}, P_{d + 1}, {s_state}, R_{d})"
 
 
 def v_cycle_individual(levels: int, pre: int = 1, post: int = 1, weight_index: int = 18,

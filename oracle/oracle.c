@@ -23,6 +23,7 @@
 #include <omp.h>
 #endif
 #include "../include/evostencils_b200.h"
+#include "../include/evo_math.h"
 
 typedef struct Sten {
     int nnz;

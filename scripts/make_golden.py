@@ -207,5 +207,71 @@ def main():
                        "records": records}, f, indent=1)
 
 
+def main_fas():
+    """FAS golden records: the reference's FAS grammar (generate_primitive_set(..., FAS=True)) and its FAS
+    emitter (ProgramGeneratorFAS.generate_cycle_function, exastencils_FAS.py:428-439) on the shipped
+    FAS_2D_Basic template (levels 10..8 of its knowledge file)."""
+    sys.path.insert(0, REF)
+    from evostencils.code_generation.exastencils_FAS import ProgramGeneratorFAS
+    from evostencils.grammar import multigrid as mg
+    from evostencils.ir import base, system
+    from evostencils_b200 import fitness, lowering_fas, problems, tree
+    from oracle import oracle as orc
+    pg = ProgramGeneratorFAS("FAS_2D_Basic", "Solution", "RHS", "Residual", "Approximation", "RestrictionNode",
+                             "CorrectionNode", "Laplace", "gamSten", "gen_mgCycle", "CGS",
+                             build_path=os.path.join(REF, "example_problems"))
+    depth = 2
+    problem = problems.FAS2D(pg.max_level - depth, pg.max_level)
+
+    def fresh_pset():
+        approximation = system.Approximation("x", [base.Approximation(f.name, g) for f, g in zip(pg.fields, pg.finest_grid)])
+        rhs = system.RightHandSide("b", [base.RightHandSide("RHS_u", g) for g in pg.finest_grid])
+        pset, _ = mg.generate_primitive_set(approximation, rhs, pg.dimension, pg.coarsening_factor, pg.max_level,
+                                            pg.equations, pg.operators, pg.fields, depth=depth, FAS=True)
+        return pset
+    strings = [tree.fas_v_cycle_individual(depth, 2, 2, 14, 1, "single"),
+               tree.fas_v_cycle_individual(depth, 1, 1, 14, 2, "single"),
+               tree.fas_v_cycle_individual(depth, 2, 1, 10, 0, "red_black"),
+               tree.fas_v_cycle_individual(depth, 1, 2, 16, 3, "red_black")]
+    rng = random.Random(4242)
+    tries = 0
+    while len(strings) < 9 and tries < 500:
+        tries += 1
+        try:
+            s, size = grow_individual(fresh_pset(), rng, size_limit=60)
+        except (RuntimeError, IndexError):
+            continue
+        strings.append(s)
+    records = []
+    ops_default = {l: problem.operator(l) for l in range(problem.min_level, problem.max_level + 1)}
+    for n, s in enumerate(strings):
+        ctx = dict(fresh_pset().context)
+        ctx.pop("__builtins__", None)
+        expression, _ = eval(s, {"__builtins__": {}}, ctx)
+        text = pg.generate_cycle_function(expression)
+        prog = lowering_fas.lower_fas_cycle(expression, problem.min_level, problem.max_level, 2,
+                                            problem.settings.cgs_max_iters, problem.settings.damping,
+                                            problem.restrict_weights(), problem.prolong_weights(), ops_default)
+        rec = {"individual": s, "exaslang": text, "program": prog.to_json()}
+        if n < 5:
+            oc = orc.OracleProblem(problem).build(prog)
+            res = oc.solve(problem.settings.tol, problem.settings.max_iters, 1)
+            t, cf, its = fitness.fas_fitness(res.residuals, res.time_ms)
+            rec["oracle"] = {"iterations": res.iterations, "status": res.status,
+                             "residuals": [float.hex(float(r)) for r in res.residuals],
+                             "convergence_factor": cf, "fitness_iterations": its}
+            print(f"fas2d: {len(prog.ops):3d} ops, iters={res.iterations:3d}, cf={cf:.6g}  {s[:70]}...")
+        else:
+            print(f"fas2d: {len(prog.ops):3d} ops  {s[:90]}...")
+        records.append(rec)
+    with open(os.path.join(ROOT, "tests", "golden", "fas2d.json"), "w") as f:
+        json.dump({"problem": "fas2d", "min_level": problem.min_level, "max_level": problem.max_level,
+                   "generator": "scripts/make_golden.py", "records": records}, f, indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if "--fas-only" not in sys.argv:
+        main()
+    else:
+        install_deap_stub()
+    main_fas()
