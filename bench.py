@@ -25,6 +25,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one stream per in-flight individual
 
 import numpy as np  # noqa: E402
 
@@ -314,6 +315,115 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: one G3P generation = 256 evolved cycles, half on Poisson 2D (levels 5..9),
+# half on LinearElasticity (levels 4..8), individuals sharded round-robin over the GPUs
+# (reference: optimization/program.py:534-535 distributes `i % nprocs == rank`).
+def population_individuals(n_total: int, seed: int = 0):
+    import random
+    from evostencils_b200 import tree
+    probs = [problems.Poisson2D(5, 9), problems.LinearElasticity2D(4, 8)]
+    rng = random.Random(seed)
+    out = []
+    for i in range(n_total):
+        prob = probs[i % 2]
+        out.append((i % 2, tree.random_individual(prob, rng, maximum_local_system_size=4)))
+    return probs, out
+
+
+def run_population(args, rank, world, local_rank):
+    from evostencils_b200 import backend, tree
+    from evostencils_b200.program_generator import B200ProgramGenerator
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    n_total = args.population
+    probs, individuals = population_individuals(n_total)
+    mine = [(k, s) for i, (k, s) in enumerate(individuals) if i % world == rank]
+    gens = [B200ProgramGenerator(problem=p, device=local_rank) for p in probs]
+    for g in gens:
+        g.initialize_code_generation(g.min_level, g.max_level)
+    # host side of the hot path: string -> tree -> lowered program (done per step, inside the e2e region)
+    def lower_all():
+        progs = [[], []]
+        for k, s in mine:
+            progs[k].append(gens[k].lower(tree.build_tree(probs[k], s), gens[k].min_level))
+        return progs
+    progs = lower_all()
+
+    def evaluate(progs):
+        ms, res, launches0 = 0.0, [], sum(g.total_kernel_launches for g in gens)
+        for k in (0, 1):
+            r, t = gens[k].evaluate_population([], programs=progs[k], max_in_flight=args.in_flight)
+            ms += t
+            res += r
+        return ms, res, sum(g.total_kernel_launches for g in gens) - launches0
+
+    for _ in range(args.warmup):
+        evaluate(progs)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_dev, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, res, ln = evaluate(progs)
+        t_dev += ms
+        launches += ln
+    barrier()
+    t_wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: strings -> trees -> lowering -> build -> solve -> fitness tuples on the host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        evaluate(lower_all())
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_dev, t_wall, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_wall, t_e2e = [float(v) for v in t.tolist()]
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+    if rank == 0:
+        evals = n_total * args.steps
+        converged = sum(1 for r in res if r[1] < 1)
+        line = {"metric": METRIC, "value": evals / t_wall, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_wall * 1e3 / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "population", "individuals": n_total,
+                           "problems": "Poisson 2D levels 9..5 (513^2) + LinearElasticity 2D levels 8..4 (257^2, 2 fields), alternating",
+                           "generator": "evostencils_b200.tree.random_individual, seed 0, local systems <= 4",
+                           "tol": 1e-12, "max_iters": 100, "in_flight_per_gpu": args.in_flight,
+                           "parallelism": f"population sharded round-robin over {world} GPU(s)",
+                           "l2_policy": "working sets fit L2 (latency / launch bound regime; no flush)"},
+                "device_busy_ms_per_step": t_dev / args.steps,
+                "e2e": {"value": evals / t_e2e, "unit": "evals/s",
+                        "h2d_bytes_per_step": sum(len(p.ops) * 160 + len(p.operators) * 1736 for ps in progs for p in ps),
+                        "d2h_bytes_per_step": len(mine) * (101 * 8 + 48),
+                        "note": "grammar strings -> trees -> lowering -> evo_cycle_build -> evo_batch_solve -> fitness tuples"},
+                "gpu_launches": launches, "clocks": clocks, "converging_individuals_rank0": converged,
+                "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -321,6 +431,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="poisson3d_513")
+    ap.add_argument("--population", type=int, default=256)
+    ap.add_argument("--in-flight", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch kernels directly (host-side solver loop) so that ncu can see them; not a bench value")
@@ -328,7 +440,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "population" and args.impl != "reference":
+        run_population(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

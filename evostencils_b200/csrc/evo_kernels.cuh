@@ -168,8 +168,16 @@ struct SmoothParams {
     double omega;
 };
 
+// LU factorisation with partial pivoting, reciprocal pivots (one division per pivot); the factorisation
+// depends only on M, so callers with a node-independent matrix hoist it out of their loops
+template <typename T, int NU> struct DenseLU {
+    T lu[NU][NU];   // unit-lower factors below the diagonal, U on and above
+    T inv[NU];      // reciprocal pivots
+    int piv[NU];    // row exchanged with row c at step c
+};
+
 template <typename T, int NU>
-__device__ __forceinline__ void solve_dense(T (&M)[NU][NU], T (&b)[NU])
+__device__ __forceinline__ void dense_factor(T (&M)[NU][NU], DenseLU<T, NU> &f)
 {
 #pragma unroll
     for (int c = 0; c < NU; ++c) {
@@ -180,31 +188,64 @@ __device__ __forceinline__ void solve_dense(T (&M)[NU][NU], T (&b)[NU])
             double v = abs2(M[r][c]);
             if (v > best) { best = v; piv = r; }
         }
+        f.piv[c] = piv;
         if (piv != c) {
 #pragma unroll
             for (int r = 0; r < NU; ++r) {
                 if (r == piv) {
 #pragma unroll
                     for (int k = 0; k < NU; ++k) { T t = M[c][k]; M[c][k] = M[r][k]; M[r][k] = t; }
-                    T t = b[c]; b[c] = b[r]; b[r] = t;
                 }
             }
         }
+        f.inv[c] = T(1.0) / M[c][c];
 #pragma unroll
         for (int r = c + 1; r < NU; ++r) {
-            T fac = M[r][c] / M[c][c];
+            T fac = M[r][c] * f.inv[c];
+            M[r][c] = fac;
 #pragma unroll
             for (int k = c + 1; k < NU; ++k) M[r][k] = M[r][k] - fac * M[c][k];
-            b[r] = b[r] - fac * b[c];
         }
     }
 #pragma unroll
-    for (int c = NU - 1; c >= 0; --c) {
-        T s = b[c];
+    for (int r = 0; r < NU; ++r)
 #pragma unroll
-        for (int k = c + 1; k < NU; ++k) s = s - M[c][k] * b[k];
-        b[c] = s / M[c][c];
+        for (int k = 0; k < NU; ++k) f.lu[r][k] = M[r][k];
+}
+
+template <typename T, int NU>
+__device__ __forceinline__ void dense_solve(const DenseLU<T, NU> &f, T (&b)[NU])
+{
+    // P b first (the stored factors are in their final row order), then forward substitution: element for
+    // element the same operations as an elimination that carries b along
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+        if (f.piv[c] != c) {
+#pragma unroll
+            for (int r = 0; r < NU; ++r)
+                if (r == f.piv[c]) { T t = b[c]; b[c] = b[r]; b[r] = t; }
+        }
     }
+#pragma unroll
+    for (int c = 0; c < NU; ++c) {
+#pragma unroll
+        for (int r = c + 1; r < NU; ++r) b[r] = b[r] - f.lu[r][c] * b[c];
+    }
+#pragma unroll
+    for (int c = NU - 1; c >= 0; --c) {
+        T sacc = b[c];
+#pragma unroll
+        for (int k = c + 1; k < NU; ++k) sacc = sacc - f.lu[c][k] * b[k];
+        b[c] = sacc * f.inv[c];
+    }
+}
+
+template <typename T, int NU>
+__device__ __forceinline__ void solve_dense(T (&M)[NU][NU], T (&b)[NU])
+{
+    DenseLU<T, NU> f;
+    dense_factor<T, NU>(M, f);
+    dense_solve<T, NU>(f, b);
 }
 
 // local solve at one anchor; identical construction to oracle/mg_ops.inc local_solve_anchor
@@ -497,6 +538,223 @@ __global__ void __launch_bounds__(1024) k_coarse_cg(const Geom g, const __grid_c
         }
     }
     if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory resident CG for coarsest levels that fit (4 vectors x fields x n^d doubles): the
+// global-memory version above spends ~7 us per iteration on dependent global round trips; here a CG
+// iteration is 5 block barriers.  Same arithmetic and the same canonical reductions -> bit-identical.
+template <int DIM, int NF>
+__global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __grid_constant__ OpSten st, Fields<double> xg,
+                                                         Fields<double> bg, int max_it, double tol, int *iters_out)
+{
+    extern __shared__ double sm[];
+    __shared__ double rowsum[1024];
+    __shared__ double planes[64];
+    const int n = g.n, ni = n - 2, nzi = DIM == 3 ? ni : 1;
+    const int vol = n * n * (DIM == 3 ? n : 1);          // compact (unpadded) node count incl. boundary
+    const int nrows = ni * nzi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *x = sm, *r = sm + (size_t)NF * vol, *p = sm + 2 * (size_t)NF * vol, *ap = sm + 3 * (size_t)NF * vol;
+    // compact index of node (ix, iy, iz): (iz*n + iy)*n + ix
+    for (int t = threadIdx.x; t < 4 * NF * vol; t += 1024) sm[t] = 0.0;
+    __syncthreads();
+    for (int i = 0; i < NF; ++i)
+        for (int row = warp; row < nrows; row += 32) {
+            const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+            for (int xx = 1 + lane; xx <= ni; xx += 32) {
+                const double v = bg.p[i][node_index(g, xx, y, z)];
+                const int c = i * vol + (z * n + y) * n + xx;
+                r[c] = v; p[c] = v;
+            }
+        }
+    __syncthreads();
+    // second and third level of the canonical reduction over rowsum[field][row].  2-D: after ONE barrier
+    // every warp recomputes the (identical) final vecsum itself -- no broadcast; the row-sum buffer is
+    // double buffered (rs_flip) so the next pass may overwrite the other half without a second barrier.
+    int rs_flip = 0;
+    auto finish = [&]() {
+        double total = 0.0;
+        __syncthreads();
+        const double *rs = rowsum + rs_flip * 512;
+        for (int i = 0; i < NF; ++i) {
+            if (DIM == 3) {
+                for (int zz = warp; zz < nzi; zz += 32) {
+                    double sacc = warp_vecsum(rs + i * nrows + zz * ni, ni);
+                    if (lane == 0) planes[zz] = sacc;
+                }
+                __syncthreads();
+                total = total + warp_vecsum(planes, nzi);
+                __syncthreads();
+            } else {
+                total = total + warp_vecsum(rs + i * nrows, ni);
+            }
+        }
+        rs_flip ^= 1;
+        return total;
+    };
+    // r.r
+    for (int i = 0; i < NF; ++i)
+        for (int row = warp; row < nrows; row += 32) {
+            const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+            double acc = 0.0;
+            for (int xx = 1 + lane; xx <= ni; xx += 32) {
+                const int c = i * vol + (z * n + y) * n + xx;
+                acc = acc + r[c] * r[c];
+            }
+            acc = warp_butterfly(acc);
+            if (lane == 0) rowsum[rs_flip * 512 + i * nrows + row] = acc;
+        }
+    double rr = finish();
+    const double r0 = sqrt(rr);
+    int it = 0;
+    if (r0 != 0.0) {
+        while (it < max_it) {
+            // pass A: ap = A p and the row sums of p.ap
+            for (int i = 0; i < NF; ++i)
+                for (int row = warp; row < nrows; row += 32) {
+                    const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+                    double acc = 0.0;
+                    for (int xx = 1 + lane; xx <= ni; xx += 32) {
+                        const int c0 = (z * n + y) * n + xx;
+                        double a = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NF; ++j) {
+                            const Sten &sj = st.s[i][j];
+                            for (int q = 0; q < sj.nnz; ++q)
+                                a = a + sj.re[q] * p[j * vol + c0 + (sj.oz[q] * n + sj.oy[q]) * n + sj.ox[q]];
+                        }
+                        ap[i * vol + c0] = a;
+                        acc = acc + p[i * vol + c0] * a;
+                    }
+                    acc = warp_butterfly(acc);
+                    if (lane == 0) rowsum[rs_flip * 512 + i * nrows + row] = acc;
+                }
+            const double pap = finish();
+            const double alpha = rr / pap;
+            // pass B: x += alpha p, r -= alpha ap and the row sums of r.r
+            for (int i = 0; i < NF; ++i)
+                for (int row = warp; row < nrows; row += 32) {
+                    const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+                    double acc = 0.0;
+                    for (int xx = 1 + lane; xx <= ni; xx += 32) {
+                        const int c = i * vol + (z * n + y) * n + xx;
+                        x[c] = x[c] + alpha * p[c];
+                        const double rv = r[c] - alpha * ap[c];
+                        r[c] = rv;
+                        acc = acc + rv * rv;
+                    }
+                    acc = warp_butterfly(acc);
+                    if (lane == 0) rowsum[rs_flip * 512 + i * nrows + row] = acc;
+                }
+            const double rr_new = finish();
+            ++it;
+            if (!(sqrt(rr_new) > tol * r0)) break;
+            const double beta = rr_new / rr;
+            for (int t = threadIdx.x; t < NF * vol; t += 1024) p[t] = r[t] + beta * p[t];   // boundary entries stay 0
+            rr = rr_new;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // x -> SOL (inner nodes; the boundary layer of SOL is 0 on the coarsest level and stays so)
+    for (int i = 0; i < NF; ++i)
+        for (int row = warp; row < nrows; row += 32) {
+            const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+            for (int xx = 1 + lane; xx <= ni; xx += 32) xg.p[i][node_index(g, xx, y, z)] = x[i * vol + (z * n + y) * n + xx];
+        }
+    if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Order-dependent coloured pointwise sweep of a 2-D system (collective RB-GS on the elasticity system),
+// rolling shared-memory window: the sequential chain is one block barrier per row instead of a global
+// memory round trip per row.  Rows j-1 (already updated), j and j+1 (old values) are in shared memory,
+// row j+3 is fetched by cp.async two steps ahead; results go to shared memory (for the next row) and to
+// global memory.  Unknown a == field a at the anchor node (NU == NF); arithmetic identical to
+// local_solve (same (j, q) order, same dense solve).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NF>
+__global__ void __launch_bounds__(1024) k2_smooth_rowseq_win(const Geom g, const __grid_constant__ OpSten st, const double omega,
+                                                             Fields<double> u, Fields<double> rhs)
+{
+    extern __shared__ __align__(16) double win[];   // [5 slots][2*NF arrays][pitch]
+    const int n = g.n, pitch = g.pitch;
+    const int chunks = pitch / 2;                    // 16-byte chunks per row
+    auto slot_u = [&](int row, int f) { return win + ((size_t)(row % 5) * 2 * NF + f) * pitch; };
+    auto slot_f = [&](int row, int f) { return win + ((size_t)(row % 5) * 2 * NF + NF + f) * pitch; };
+    auto fetch = [&](int row) {
+        if (row >= 0 && row <= n - 1)
+            for (int t = threadIdx.x; t < 2 * NF * chunks; t += 1024) {
+                const int a = t / chunks, c = t - a * chunks;
+                const double *src = (a < NF ? u.p[a] : rhs.p[a - NF]) + (long long)row * pitch + 2 * c;
+                cp_async16(win + ((size_t)(row % 5) * 2 * NF + a) * pitch + 2 * c, src);
+            }
+        cp_async_commit();
+    };
+    // the local matrix (diagonal entries of the blocks) is the same at every anchor: factor it once
+    double M0[NF][NF];
+#pragma unroll
+    for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int m = 0; m < NF; ++m) M0[a][m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const Sten &sj = st.s[a][j];
+            for (int q = 0; q < sj.nnz; ++q)
+                if (sj.ox[q] == 0 && sj.oy[q] == 0) {
+#pragma unroll
+                    for (int m = 0; m < NF; ++m)
+                        if (m == j) M0[a][m] = M0[a][m] + sj.re[q];
+                }
+        }
+    DenseLU<double, NF> lu;
+    dense_factor<double, NF>(M0, lu);
+    for (int color = 0; color < 2; ++color) {
+        __threadfence();
+        __syncthreads();
+        fetch(0); fetch(1); fetch(2);
+        for (int y = 1; y <= n - 2; ++y) {
+            fetch(y + 2);
+            cp_async_wait<1>();      // everything but the newest group (row y+2) has landed
+            __syncthreads();         // ... for all threads; row y-1 results of the previous step are visible
+            for (int t = threadIdx.x;; t += 1024) {
+                const int x = 1 + 2 * t + ((1 + y + color) & 1);
+                if (x > n - 2) break;
+                double b[NF];
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        const Sten &sj = st.s[a][j];
+                        for (int q = 0; q < sj.nnz; ++q)
+                            if (!(sj.ox[q] == 0 && sj.oy[q] == 0)) sacc = sacc + sj.re[q] * slot_u(y + sj.oy[q], j)[x + sj.ox[q]];
+                    }
+                    b[a] = slot_f(y, a)[x] - sacc;
+                }
+                if (NF == 1) b[0] = b[0] * lu.inv[0];
+                else dense_solve<double, NF>(lu, b);
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    const double old = slot_u(y, a)[x];
+                    const double nv = old + omega * (b[a] - old);
+                    slot_u(y, a)[x] = nv;
+                    u.p[a][(long long)y * pitch + x] = nv;
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
 }
 
 }  // namespace evo

@@ -21,6 +21,14 @@
 
 using namespace evo;
 
+// Many individuals are evaluated concurrently, one stream each: the default of 8 hardware work queues
+// would serialise unrelated streams, so ask for the maximum before the CUDA context is created.
+namespace {
+struct EnvInit {
+    EnvInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_env_init;
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...)
@@ -83,6 +91,8 @@ struct evo_problem {
     void *init_sol[EVO_MAX_FIELDS];  // pristine finest-level SOL (incl. boundary values), padded layout
     void *rhs0[EVO_MAX_FIELDS];      // finest-level RHS, read-only, shared by all cycles
     std::vector<std::pair<void *, size_t>> pool;  // recycled cycle work slabs
+    int live_cycles = 0;                          // cycles still referring to this problem
+    bool closed = false;                          // evo_problem_destroy called while cycles were alive
 };
 
 struct LevelMem {
@@ -199,14 +209,22 @@ extern "C" int evo_problem_create(const evo_problem_desc *d, evo_problem **out)
     return EVO_OK;
 }
 
+static void free_problem(evo_problem *p);
+
 extern "C" int evo_problem_destroy(evo_problem *p)
 {
     if (!p) return EVO_OK;
+    if (p->live_cycles > 0) { p->closed = true; return EVO_OK; }   // freed when its last cycle goes
+    free_problem(p);
+    return EVO_OK;
+}
+
+static void free_problem(evo_problem *p)
+{
     cudaSetDevice(p->desc.device);
     for (int i = 0; i < EVO_MAX_FIELDS; ++i) { cudaFree(p->init_sol[i]); cudaFree(p->rhs0[i]); }
     for (auto &s : p->pool) cudaFree(s.first);
     delete p;
-    return EVO_OK;
 }
 
 // dense host array (n^dim entries, x fastest) <-> padded device array
@@ -437,7 +455,25 @@ template <typename T, int DIM, int NF> struct Launch {
                 auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF);
                 if (color_order_dependent(c->sten[l], sp, NF)) {
                     if constexpr (NU == NF) {
-                        k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
+                        bool done = false;
+                        if constexpr (DIM == 2 && std::is_same<T, double>::value) {
+                            // unknown a must be field a at the anchor (collective pointwise smoother)
+                            bool canonical = true;
+                            for (int a = 0; a < NU; ++a)
+                                if (sp.field[a] != a || sp.off[a][0] || sp.off[a][1] || sp.off[a][2]) canonical = false;
+                            const size_t smem = (size_t)5 * 2 * NF * g.pitch * sizeof(double);
+                            static const bool disabled = getenv("EVO_ROWSEQ_GLOBAL") != nullptr;
+                            if (canonical && !disabled && smem <= 200 * 1024) {
+                                static bool attr = false;
+                                if (!attr) {
+                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_win<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                    attr = true;
+                                }
+                                k2_smooth_rowseq_win<NF><<<1, 1024, smem, s>>>(g, c->sten[l], sp.omega, u, rhs);
+                                done = true;
+                            }
+                        }
+                        if (!done) k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
                         c->launch_counter++;
                     } else {
                         return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
@@ -563,6 +599,25 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
     const Geom &g = c->p->geom[l];
     if (l != c->p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
     auto x = fields_of<double>(c->lv[l].buf[EVO_BUF_SOL], NF), b = fields_of<double>(c->lv[l].buf[EVO_BUF_RHS], NF);
+    {
+        // shared-memory resident variant when the four CG vectors fit
+        const int ni = g.n - 2;
+        const size_t vol = (size_t)g.n * g.n * (DIM == 3 ? g.n : 1);
+        const size_t smem = 4 * NF * vol * sizeof(double);
+        const int nrows = ni * (DIM == 3 ? ni : 1);
+        static const bool disabled = getenv("EVO_CG_GLOBAL") != nullptr;
+        if (!disabled && smem <= 160 * 1024 && NF * nrows <= 512 && (DIM == 2 || ni <= 64)) {
+            static bool attr = false;
+            if (!attr) {
+                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr = true;
+            }
+            k_coarse_cg_smem<DIM, NF><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
+            c->launch_counter++;
+            CU(cudaGetLastError());
+            return EVO_OK;
+        }
+    }
     auto r = fields_of<double>(c->krylov[0], NF), p = fields_of<double>(c->krylov[1], NF), ap = fields_of<double>(c->krylov[2], NF);
     k_coarse_cg<DIM, NF><<<1, 1024, 0, s>>>(g, c->sten[l], x, b, r, p, ap, (double *)c->krylov[3][0], op.count, op.tol,
                                             c->d_cg_iters);
@@ -788,8 +843,10 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
 {
     if (!p || !out || (n_ops > 0 && !ops) || (n_operators > 0 && !operators)) return fail(EVO_ERR_INVALID, "null argument");
     CU(cudaSetDevice(p->desc.device));
+    if (p->closed) return fail(EVO_ERR_INVALID, "problem already destroyed");
     evo_cycle *c = new evo_cycle();
     c->p = p;
+    p->live_cycles++;
     // consecutive identical `solve locally` statements become one op with a repeat count (the kernels
     // fuse repeated sweeps; semantics are unchanged)
     for (int t = 0; t < n_ops; ++t) {
@@ -816,7 +873,7 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
     memset(c->lv, 0, sizeof(c->lv));
     for (int t = 0; t < n_operators; ++t) {
         const int l = operators[t].level;
-        if (l < p->desc.min_level || l > p->desc.max_level) { delete c; return fail(EVO_ERR_INVALID, "operator level %d out of range", l); }
+        if (l < p->desc.min_level || l > p->desc.max_level) { p->live_cycles--; delete c; return fail(EVO_ERR_INVALID, "operator level %d out of range", l); }
         OpSten &os = c->sten[l];
         memset(&os, 0, sizeof(os));
         for (int i = 0; i < p->desc.n_fields; ++i)
@@ -826,7 +883,7 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
                     double re = operators[t].coef[i][j][q][0], im = operators[t].coef[i][j][q][1];
                     if (re == 0.0 && im == 0.0) continue;
                     int oz = q / 9 - 1;
-                    if (p->desc.dim == 2 && oz != 0) { delete c; return fail(EVO_ERR_INVALID, "3-D stencil entry in a 2-D problem"); }
+                    if (p->desc.dim == 2 && oz != 0) { p->live_cycles--; delete c; return fail(EVO_ERR_INVALID, "3-D stencil entry in a 2-D problem"); }
                     int k = s.nnz++;
                     s.ox[k] = (signed char)(q % 3 - 1); s.oy[k] = (signed char)((q / 3) % 3 - 1); s.oz[k] = (signed char)oz;
                     s.re[k] = re; s.im[k] = im;
@@ -880,7 +937,9 @@ extern "C" int evo_cycle_destroy(evo_cycle *c)
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_hist) cudaFreeHost(c->h_hist);
     if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream); }
+    evo_problem *p = c->p;
     delete c;
+    if (--p->live_cycles == 0 && p->closed) free_problem(p);
     return EVO_OK;
 }
 
@@ -1164,7 +1223,6 @@ extern "C" int evo_batch_solve(evo_cycle **cycles, int n, const evo_solve_params
     if (!cycles || !prm || !results || n < 0) return fail(EVO_ERR_INVALID, "null argument");
     if (n == 0) { if (batch_ms) *batch_ms = 0.0; return EVO_OK; }
     if (prm->flags & EVO_SOLVE_NO_GRAPH) return fail(EVO_ERR_UNSUPPORTED, "batch solve needs the device-side outer loop");
-    for (int i = 0; i < n; ++i) EV(prepare_solve(cycles[i], prm));
     const int samples = prm->samples > 0 ? prm->samples : 1;
     std::vector<std::vector<float>> times(n);
     std::vector<float> wall;
@@ -1176,6 +1234,8 @@ extern "C" int evo_batch_solve(evo_cycle **cycles, int n, const evo_solve_params
         // fork: all streams wait for b0 on stream 0; join: stream 0 waits for every ev1
         CU(cudaEventRecord(b0, s0));
         for (int i = 0; i < n; ++i) {
+            // graph capture / instantiation of individual i overlaps with the solves already in flight
+            EV(prepare_solve(cycles[i], prm));
             if (i) CU(cudaStreamWaitEvent(cycles[i]->stream, b0, 0));
             EV(enqueue_solve(cycles[i], prm));
         }
