@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "evo_problem_create", "evo_problem_destroy", "evo_problem_set_field",
     "evo_cycle_build", "evo_cycle_destroy", "evo_cycle_reset", "evo_cycle_apply",
     "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm", "evo_cycle_profile_op",
-    "evo_cycle_solve", "evo_batch_solve",
+    "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
 )
 
 _lib = None
@@ -66,6 +66,8 @@ def load_library(path: Optional[str] = None):
                                          C.POINTER(C.c_int64)]
     lib.evo_cycle_solve.argtypes = [C.c_void_p, C.POINTER(ol.CEvoSolveParams), C.POINTER(ol.CEvoSolveResult),
                                     C.POINTER(C.c_double)]
+    lib.evo_helmholtz_solve.argtypes = [C.c_void_p, C.POINTER(ol.CEvoLevelOperator), C.POINTER(ol.CEvoSolveParams),
+                                        C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double)]
     lib.evo_batch_solve.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(ol.CEvoSolveParams),
                                     C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if lib.evo_abi_version() != ol.ABI_VERSION:
@@ -184,6 +186,22 @@ class DeviceCycle:
         _check(self._lib, self._lib.evo_cycle_solve(self._h, C.byref(prm), C.byref(res),
                                                     hist.ctypes.data_as(C.POINTER(C.c_double))), "evo_cycle_solve")
         return SolveOutcome(res, hist)
+
+
+def _helmholtz_solve(cycle: "DeviceCycle", tol: float, max_iters: int, samples: int = 1) -> SolveOutcome:
+    prob = cycle.problem.problem
+    outer = ol.Program(dim=2, n_fields=1, min_level=prob.max_level, max_level=prob.max_level,
+                       operators={prob.max_level: prob.outer_operator(prob.max_level)})
+    arr, _ = outer.c_operators()
+    prm = ol.CEvoSolveParams(tol, max_iters, samples, 0, 0)
+    res = ol.CEvoSolveResult()
+    hist = np.zeros(max_iters + 1, dtype=np.float64)
+    _check(cycle._lib, cycle._lib.evo_helmholtz_solve(cycle._h, arr, C.byref(prm), C.byref(res),
+                                                      hist.ctypes.data_as(C.POINTER(C.c_double))), "evo_helmholtz_solve")
+    return SolveOutcome(res, hist)
+
+
+DeviceCycle.helmholtz_solve = _helmholtz_solve
 
 
 class DeviceProblem:

@@ -18,6 +18,7 @@
 #include "evo_kernels.cuh"
 #include "evo_kernels_star.cuh"
 #include "evo_kernels_fas.cuh"
+#include "evo_kernels_helm.cuh"
 
 using namespace evo;
 
@@ -111,6 +112,13 @@ struct evo_cycle {
     size_t slab_bytes;
     void *krylov[8][EVO_MAX_FIELDS];  // coarsest-level Krylov vectors
     void *scratch[EVO_MAX_FIELDS];    // finest-level scratch field (Richardson)
+    void *helm[9];                    // Helmholtz outer solver: x, r, p, ap, s, t, h, rhat, row sums
+    helm::HelmState *d_helm;
+    OpSten helm_A;                    // un-shifted operator of the finest level
+    cudaGraph_t helm_graph;
+    cudaGraphExec_t helm_exec;
+    double helm_tol;
+    int helm_max_iters;
     SolveState *d_state;
     double *d_hist;
     int hist_cap;
@@ -299,7 +307,8 @@ static int allocate_cycle(evo_cycle *c)
             const bool slot = level_needs_slot(c, l);
             for (int i = 0; i < nf; ++i) {
                 c->lv[l].buf[EVO_BUF_SOL][i] = take(fb);
-                c->lv[l].buf[EVO_BUF_RHS][i] = l == hi ? (pass ? p->rhs0[i] : nullptr) : take(fb);
+                c->lv[l].buf[EVO_BUF_RHS][i] = (l == hi && p->desc.kind != EVO_PROBLEM_HELMHOLTZ)
+                                                   ? (pass ? p->rhs0[i] : nullptr) : take(fb);   // Helmholtz: f is rewritten per application
                 c->lv[l].buf[EVO_BUF_RES][i] = take(fb);
                 c->lv[l].buf[EVO_BUF_COR][i] = (l == hi && uses_buffer(c, l, EVO_BUF_COR)) ? take(fb) : c->lv[l].buf[EVO_BUF_SOL][i];
                 c->lv[l].buf[EVO_BUF_APX][i] = (p->desc.kind == EVO_PROBLEM_FAS) ? take(fb) : nullptr;
@@ -310,6 +319,11 @@ static int allocate_cycle(evo_cycle *c)
         const size_t cb = (size_t)p->geom[lo].total * esz;
         for (int v = 0; v < 8; ++v)
             for (int i = 0; i < nf; ++i) c->krylov[v][i] = take(cb);
+        if (p->desc.kind == EVO_PROBLEM_HELMHOLTZ) {
+            const size_t fbh = (size_t)p->geom[hi].total * esz;
+            for (int v = 0; v < 9; ++v) c->helm[v] = take(fbh);
+            c->d_helm = (helm::HelmState *)take(sizeof(helm::HelmState));
+        }
         c->d_state = (SolveState *)take(sizeof(SolveState));
         c->d_cg_iters = (int *)take(256);
         const Geom &gf = p->geom[hi];
@@ -626,6 +640,8 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
     return EVO_OK;
 }
 
+static cplx helm_rden(const evo_problem *p, int level);
+
 template <typename T, int DIM, int NF> static int enqueue_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
 {
     using L = Launch<T, DIM, NF>;
@@ -650,8 +666,20 @@ template <typename T, int DIM, int NF> static int enqueue_op(evo_cycle *c, const
     case EVO_OP_PROLONG_ADD: return L::prolong(c, op, true, s);
     case EVO_OP_PROLONG_SET: return L::prolong(c, op, false, s);
     case EVO_OP_COARSE_SOLVE:
-        if (sizeof(T) == sizeof(double)) return coarse_cg<DIM, NF>(c, op, s);
-        return fail(EVO_ERR_UNSUPPORTED, "complex coarse-grid solver not implemented yet");
+        if constexpr (std::is_same<T, double>::value) {
+            return coarse_cg<DIM, NF>(c, op, s);
+        } else {
+            if (l != p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
+            const Geom &g = p->geom[l];
+            helm::k2_coarse_bicgstab<<<1, 1024, 0, s>>>(
+                g, c->sten[l], helm_rden(p, l), (cplx *)c->lv[l].buf[EVO_BUF_SOL][0], (const cplx *)c->lv[l].buf[EVO_BUF_RHS][0],
+                (cplx *)c->lv[l].buf[EVO_BUF_RES][0], (cplx *)c->krylov[0][0], (cplx *)c->krylov[1][0], (cplx *)c->krylov[2][0],
+                (cplx *)c->krylov[3][0], (cplx *)c->krylov[4][0], (cplx *)c->krylov[5][0], (cplx *)c->krylov[6][0], op.count, op.tol,
+                p->desc.kind == EVO_PROBLEM_HELMHOLTZ ? 1 : 0);
+            c->launch_counter++;
+            CU(cudaGetLastError());
+            return EVO_OK;
+        }
     default: return fail(EVO_ERR_UNSUPPORTED, "op code %d not implemented", op.code);
     }
 }
@@ -751,7 +779,46 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
     }
 }
 
+// 1 / (1 - i k h) by Smith's algorithm, the same operation sequence as the oracle's cdiv_smith(1.0, den)
+static cplx helm_rden(const evo_problem *p, int level)
+{
+    const double h = 1.0 / (double)(1 << level);
+    // I * k = (0*kr - 1*ki) + (0*ki + 1*kr) i ; times h ; den = 1.0 - that
+    const double kr = p->desc.k_re, ki = p->desc.k_im;
+    const double ikr = 0.0 * kr - 1.0 * ki, iki = 0.0 * ki + 1.0 * kr;
+    const cplx den(1.0 - ikr * h, 0.0 - iki * h);
+    return cplx(1.0, 0.0) / den;
+}
+
+static int helm_bc(evo_cycle *c, int level, void *field, cudaStream_t s)
+{
+    const Geom &g = c->p->geom[level];
+    helm::k2_helm_bc<<<(g.n + 127) / 128, 128, 0, s>>>(g, (cplx *)field, helm_rden(c->p, level));
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+static int dispatch_op_inner(evo_cycle *c, const evo_op &op, cudaStream_t s);
+
+// Helmholtz: u / gen_error_u / gen_residual_u carry the Robin boundary function; it is applied after every
+// statement that writes one of them (same rule as oracle helm_bc_after_op)
 static int dispatch_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
+{
+    EV(dispatch_op_inner(c, op, s));
+    if (c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ) return EVO_OK;
+    int buf = -1;
+    switch (op.code) {
+    case EVO_OP_ZERO: case EVO_OP_COPY: case EVO_OP_PROLONG_SET: buf = op.dst; break;
+    case EVO_OP_SMOOTH: case EVO_OP_RICHARDSON: case EVO_OP_PROLONG_ADD: case EVO_OP_COARSE_SOLVE: buf = EVO_BUF_SOL; break;
+    case EVO_OP_RESIDUAL: buf = EVO_BUF_RES; break;
+    default: return EVO_OK;
+    }
+    if (buf == EVO_BUF_RHS) return EVO_OK;
+    return helm_bc(c, op.level, c->lv[op.level].buf[buf][0], s);
+}
+
+static int dispatch_op_inner(evo_cycle *c, const evo_op &op, cudaStream_t s)
 {
     const evo_problem_desc &d = c->p->desc;
     if (d.kind == EVO_PROBLEM_FAS) {
@@ -852,7 +919,8 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
     for (int t = 0; t < n_ops; ++t) {
         evo_op op = ops[t];
         if (op.code == EVO_OP_SMOOTH && op.count < 1) op.count = 1;
-        if (!c->ops.empty() && op.code == EVO_OP_SMOOTH && op.kind == EVO_KIND_LINEAR) {
+        // (not for Helmholtz: the Robin boundary function is re-applied between two statements)
+        if (!c->ops.empty() && op.code == EVO_OP_SMOOTH && op.kind == EVO_KIND_LINEAR && p->desc.kind != EVO_PROBLEM_HELMHOLTZ) {
             evo_op &prev = c->ops.back();
             evo_op a = prev, b = op;
             a.count = b.count = 0;
@@ -869,6 +937,10 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
     c->d_hist = nullptr;
     c->hist_cap = 0;
     c->use_while_graph = true;
+    c->helm_graph = nullptr;
+    c->helm_exec = nullptr;
+    c->d_helm = nullptr;
+    for (int v = 0; v < 9; ++v) c->helm[v] = nullptr;
     memset(c->has_sten, 0, sizeof(c->has_sten));
     memset(c->lv, 0, sizeof(c->lv));
     for (int t = 0; t < n_operators; ++t) {
@@ -924,6 +996,8 @@ extern "C" int evo_cycle_destroy(evo_cycle *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->exec) cudaGraphExecDestroy(c->exec);
     if (c->graph) cudaGraphDestroy(c->graph);
+    if (c->helm_exec) cudaGraphExecDestroy(c->helm_exec);
+    if (c->helm_graph) cudaGraphDestroy(c->helm_graph);
     if (c->slab) c->p->pool.push_back({c->slab, c->slab_bytes});
     // keep the pool bounded: free slabs beyond a generous budget
     size_t pooled = 0;
@@ -987,8 +1061,9 @@ extern "C" int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, 
     if (!c || !host) return fail(EVO_ERR_INVALID, "null argument");
     void *dev;
     EV(field_ptr(c, level, buf, field, &dev));
-    if (level == c->p->desc.max_level && buf == EVO_BUF_RHS)
-        return fail(EVO_ERR_UNSUPPORTED, "the finest right-hand side is shared by all cycles: use evo_problem_set_field");
+    if (level == c->p->desc.max_level && buf == EVO_BUF_RHS && c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ)
+        if (c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ)
+            return fail(EVO_ERR_UNSUPPORTED, "the finest right-hand side is shared by all cycles: use evo_problem_set_field");
     const Geom &g = c->p->geom[level];
     if (n_doubles != (size_t)g.n * g.n * g.nz * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
     CU(cudaSetDevice(c->p->desc.device));
@@ -1208,6 +1283,202 @@ extern "C" int evo_cycle_solve(evo_cycle *c, const evo_solve_params *prm, evo_so
         EV(collect_solve(c, prm, res, res_hist, &ms));
         times.push_back(ms);
     }
+    std::sort(times.begin(), times.end());
+    res->time_ms = times[times.size() / 2];
+    res->time_ms_min = times[0];
+    return EVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Helmholtz: outer PreconditionedBiCGStab@finest (exa3:144-200) with the cycle as preconditioner, one CUDA
+// graph: prologue + WHILE(!done) { one BiCGStab iteration = 2 cycle applications }
+static int helm_dot(evo_cycle *c, const cplx *a, const cplx *b, int slot, cudaStream_t s)
+{
+    const Geom &g = c->p->geom[c->p->desc.max_level];
+    const int ni = g.n - 2;
+    helm::k2_cdot_rows<<<(ni + 3) / 4, 128, 0, s>>>(g, a, b, (cplx *)c->helm[8]);
+    helm::k2_cdot_final<<<1, 32, 0, s>>>((const cplx *)c->helm[8], ni, c->d_helm, slot);
+    c->launch_counter += 2;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+static int helm_precondition(evo_cycle *c, const cplx *src, cudaStream_t s)
+{
+    // u = 0; f = src; gen_mgCycle()
+    const int hi = c->p->desc.max_level;
+    const Geom &g = c->p->geom[hi];
+    CU(cudaMemsetAsync(c->lv[hi].buf[EVO_BUF_SOL][0], 0, (size_t)g.total * sizeof(cplx), s));
+    helm::k2_helm_vec<<<row_grid(g), BX, 0, s>>>(g, 4, c->d_helm, (cplx *)c->lv[hi].buf[EVO_BUF_RHS][0], nullptr, src, nullptr, nullptr, nullptr);
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return enqueue_cycle(c, s);
+}
+
+static int helm_iteration(evo_cycle *c, double tol, int max_iters, cudaStream_t s)
+{
+    const int hi = c->p->desc.max_level;
+    const Geom &g = c->p->geom[hi];
+    cplx *x = (cplx *)c->helm[0], *r = (cplx *)c->helm[1], *p = (cplx *)c->helm[2], *ap = (cplx *)c->helm[3],
+         *sv = (cplx *)c->helm[4], *t = (cplx *)c->helm[5], *h = (cplx *)c->helm[6], *rh = (cplx *)c->helm[7];
+    const dim3 grid = row_grid(g);
+    EV(helm_dot(c, rh, r, 0, s));
+    helm::k_helm_scalar<<<1, 32, 0, s>>>(c->d_helm, c->d_hist, tol, max_iters, 1);
+    helm::k2_helm_vec<<<grid, BX, 0, s>>>(g, 0, c->d_helm, p, nullptr, r, ap, nullptr, nullptr);
+    c->launch_counter += 2;
+    EV(helm_precondition(c, p, s));
+    cplx *u = (cplx *)c->lv[hi].buf[EVO_BUF_SOL][0];
+    helm::k2_apply_op<<<grid, BX, 0, s>>>(g, c->helm_A, u, ap, nullptr);
+    c->launch_counter++;
+    EV(helm_dot(c, rh, ap, 1, s));
+    helm::k_helm_scalar<<<1, 32, 0, s>>>(c->d_helm, c->d_hist, tol, max_iters, 2);
+    helm::k2_helm_vec<<<grid, BX, 0, s>>>(g, 1, c->d_helm, h, sv, x, u, r, ap);
+    c->launch_counter += 2;
+    EV(helm_precondition(c, sv, s));
+    u = (cplx *)c->lv[hi].buf[EVO_BUF_SOL][0];
+    helm::k2_apply_op<<<grid, BX, 0, s>>>(g, c->helm_A, u, t, nullptr);
+    c->launch_counter++;
+    EV(helm_dot(c, t, sv, 2, s));
+    EV(helm_dot(c, t, t, 3, s));
+    helm::k_helm_scalar<<<1, 32, 0, s>>>(c->d_helm, c->d_hist, tol, max_iters, 3);
+    helm::k2_helm_vec<<<grid, BX, 0, s>>>(g, 2, c->d_helm, x, nullptr, h, u, nullptr, nullptr);
+    c->launch_counter += 2;
+    EV(helm_bc(c, hi, x, s));
+    helm::k2_helm_vec<<<grid, BX, 0, s>>>(g, 3, c->d_helm, r, nullptr, sv, t, nullptr, nullptr);
+    c->launch_counter++;
+    EV(helm_dot(c, r, r, 0, s));
+    helm::k_helm_scalar<<<1, 32, 0, s>>>(c->d_helm, c->d_hist, tol, max_iters, 4);
+    c->launch_counter++;
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+static int helm_prologue(evo_cycle *c, double tol, int max_iters, cudaStream_t s)
+{
+    const int hi = c->p->desc.max_level;
+    const Geom &g = c->p->geom[hi];
+    const size_t bytes = (size_t)g.total * sizeof(cplx);
+    cplx *x = (cplx *)c->helm[0], *r = (cplx *)c->helm[1], *rh = (cplx *)c->helm[7];
+    CU(cudaMemcpyAsync(x, c->p->init_sol[0], bytes, cudaMemcpyDeviceToDevice, s));   // Solution = 0 (+ boundary function)
+    for (int v = 2; v < 7; ++v) CU(cudaMemsetAsync(c->helm[v], 0, bytes, s));
+    CU(cudaMemsetAsync(r, 0, bytes, s));
+    EV(helm_bc(c, hi, x, s));
+    helm::k2_apply_op<<<row_grid(g), BX, 0, s>>>(g, c->helm_A, x, r, (const cplx *)c->p->rhs0[0]);   // Residual = RHS - A Solution
+    c->launch_counter++;
+    EV(helm_dot(c, r, r, 0, s));
+    helm::k_helm_scalar<<<1, 32, 0, s>>>(c->d_helm, c->d_hist, tol, max_iters, 0);
+    c->launch_counter++;
+    CU(cudaMemcpyAsync(rh, r, bytes, cudaMemcpyDeviceToDevice, s));
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+static int build_helm_graph(evo_cycle *c, double tol, int max_iters)
+{
+    if (c->helm_exec && c->helm_tol == tol && c->helm_max_iters == max_iters) return EVO_OK;
+    if (c->helm_exec) { cudaGraphExecDestroy(c->helm_exec); c->helm_exec = nullptr; }
+    if (c->helm_graph) { cudaGraphDestroy(c->helm_graph); c->helm_graph = nullptr; }
+    cudaStream_t s = c->stream;
+    c->launch_counter = 0;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc = helm_prologue(c, tol, max_iters, s);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc != EVO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "helmholtz prologue capture: %s", cudaGetErrorString(e));
+    c->kernels_prologue = c->launch_counter;
+    size_t n_nodes = 0;
+    CU(cudaGraphGetNodes(g, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes), leaves;
+    CU(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+    for (cudaGraphNode_t nd : nodes) {
+        size_t nd_dep = 0;
+        CU(cudaGraphNodeGetDependentNodes(nd, nullptr, &nd_dep));
+        if (nd_dep == 0) leaves.push_back(nd);
+    }
+    cudaGraphConditionalHandle handle;
+    CU(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNode_t cond_init, wnode;
+    {
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        void *args[2] = {(void *)&handle, (void *)&c->d_helm};
+        kp.func = (void *)helm::k_set_while_condition_helm;
+        kp.gridDim = dim3(1);
+        kp.blockDim = dim3(32);
+        kp.kernelParams = args;
+        CU(cudaGraphAddKernelNode(&cond_init, g, leaves.data(), leaves.size(), &kp));
+        c->kernels_prologue++;
+    }
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    CU(cudaGraphAddNode(&wnode, g, &cond_init, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    c->launch_counter = 0;
+    CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    rc = helm_iteration(c, tol, max_iters, s);
+    if (rc == EVO_OK) {
+        helm::k_set_while_condition_helm<<<1, 32, 0, s>>>(handle, c->d_helm);
+        c->launch_counter++;
+    }
+    e = cudaStreamEndCapture(s, nullptr);
+    if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "helmholtz body capture: %s", cudaGetErrorString(e)); }
+    c->kernels_per_cycle = c->launch_counter;
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    c->helm_graph = g; c->helm_exec = exec; c->helm_tol = tol; c->helm_max_iters = max_iters;
+    return EVO_OK;
+}
+
+extern "C" int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, const evo_solve_params *prm, evo_solve_result *res,
+                                   double *res_hist)
+{
+    if (!c || !A || !prm || !res) return fail(EVO_ERR_INVALID, "null argument");
+    if (c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ || c->p->desc.scalar_words != 2) return fail(EVO_ERR_INVALID, "not a Helmholtz problem");
+    if (prm->max_iters < 0 || prm->max_iters > 1000000) return fail(EVO_ERR_INVALID, "max_iters out of range");
+    CU(cudaSetDevice(c->p->desc.device));
+    memset(&c->helm_A, 0, sizeof(c->helm_A));
+    {
+        Sten &sA = c->helm_A.s[0][0];
+        for (int q = 0; q < 27; ++q) {
+            double re = A->coef[0][0][q][0], im = A->coef[0][0][q][1];
+            if (re == 0.0 && im == 0.0) continue;
+            if (q / 9 - 1 != 0) return fail(EVO_ERR_INVALID, "3-D stencil entry in a 2-D problem");
+            int k = sA.nnz++;
+            sA.ox[k] = (signed char)(q % 3 - 1); sA.oy[k] = (signed char)((q / 3) % 3 - 1); sA.oz[k] = 0;
+            sA.re[k] = re; sA.im[k] = im;
+        }
+    }
+    EV(ensure_hist(c, prm->max_iters));
+    // the operator is baked into the graph: rebuild when it changes is the caller's business (one A per cycle)
+    EV(build_helm_graph(c, prm->tol, prm->max_iters));
+    const int samples = prm->samples > 0 ? prm->samples : 1;
+    std::vector<float> times;
+    memset(res, 0, sizeof(*res));
+    helm::HelmState hs;
+    for (int sidx = 0; sidx < samples; ++sidx) {
+        cudaStream_t s = c->stream;
+        EV(reset_cycle(c, s));
+        CU(cudaEventRecord(c->ev0, s));
+        CU(cudaGraphLaunch(c->helm_exec, s));
+        CU(cudaEventRecord(c->ev1, s));
+        CU(cudaMemcpyAsync(&hs, c->d_helm, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(c->h_hist, c->d_hist, sizeof(double) * (prm->max_iters + 1), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        times.push_back(ms);
+    }
+    res->status = hs.bad ? 1 : 0;
+    res->iterations = hs.it;
+    res->initial_residual = hs.init;
+    res->final_residual = hs.cur;
+    res->kernel_launches = c->kernels_prologue + c->kernels_per_cycle * (int64_t)hs.it;
+    if (res_hist) memcpy(res_hist, c->h_hist, sizeof(double) * (hs.it + 1));
     std::sort(times.begin(), times.end());
     res->time_ms = times[times.size() / 2];
     res->time_ms_min = times[0];

@@ -103,3 +103,28 @@ def fas_fitness(residuals: Sequence[float], time_ms: float, infinity: float = 1e
     if isinstance(c, complex) or math.isinf(c) or math.isnan(c):
         return infinity, infinity, infinity
     return float(time_ms), c, n
+
+
+def helmholtz_fitness(residuals: Sequence[float], time_ms: float, max_iters: int, infinity: float = 1e100,
+                      solver_iteration_limit: Optional[int] = None, tol: float = 1e-7) -> Tuple[float, float, float]:
+    """What ``parse_output`` (exastencils.py:540-584) makes of the Helmholtz solver's prints
+    (example_problems/Helmholtz/2D_FD_Helmholtz_fromL3.exa3:192-199): ONE line
+    "Residual after <curStep> iterations is ... --- convergence factor is <|res|/|res0|>" when the loop ends,
+    curStep being the 0-based index of the last iteration, so the "convergence factor" is the total
+    reduction and an immediate convergence (curStep = 0) counts as infinity (:580-581); hitting the cap
+    prints "Maximum number of solver iterations" first -> iterations = infinity (:555-557)."""
+    n = len(residuals) - 1
+    if n <= 0:
+        return float(time_ms), infinity, infinity
+    res0, res = residuals[0], residuals[-1]
+    rho = _cout(res / res0) if res0 != 0 else math.nan
+    cf = math.sqrt(infinity) if (math.isinf(rho) or math.isnan(rho)) else rho
+    if math.isinf(rho) or math.isnan(rho):
+        cf = infinity            # count == 0 (:554, :574-576)
+    converged = res < tol * res0
+    iters: float = n - 1 if converged else infinity
+    if iters == 0:
+        iters = infinity
+    if solver_iteration_limit is not None and iters >= solver_iteration_limit:
+        iters = infinity
+    return float(time_ms), cf, iters

@@ -302,15 +302,29 @@ class B200ProgramGenerator:
     def _evaluate_program(self, prog: ol.Program, min_level, problem, infinity, evaluation_samples):
         dev = self._device_problem(min_level, self.max_level, problem)
         s = dev.problem.settings
+        helmholtz = dev.problem.kind == ol.PROBLEM_HELMHOLTZ
+        if problem is not None:
+            # PDE parameters patched for this run (exastencils.py:269-288 rewrites the generated globals):
+            # the operators are rediscretised with the new values
+            import copy
+            prog = copy.copy(prog)
+            prog.operators = {l: dev.problem.operator(l) for l in prog.operators}
         cyc = dev.build(prog)
         try:
-            out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
+            if helmholtz:
+                out = cyc.helmholtz_solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
+            else:
+                out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
         finally:
             cyc.close()
         self.last_outcome = out
         self.total_kernel_launches += out.kernel_launches * max(1, int(evaluation_samples))
-        t, cf, its = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters, infinity,
-                                                  self._solver_iteration_limit)
+        if helmholtz:
+            t, cf, its = fitness.helmholtz_fitness(out.residuals, out.time_ms, s.max_iters, infinity,
+                                                   self._solver_iteration_limit, s.tol)
+        else:
+            t, cf, its = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters, infinity,
+                                                      self._solver_iteration_limit)
         return self._apply_sentinels(t, cf, its, infinity)
 
     def generate_and_evaluate(self, expression, storages, min_level: int, max_level: int, solver_program: str,
@@ -338,6 +352,7 @@ class B200ProgramGenerator:
                         problem.parameters[k] = float(v)
                 if "k" in mapping:
                     problem.wave_number = complex(float(mapping["k"]))
+                    problem.parameters["k"] = float(mapping["k"])
             try:
                 t, cf, its = self._evaluate_program(prog, min_level, problem, infinity, evaluation_samples)
             except backend.BackendError:

@@ -195,6 +195,13 @@ int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, double *ms_
  *    exastencils.py:417-443): res0 = ||f - A u0||; repeat { cycle; res = ||f - A u|| } until
  *    res < tol*res0 or max_iters.  res_hist receives res0, res1, ... (max_iters+1 entries).     */
 int evo_cycle_solve(evo_cycle *c, const evo_solve_params *params, evo_solve_result *result, double *res_hist);
+/* Helmholtz (complex) problems: the outer PreconditionedBiCGStab@finest of the reference's problem file
+ * (example_problems/Helmholtz/2D_FD_Helmholtz_fromL3.exa3:144-200: stop |res| < tol |res0| or max_iters) on the
+ * un-shifted operator `A` of the finest level, with the cycle (built on the shifted operator M) applied as
+ * right preconditioner `u = 0; f = v; gen_mgCycle()` twice per iteration.  res_hist[k] = |curRes| after k
+ * iterations.                                                                                          */
+int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, const evo_solve_params *params, evo_solve_result *result,
+                        double *res_hist);
 /* many individuals in flight on one GPU, one stream each (population evaluation, program.py:491) */
 int evo_batch_solve(evo_cycle **cycles, int n_cycles, const evo_solve_params *params, evo_solve_result *results,
                     double *res_hist /* n_cycles * (max_iters+1) */, double *batch_ms);

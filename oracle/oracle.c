@@ -70,6 +70,8 @@ static double wall_ms(void)
 #define CO(s, q) ((s)->re[q])
 #define ABS2(x) ((x) * (x))
 #define REAL(x) (x)
+#define RECIP(x) (1.0 / (x))
+#define MUL(a, b) ((a) * (b))
 #include "mg_ops.inc"
 #include "mg_krylov.inc"
 #undef T
@@ -77,6 +79,26 @@ static double wall_ms(void)
 #undef CO
 #undef ABS2
 #undef REAL
+#undef RECIP
+#undef MUL
+
+/* complex division by Smith's algorithm, written out so that the CUDA kernels (cplx operator/ in
+ * csrc/evo_common.cuh) perform the identical operation sequence (libgcc's __divdc3 differs in the last bit) */
+static inline double complex cdiv_smith(double complex a, double complex b)
+{
+    const double ar = creal(a), ai = cimag(a), br = creal(b), bi = cimag(b);
+    if (fabs(br) < fabs(bi)) {
+        const double ratio = br / bi, denom = br * ratio + bi;
+        return ((ar * ratio + ai) / denom) + ((ai * ratio - ar) / denom) * I;
+    }
+    const double ratio = bi / br, denom = bi * ratio + br;
+    return ((ai * ratio + ar) / denom) + ((ai - ar * ratio) / denom) * I;
+}
+/* complex product written out (no libgcc __muldc3 fix-ups, no contraction) */
+static inline double complex cmul(double complex a, double complex b)
+{
+    return (creal(a) * creal(b) - cimag(a) * cimag(b)) + (creal(a) * cimag(b) + cimag(a) * creal(b)) * I;
+}
 
 /* ------------------------------------------------------------------ complex instantiation */
 #define T double complex
@@ -84,6 +106,8 @@ static double wall_ms(void)
 #define CO(s, q) ((s)->re[q] + (s)->im[q] * I)
 #define ABS2(x) (creal(x) * creal(x) + cimag(x) * cimag(x))
 #define REAL(x) creal(x)
+#define RECIP(x) cdiv_smith(1.0, (x))
+#define MUL(a, b) ((a) * (b))
 #define EVO_COMPLEX 1
 #include "mg_ops.inc"
 #include "mg_krylov.inc"
@@ -93,6 +117,8 @@ static double wall_ms(void)
 #undef CO
 #undef ABS2
 #undef REAL
+#undef RECIP
+#undef MUL
 
 #include "mg_fas.inc"
 
@@ -214,6 +240,23 @@ int orc_reset(void *h)
     return EVO_OK;
 }
 
+/* Helmholtz: fields u / gen_error_u / gen_residual_u carry the Robin boundary function (Helmholtz/
+ * 2D_FD_Helmholtz_fromL3.exa3:11-38, .exa4:25-108); it is applied after every statement that writes one
+ * of them ([UNVERIFIED-EXA]: ExaStencils adds `apply bc` after loops over fields with a boundary function) */
+static void helm_bc_after_op(Hier *H, const evo_op *op)
+{
+    int level = op->level, buf = -1;
+    switch (op->code) {
+    case EVO_OP_ZERO: case EVO_OP_COPY: case EVO_OP_PROLONG_SET: buf = op->dst; break;
+    case EVO_OP_SMOOTH: case EVO_OP_RICHARDSON: case EVO_OP_PROLONG_ADD: case EVO_OP_COARSE_SOLVE: buf = EVO_BUF_SOL; break;
+    case EVO_OP_RESIDUAL: buf = EVO_BUF_RES; break;
+    default: return;
+    }
+    if (buf == EVO_BUF_RHS) return; /* f / gen_rhs have no boundary function */
+    for (int i = 0; i < H->nf; ++i)
+        if (H->lv[level].buf[buf][i]) helm_apply_bc_c(H, &H->lv[level], level, (double complex *)H->lv[level].buf[buf][i]);
+}
+
 /* buffers that only some statements need are allocated when a statement first touches them */
 static void ensure_for_op(Hier *H, const evo_op *op)
 {
@@ -291,6 +334,7 @@ static int run_op(Hier *H, const evo_op *op)
         break;
     default: return EVO_ERR_UNSUPPORTED;
     }
+    if (H->kind == EVO_PROBLEM_HELMHOLTZ) helm_bc_after_op(H, op);
     return EVO_OK;
 }
 
@@ -355,6 +399,109 @@ int orc_solve(void *h, const evo_op *ops, int n_ops, const evo_solve_params *prm
     out->time_ms = times[m / 2];
     out->time_ms_min = best;
     out->kernel_launches = 0;
+    return EVO_OK;
+}
+
+/* Helmholtz outer solver: PreconditionedBiCGStab@finest, statement by statement
+ * (example_problems/Helmholtz/2D_FD_Helmholtz_fromL3.exa3:144-200).  The preconditioner application is
+ * `u = 0; f = p; gen_mgCycle()` with the evolved cycle `ops` on the shifted operator M (the operators
+ * installed with orc_set_operators); `A` is the un-shifted operator of the finest level.
+ * res_hist[k] = |curRes| after k iterations (res_hist[0] = |initRes|); out->iterations = iterations run. */
+int orc_helmholtz_solve(void *h, const evo_op *ops, int n_ops, const evo_level_operator *A, const evo_solve_params *prm,
+                        evo_solve_result *out, double *res_hist)
+{
+    Hier *H = (Hier *)h;
+    if (H->words != 2 || H->nf != 1 || H->dim != 2) return EVO_ERR_UNSUPPORTED;
+    const int l = H->max_level;
+    Level *L = &H->lv[l];
+    const int n = L->n;
+    const size_t tot = L->total;
+    typedef double complex C;
+    /* un-shifted operator as a stencil of the finest level */
+    Sten SA; SA.nnz = 0;
+    for (int p = 0; p < 27; ++p) {
+        double re = A->coef[0][0][p][0], im = A->coef[0][0][p][1];
+        if (re == 0.0 && im == 0.0) continue;
+        int q = SA.nnz++;
+        SA.off[q][0] = p % 3 - 1; SA.off[q][1] = (p / 3) % 3 - 1; SA.off[q][2] = 0;
+        SA.delta[q] = (ptrdiff_t)SA.off[q][1] * n + SA.off[q][0];
+        SA.re[q] = re; SA.im[q] = im;
+    }
+    C *x = (C *)calloc(tot, sizeof(C)), *b = (C *)calloc(tot, sizeof(C)), *r = (C *)calloc(tot, sizeof(C)),
+      *p = (C *)calloc(tot, sizeof(C)), *ap = (C *)calloc(tot, sizeof(C)), *s = (C *)calloc(tot, sizeof(C)),
+      *t = (C *)calloc(tot, sizeof(C)), *hh = (C *)calloc(tot, sizeof(C)), *rh = (C *)calloc(tot, sizeof(C));
+    memset(out, 0, sizeof(*out));
+    const int samples = prm->samples > 0 ? prm->samples : 1;
+    double times[64];
+    for (int smp = 0; smp < samples; ++smp) {
+        orc_reset(H);
+        memcpy(x, H->init[EVO_BUF_SOL][0], tot * sizeof(C));     /* Solution = 0 + boundary function */
+        memcpy(b, H->init[EVO_BUF_RHS][0], tot * sizeof(C));
+        memset(p, 0, tot * sizeof(C)); memset(ap, 0, tot * sizeof(C));
+        C *u = (C *)L->buf[EVO_BUF_SOL][0], *f = (C *)L->buf[EVO_BUF_RHS][0];
+        double t0 = wall_ms();
+#define INNER for (int j_ = 1; j_ < n - 1; ++j_) for (int x_ = 1; x_ < n - 1; ++x_)
+#define IDX ((size_t)j_ * n + x_)
+#define APPLY_A(dst, src) INNER { C acc = 0; for (int q = 0; q < SA.nnz; ++q) acc = acc + (SA.re[q] + SA.im[q] * I) * (src)[(ptrdiff_t)IDX + SA.delta[q]]; (dst)[IDX] = acc; }
+        helm_apply_bc_c(H, L, l, x);
+        INNER { C acc = 0; for (int q = 0; q < SA.nnz; ++q) acc = acc + (SA.re[q] + SA.im[q] * I) * x[(ptrdiff_t)IDX + SA.delta[q]]; r[IDX] = b[IDX] - acc; }
+        C *rp[1] = {r}, *rhp[1] = {rh}, *app[1] = {ap}, *sp[1] = {s}, *tp[1] = {t};
+        C d0 = dot_inner_c(H, L, rp, rp);
+        const double init = sqrt(sqrt(creal(d0) * creal(d0) + cimag(d0) * cimag(d0)));   /* |sqrt(z)| = sqrt(|z|) */
+        double cur = init;
+        res_hist[0] = init;
+        int it = 0, bad = 0;
+        if (init != 0.0) {
+            C alpha = 1.0, beta = 1.0, rho, rho_new = 1.0, omega = 1.0;
+            memcpy(rh, r, tot * sizeof(C));
+            while (it < prm->max_iters) {
+                rho = rho_new;
+                rho_new = dot_inner_c(H, L, rhp, rp);
+                beta = cdiv_smith(rho_new, rho) * cdiv_smith(alpha, omega);
+                INNER { p[IDX] = r[IDX] + beta * (p[IDX] - omega * ap[IDX]); }
+                /* u = 0; f = p; gen_mgCycle() */
+                u = (C *)L->buf[EVO_BUF_SOL][0];
+                memset(u, 0, tot * sizeof(C)); helm_apply_bc_c(H, L, l, u);
+                INNER { f[IDX] = p[IDX]; }
+                int rc = orc_run_ops(H, ops, n_ops, 1);
+                if (rc) return rc;
+                u = (C *)L->buf[EVO_BUF_SOL][0];
+                APPLY_A(ap, u)
+                alpha = cdiv_smith(rho_new, dot_inner_c(H, L, rhp, app));
+                INNER { hh[IDX] = x[IDX] + alpha * u[IDX]; s[IDX] = r[IDX] - alpha * ap[IDX]; }
+                memset(u, 0, tot * sizeof(C)); helm_apply_bc_c(H, L, l, u);
+                INNER { f[IDX] = s[IDX]; }
+                rc = orc_run_ops(H, ops, n_ops, 1);
+                if (rc) return rc;
+                u = (C *)L->buf[EVO_BUF_SOL][0];
+                APPLY_A(t, u)
+                omega = cdiv_smith(dot_inner_c(H, L, tp, sp), dot_inner_c(H, L, tp, tp));
+                INNER { x[IDX] = hh[IDX] + omega * u[IDX]; }
+                helm_apply_bc_c(H, L, l, x);
+                INNER { r[IDX] = s[IDX] - omega * t[IDX]; }
+                C d = dot_inner_c(H, L, rp, rp);
+                cur = sqrt(sqrt(creal(d) * creal(d) + cimag(d) * cimag(d)));
+                ++it;
+                res_hist[it] = cur;
+                if (!isfinite(cur)) { bad = 1; break; }
+                if (cur < prm->tol * init) break;
+            }
+        }
+#undef INNER
+#undef IDX
+#undef APPLY_A
+        times[smp < 64 ? smp : 63] = wall_ms() - t0;
+        out->status = bad; out->iterations = it; out->initial_residual = init; out->final_residual = cur;
+    }
+    int m = samples < 64 ? samples : 64;
+    for (int a = 0; a < m; ++a)
+        for (int c2 = a + 1; c2 < m; ++c2)
+            if (times[c2] < times[a]) { double tt = times[a]; times[a] = times[c2]; times[c2] = tt; }
+    out->time_ms = times[m / 2]; out->time_ms_min = times[0];
+    /* leave the outer solution in COR@finest for inspection */
+    if (!L->buf[EVO_BUF_COR][0]) L->buf[EVO_BUF_COR][0] = calloc(tot, sizeof(C));
+    memcpy(L->buf[EVO_BUF_COR][0], x, tot * sizeof(C));
+    free(x); free(b); free(r); free(p); free(ap); free(s); free(t); free(hh); free(rh);
     return EVO_OK;
 }
 

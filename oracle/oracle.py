@@ -48,6 +48,9 @@ def load():
         lib.orc_residual_norm.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.orc_solve.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.POINTER(ol.CEvoSolveParams),
                                   C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double)]
+        lib.orc_helmholtz_solve.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.POINTER(ol.CEvoLevelOperator),
+                                            C.POINTER(ol.CEvoSolveParams), C.POINTER(ol.CEvoSolveResult),
+                                            C.POINTER(C.c_double)]
         lib.orc_cg_iterations.restype = C.c_long
         lib.orc_cg_iterations.argtypes = [C.c_void_p]
         lib.orc_num_threads.restype = C.c_int
@@ -121,6 +124,20 @@ class OracleCycle:
         hist = np.zeros(max_iters + 1, dtype=np.float64)
         _check(self._lib.orc_solve(self.problem._h, self._ops, self._n_ops, C.byref(prm), C.byref(res),
                                    hist.ctypes.data_as(C.POINTER(C.c_double))), "orc_solve")
+        return SolveOutcome(res, hist)
+
+    def helmholtz_solve(self, tol: float, max_iters: int, samples: int = 1) -> SolveOutcome:
+        """Outer preconditioned BiCGStab with this cycle as the preconditioner (Helmholtz problems)."""
+        self._bind()
+        prob = self.problem.problem
+        outer = ol.Program(dim=2, n_fields=1, min_level=prob.max_level, max_level=prob.max_level,
+                           operators={prob.max_level: prob.outer_operator(prob.max_level)})
+        arr, _ = outer.c_operators()
+        prm = ol.CEvoSolveParams(tol, max_iters, samples, 0, 0)
+        res = ol.CEvoSolveResult()
+        hist = np.zeros(max_iters + 1, dtype=np.float64)
+        _check(self._lib.orc_helmholtz_solve(self.problem._h, self._ops, self._n_ops, arr, C.byref(prm), C.byref(res),
+                                             hist.ctypes.data_as(C.POINTER(C.c_double))), "orc_helmholtz_solve")
         return SolveOutcome(res, hist)
 
     def cg_iterations(self) -> int:
