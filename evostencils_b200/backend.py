@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = (
     "evo_cycle_build", "evo_cycle_destroy", "evo_cycle_reset", "evo_cycle_apply",
     "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm", "evo_cycle_profile_op",
     "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
+    "evo_problem_set_slab", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
+    "evo_cycle_residual_plane_sums", "evo_cycle_vecsum",
 )
 
 _lib = None
@@ -70,6 +72,13 @@ def load_library(path: Optional[str] = None):
                                         C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double)]
     lib.evo_batch_solve.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(ol.CEvoSolveParams),
                                     C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.evo_problem_set_slab.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.evo_problem_slab_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+    lib.evo_cycle_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.evo_cycle_exec_ops.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.c_int, C.c_int]
+    lib.evo_cycle_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.evo_cycle_residual_plane_sums.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.evo_cycle_vecsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     if lib.evo_abi_version() != ol.ABI_VERSION:
         raise BackendError("ABI version mismatch between the Python host and libevostencils_b200.so")
     if path == LIB_PATH:
@@ -179,6 +188,29 @@ class DeviceCycle:
                "evo_cycle_profile_op")
         return float(ms.value), int(n.value)
 
+    # -- host-orchestrated execution (evostencils_b200.domain) ------------------------------------
+    def set_stream(self, cuda_stream: int):
+        _check(self._lib, self._lib.evo_cycle_set_stream(self._h, C.c_void_p(cuda_stream)), "evo_cycle_set_stream")
+
+    def exec_ops(self, c_ops, n: int, zc_lo: int = -1, zc_hi: int = -1):
+        _check(self._lib, self._lib.evo_cycle_exec_ops(self._h, c_ops, n, zc_lo, zc_hi), "evo_cycle_exec_ops")
+
+    def buffer_ptr(self, level: int, buf: int, field: int = 0) -> int:
+        p = C.c_void_p()
+        _check(self._lib, self._lib.evo_cycle_buffer(self._h, level, buf, field, C.byref(p)), "evo_cycle_buffer")
+        return int(p.value)
+
+    def residual_plane_sums(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_int()
+        _check(self._lib, self._lib.evo_cycle_residual_plane_sums(self._h, C.byref(p), C.byref(n)),
+               "evo_cycle_residual_plane_sums")
+        return int(p.value), int(n.value)
+
+    def vecsum(self, device_ptr: int, m: int) -> float:
+        v = C.c_double()
+        _check(self._lib, self._lib.evo_cycle_vecsum(self._h, C.c_void_p(device_ptr), m, C.byref(v)), "evo_cycle_vecsum")
+        return float(v.value)
+
     def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0) -> SolveOutcome:
         prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)
         res = ol.CEvoSolveResult()
@@ -209,7 +241,9 @@ class DeviceProblem:
 
     backend_name = "cuda"
 
-    def __init__(self, problem: Problem, device: int = 0, lib=None):
+    def __init__(self, problem: Problem, device: int = 0, lib=None, slab: Optional[Tuple[int, int, int]] = None):
+        """slab = (rank, world, coarsest distributed level): hold only this rank's z-slab of every level
+        >= that level (domain decomposition of one grid; see evostencils_b200.domain)."""
         self._lib = lib or load_library()
         n = self._lib.evo_device_count()
         if n <= 0:
@@ -220,6 +254,9 @@ class DeviceProblem:
         self._h = C.c_void_p()
         desc = make_desc(problem, device)
         _check(self._lib, self._lib.evo_problem_create(C.byref(desc), C.byref(self._h)), "evo_problem_create")
+        self.slab = slab
+        if slab is not None:
+            _check(self._lib, self._lib.evo_problem_set_slab(self._h, *[int(v) for v in slab]), "evo_problem_set_slab")
         for fi in range(problem.n_fields):
             for buf, arr in ((ol.BUF_SOL, problem.initial_solution(fi)), (ol.BUF_RHS, problem.rhs(fi))):
                 flat = _as_doubles(arr, problem.complex_valued)
@@ -240,6 +277,12 @@ class DeviceProblem:
 
     def build(self, program: ol.Program) -> DeviceCycle:
         return DeviceCycle(self, program)
+
+    def slab_info(self, level: int) -> dict:
+        info = (C.c_longlong * 8)()
+        _check(self._lib, self._lib.evo_problem_slab_info(self._h, level, info), "evo_problem_slab_info")
+        keys = ("zoff", "nz", "zlo", "zhi", "g0", "g1", "pitch", "plane")
+        return {k: int(v) for k, v in zip(keys, info)}
 
     def batch_solve(self, cycles: Sequence[DeviceCycle], tol: float, max_iters: int, samples: int = 1,
                     flags: int = 0) -> Tuple[List[SolveOutcome], float]:

@@ -55,6 +55,12 @@ struct Geom {
     int nz;         // n for 3-D, 1 for 2-D
     long long plane;  // pitch * n
     long long total;  // plane * nz
+    // z-slab view (domain decomposition; for an undecomposed grid: zlo = zin0 = 1, zhi = zin1 = n-2, zpar = 0,
+    // zoff = 0): the array holds planes [zoff, zoff + nz) of the global grid
+    int zlo, zhi;     // local plane range this rank owns / sweeps over
+    int zin0, zin1;   // local range of planes that are inner planes of the GLOBAL grid (halo recomputation limit)
+    int zpar;         // parity of zoff: global colour of a node = (x + y + z_local + zpar) & 1
+    int zoff;         // global z index of local plane 0
 };
 
 // stencil of one (row field, column field) block, non-zeros in ascending table order

@@ -118,11 +118,11 @@ __global__ void __launch_bounds__(128) k_row_sumsq(const Geom g, Fields<T> r, do
 
 // canonical reduction, second and third level: row sums -> plane sums (3-D: one warp per plane, many
 // blocks) -> field sums -> total (one warp)
-__global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int nf, int ni, double *planes)
+__global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int count /* fields * planes */, int ni, double *planes)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long id = (long long)blockIdx.x * 8 + warp;   // (field, plane)
-    if (id >= (long long)nf * ni) return;
+    if (id >= count) return;
     double s = warp_vecsum(rows + id * ni, ni);
     if (lane == 0) planes[id] = s;
 }
@@ -371,9 +371,10 @@ template <typename T, int DIM, int NF>
 __global__ void __launch_bounds__(BX) k_restrict(const Geom gf, const Geom gc, const __grid_constant__ TransferW R,
                                                  Fields<T> src, Fields<T> dst)
 {
-    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
+    // z-slab aware: local coarse plane z holds global plane z + gc.zoff, whose fine plane is 2*(z + gc.zoff)
+    const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? gc.zlo + blockIdx.z : 0;
     if (x > gc.n - 2) return;
-    const long long fidx = node_index(gf, 2 * x, 2 * y, DIM == 3 ? 2 * z : 0);
+    const long long fidx = node_index(gf, 2 * x, 2 * y, DIM == 3 ? 2 * (z + gc.zoff) - gf.zoff : 0);
     const long long cidx = node_index(gc, x, y, z);
 #pragma unroll
     for (int i = 0; i < NF; ++i) {

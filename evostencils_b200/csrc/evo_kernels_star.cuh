@@ -176,13 +176,13 @@ __device__ __forceinline__ void rb_load_f(const RbItems<S, TY, NT> &it, double (
     using C = StageCfg<S, TY, NT, s>;
     constexpr int base = stage_base<S, TY, NT, s>();
     const int z = t - s;
-    if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
+    if (z >= max(za - C::E, g.zin0) && z <= min(zb + C::E, g.zin1)) {
         const double *fp = f + (long long)z * g.plane;
 #pragma unroll
         for (int j = 0; j < C::ROUNDS; ++j) {
             const int idx = base + j;
             // active node = left node iff its colour (x+y+z+c) is even
-            const unsigned p = ((it.par >> idx) ^ (unsigned)z) & 1u;
+            const unsigned p = ((it.par >> idx) ^ (unsigned)(z + g.zpar)) & 1u;
             const bool ok = ((p ? it.v1 : it.v0) >> idx) & 1u;
             if (ok) fv[idx] = __ldg(fp + it.goff[idx] + p);
         }
@@ -198,14 +198,14 @@ __device__ __forceinline__ void rb_stages(const RbItems<S, TY, NT> &it, const do
     using R = RbCfg<S, TY, NT>;
     constexpr int base = stage_base<S, TY, NT, s>();
     const int z = t - s;
-    if (z >= max(za - C::E, 1) && z <= min(zb + C::E, g.n - 2)) {
+    if (z >= max(za - C::E, g.zin0) && z <= min(zb + C::E, g.zin1)) {
         double *pc = ring + (size_t)((z - pbase) % R::NP) * R::PSTRIDE;
         const double *pm = ring + (size_t)((z - 1 - pbase) % R::NP) * R::PSTRIDE;
         const double *pp = ring + (size_t)((z + 1 - pbase) % R::NP) * R::PSTRIDE;
 #pragma unroll
         for (int j = 0; j < C::ROUNDS; ++j) {
             const int idx = base + j;
-            const unsigned p = ((it.par >> idx) ^ (unsigned)z) & 1u;
+            const unsigned p = ((it.par >> idx) ^ (unsigned)(z + g.zpar)) & 1u;
             const bool ok = ((p ? it.v1 : it.v0) >> idx) & 1u;
             if (ok) {
                 const int li = it.loff[idx] + (int)p;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT) k3_rbgs_stream(const __grid_constant__ CUt
 
     const int n = g.n;
     const int x0 = 1 + blockIdx.x * RB_TX, y0 = 1 + blockIdx.y * TY;
-    const int za = 1 + blockIdx.z * tz, zb = min(za + tz - 1, n - 2);
+    const int za = g.zlo + blockIdx.z * tz, zb = min(za + tz - 1, g.zhi);
     const int xb = x0 - H - 1, yb = y0 - H;  // global coordinates of local (0, 0); xb is even
     const int pbase = za - H;                // first plane ever loaded (may be < 0: zero filled, never used)
     const int tid = threadIdx.x;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(NT) k3_rbgs_stream(const __grid_constant__ CUt
 
     const int t0 = za - (S - 1);         // first plane of stage 0
     const int t1 = zb + (S - 1);         // last step: stage S-1 reaches plane zb
-    const int pmax = min(zb + H, n - 1); // last plane that is ever read
+    const int pmax = min(zb + H, g.nz - 1); // last plane that is ever read
     if (tid == 0) {
         for (int p = pbase; p <= min(t0 + 1, pmax); ++p) issue(p);
     }
@@ -316,21 +316,21 @@ static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, cons
         if (cudaFuncSetAttribute(k3_rbgs_stream<S, TY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_stream<S, TY, NT>, NT, smem) != cudaSuccess || occ < 1) occ = 1;
     }
-    const int inner = g.n - 2;
+    const int inner = g.n - 2, planes = g.zhi - g.zlo + 1;
     const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + TY - 1) / TY;
     // z slabs: minimise (waves) x (planes per slab + pipeline fill) over 1..16 slabs
     const long long slots = (long long)occ * sm_count;
     int best = 1;
     double best_cost = 1e300;
-    for (int slabs = 1; slabs <= 16 && slabs * 8 <= inner; ++slabs) {
-        const int tzc = (inner + slabs - 1) / slabs;
-        const long long ctas = (long long)tx * ty * ((inner + tzc - 1) / tzc);
+    for (int slabs = 1; slabs <= 16 && (slabs == 1 || slabs * 8 <= planes); ++slabs) {
+        const int tzc = (planes + slabs - 1) / slabs;
+        const long long ctas = (long long)tx * ty * ((planes + tzc - 1) / tzc);
         const double waves = (double)((ctas + slots - 1) / slots);
         const double cost = waves * (tzc + 2 * S + 2);
         if (cost < best_cost) { best_cost = cost; best = slabs; }
     }
-    const int tz = (inner + best - 1) / best;
-    const int slabs = (inner + tz - 1) / tz;
+    const int tz = (planes + best - 1) / best;
+    const int slabs = (planes + tz - 1) / tz;
     k3_rbgs_stream<S, TY, NT><<<dim3(tx, ty, slabs), NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
     return cudaGetLastError() == cudaSuccess;
 }
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star
 {
     const int ni = g.n - 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = 1 + blockIdx.x * 8 + warp, z = 1 + blockIdx.y;
+    const int y = 1 + blockIdx.x * 8 + warp, z = g.zlo + blockIdx.y;
     if (y > ni) return;
     const long long base = (long long)z * g.plane + (long long)y * g.pitch;
     const double *uc = u + base, *fc = f + base;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star
     }
     if (NORM) {
         acc = warp_butterfly(acc);
-        if (lane == 0) rows[(long long)(z - 1) * ni + (y - 1)] = acc;
+        if (lane == 0) rows[(long long)(z - g.zlo) * ni + (y - 1)] = acc;
     }
 }
 
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256) k3_jacobi_rows(const Geom g, const Star7 
 {
     const int ni = g.n - 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = 1 + blockIdx.x * 8 + warp, z = 1 + blockIdx.y;
+    const int y = 1 + blockIdx.x * 8 + warp, z = g.zlo + blockIdx.y;
     if (y > ni) return;
     const long long base = (long long)z * g.plane + (long long)y * g.pitch;
     const double *uc = u + base, *fc = f + base;
@@ -476,10 +476,12 @@ __device__ __forceinline__ double prolong_node(const DenseW &P, const double (&e
 
 __global__ void __launch_bounds__(128) k3_prolong_add(const Geom gf, const Geom gc, const DenseW P,
                                                       const double *__restrict__ ec, double *__restrict__ u,
-                                                      const double weight)
+                                                      const double weight, const int zc0)
 {
-    const int X = blockIdx.x * 128 + threadIdx.x, Y = blockIdx.y, Z = blockIdx.z;
+    // coarse cell index in local coarse planes; the fine plane of local coarse plane Z is 2*(Z + gc.zoff) - gf.zoff
+    const int X = blockIdx.x * 128 + threadIdx.x, Y = blockIdx.y, Z = zc0 + blockIdx.z;
     if (X > gc.n - 2) return;
+    const int zf0 = 2 * (Z + gc.zoff) - gf.zoff;
     double e[2][2][2];
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz)
@@ -492,8 +494,8 @@ __global__ void __launch_bounds__(128) k3_prolong_add(const Geom gf, const Geom 
     const int n2 = gf.n - 2;
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz) {
-        const int z = 2 * Z + dz;
-        if (z < 1 || z > n2) continue;
+        const int z = zf0 + dz;
+        if (z < gf.zlo || z > gf.zhi) continue;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
             const int y = 2 * Y + dy;
@@ -519,7 +521,7 @@ static bool try_residual(int, const Geom &g, const OpSten &st, Fields<T> u, Fiel
         Star7 c;
         if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
         const int ni = g.n - 2;
-        k3_residual_rows<true, false><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], nullptr);
+        k3_residual_rows<true, false><<<dim3((ni + 7) / 8, g.zhi - g.zlo + 1), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], nullptr);
         return cudaGetLastError() == cudaSuccess;
     } else {
         return false;
@@ -535,8 +537,8 @@ static bool try_residual_norm(const Geom &g, const OpSten &st, Fields<T> u, Fiel
         Star7 c;
         if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
         const int ni = g.n - 2;
-        if (store) k3_residual_rows<true, true><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
-        else k3_residual_rows<false, true><<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
+        if (store) k3_residual_rows<true, true><<<dim3((ni + 7) / 8, g.zhi - g.zlo + 1), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
+        else k3_residual_rows<false, true><<<dim3((ni + 7) / 8, g.zhi - g.zlo + 1), 256, 0, s>>>(g, c, u.p[0], f.p[0], r.p[0], rows);
         return cudaGetLastError() == cudaSuccess;
     } else {
         return false;
@@ -552,7 +554,7 @@ static bool try_smooth_point(int, const Geom &g, const OpSten &st, const SmoothP
         // only the out-of-place Jacobi sweep (colour passes of RB-GS go through the streaming kernel)
         if (sp.color >= 0 || src.p[0] == dst.p[0] || g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
         const int ni = g.n - 2;
-        k3_jacobi_rows<<<dim3((ni + 7) / 8, ni), 256, 0, s>>>(g, c, 1.0 / c.c, sp.omega, src.p[0], rhs.p[0], dst.p[0]);
+        k3_jacobi_rows<<<dim3((ni + 7) / 8, g.zhi - g.zlo + 1), 256, 0, s>>>(g, c, 1.0 / c.c, sp.omega, src.p[0], rhs.p[0], dst.p[0]);
         return cudaGetLastError() == cudaSuccess;
     } else {
         return false;
@@ -574,7 +576,11 @@ static bool try_prolong_add(int, const Geom &gf, const Geom &gc, const TransferW
         for (int i = 0; i < 27; ++i) W.w[i] = 0.0;
         for (int q = 0; q < P.nnz; ++q) W.w[(P.oz[q] + 1) * 9 + (P.oy[q] + 1) * 3 + (P.ox[q] + 1)] = P.w[q];
         const int cells = gc.n - 1;
-        k3_prolong_add<<<dim3((cells + 127) / 128, cells, cells), 128, 0, s>>>(gf, gc, W, src.p[0], dst.p[0], weight);
+        // coarse cells (local planes) whose two fine planes intersect the owned fine range
+        const int zc0 = std::max(0, (gf.zlo + gf.zoff) / 2 - gc.zoff);
+        const int zc1 = std::min(gc.nz - 2, (gf.zhi + gf.zoff) / 2 - gc.zoff);
+        if (zc1 < zc0) return true;
+        k3_prolong_add<<<dim3((cells + 127) / 128, cells, zc1 - zc0 + 1), 128, 0, s>>>(gf, gc, W, src.p[0], dst.p[0], weight, zc0);
         return cudaGetLastError() == cudaSuccess;
     } else {
         return false;

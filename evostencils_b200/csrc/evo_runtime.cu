@@ -64,6 +64,10 @@ static Geom make_geom(int level, int dim)
     g.nz = dim == 3 ? g.n : 1;
     g.plane = (long long)g.pitch * g.n;
     g.total = g.plane * g.nz;
+    g.zlo = g.zin0 = 1;
+    g.zhi = g.zin1 = g.n - 2;
+    g.zpar = 0;
+    g.zoff = 0;
     return g;
 }
 
@@ -92,6 +96,8 @@ struct evo_problem {
     void *init_sol[EVO_MAX_FIELDS];  // pristine finest-level SOL (incl. boundary values), padded layout
     void *rhs0[EVO_MAX_FIELDS];      // finest-level RHS, read-only, shared by all cycles
     std::vector<std::pair<void *, size_t>> pool;  // recycled cycle work slabs
+    int slab_world = 1, slab_rank = 0, slab_lc = 0;  // domain decomposition (slab_lc = 0: none)
+    int own_g0[EVO_MAX_LEVELS], own_g1[EVO_MAX_LEVELS];   // owned global plane range per distributed level
     int live_cycles = 0;                          // cycles still referring to this problem
     bool closed = false;                          // evo_problem_destroy called while cycles were alive
 };
@@ -137,6 +143,8 @@ struct evo_cycle {
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
     bool use_while_graph;
+    int zc_lo = -1, zc_hi = -1;  // coarse plane override of RESTRICT (domain decomposition)
+    bool own_stream = true;
     bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
                              // (convergence test) need not be stored
 };
@@ -152,7 +160,7 @@ static dim3 row_grid(const Geom &g, int per_thread = 1)
 {
     int inner = g.n - 2;
     int threads = (inner + per_thread - 1) / per_thread;
-    return dim3((threads + BX - 1) / BX, inner, g.dim == 3 ? inner : 1);
+    return dim3((threads + BX - 1) / BX, inner, g.dim == 3 ? g.zhi - g.zlo + 1 : 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,13 +243,74 @@ static void free_problem(evo_problem *p)
     delete p;
 }
 
+static bool slab_level(const evo_problem *p, int level) { return p->slab_lc > 0 && level >= p->slab_lc; }
+
+extern "C" int evo_problem_set_slab(evo_problem *p, int rank, int world, int lc)
+{
+    if (!p) return fail(EVO_ERR_INVALID, "null argument");
+    const evo_problem_desc &d = p->desc;
+    if (d.dim != 3 || d.n_fields != 1 || d.scalar_words != 1 || d.kind != EVO_PROBLEM_LINEAR)
+        return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: 3-D real scalar linear problems only");
+    if (world < 1 || rank < 0 || rank >= world) return fail(EVO_ERR_INVALID, "invalid rank/world");
+    if (lc < 5 || lc < d.min_level || lc > d.max_level) return fail(EVO_ERR_INVALID, "coarsest distributed level must be >= 5 and within the hierarchy");
+    const int inner = (1 << lc) - 1;
+    if (inner < 2 * world) return fail(EVO_ERR_INVALID, "too many ranks for the coarsest distributed level");
+    if (p->live_cycles > 0) return fail(EVO_ERR_INVALID, "set the slab before building cycles");
+    CU(cudaSetDevice(d.device));
+    p->slab_world = world; p->slab_rank = rank; p->slab_lc = lc;
+    const int base = inner / world, rem = inner % world;
+    int a = 1 + rank * base + std::min(rank, rem), b = a + base + (rank < rem ? 1 : 0) - 1;
+    const int G = 2;
+    for (int l = lc; l <= d.max_level; ++l) {
+        if (l > lc) { a = 2 * a - 1; b = 2 * b + (rank == world - 1 ? 1 : 0); }
+        Geom g = make_geom(l, 3);
+        p->own_g0[l] = a; p->own_g1[l] = b;
+        g.zoff = a - G;
+        g.nz = (b - a + 1) + 2 * G;
+        g.zlo = G; g.zhi = G + (b - a);
+        g.zin0 = std::max(0, 1 - g.zoff);
+        g.zin1 = std::min(g.nz - 1, (g.n - 2) - g.zoff);
+        g.zpar = g.zoff & 1;
+        g.total = g.plane * g.nz;
+        p->geom[l] = g;
+    }
+    // re-allocate the finest-level initial fields for the local slab
+    const size_t bytes = (size_t)p->geom[d.max_level].total * sizeof(double);
+    for (int i = 0; i < d.n_fields; ++i) {
+        cudaFree(p->init_sol[i]); cudaFree(p->rhs0[i]);
+        CU(cudaMalloc(&p->init_sol[i], bytes));
+        CU(cudaMalloc(&p->rhs0[i], bytes));
+        CU(cudaMemset(p->init_sol[i], 0, bytes));
+        CU(cudaMemset(p->rhs0[i], 0, bytes));
+    }
+    return EVO_OK;
+}
+
+extern "C" int evo_problem_slab_info(evo_problem *p, int level, long long info[8])
+{
+    if (!p || !info || level < p->desc.min_level || level > p->desc.max_level) return fail(EVO_ERR_INVALID, "invalid argument");
+    const Geom &g = p->geom[level];
+    info[0] = g.zoff; info[1] = g.nz; info[2] = g.zlo; info[3] = g.zhi;
+    info[4] = g.zlo + g.zoff; info[5] = g.zhi + g.zoff; info[6] = g.pitch; info[7] = g.plane;
+    return EVO_OK;
+}
+
 // dense host array (n^dim entries, x fastest) <-> padded device array
 static int copy_field(const Geom &g, int words, void *dev, const void *host_src, void *host_dst, cudaStream_t stream)
 {
     const size_t esz = sizeof(double) * words;
-    const size_t rows = (size_t)g.n * g.nz;
-    if (host_src) CU(cudaMemcpy2DAsync(dev, g.pitch * esz, host_src, g.n * esz, g.n * esz, rows, cudaMemcpyHostToDevice, stream));
-    if (host_dst) CU(cudaMemcpy2DAsync(host_dst, g.n * esz, dev, g.pitch * esz, g.n * esz, rows, cudaMemcpyDeviceToHost, stream));
+    // local planes that exist in the global grid (a z-slab holds planes [zoff, zoff + nz))
+    const int gn = g.dim == 3 ? g.n : 1;
+    int l0 = 0, l1 = g.nz - 1;                       // upload: every local plane incl. ghosts
+    if (host_dst && g.dim == 3 && (g.zoff != 0 || g.nz != g.n)) { l0 = g.zlo; l1 = g.zhi; }   // download: owned planes
+    l0 = std::max(l0, -g.zoff);
+    l1 = std::min(l1, gn - 1 - g.zoff);
+    if (l1 < l0) return EVO_OK;
+    const size_t rows = (size_t)g.n * (l1 - l0 + 1);
+    char *d0 = (char *)dev + (size_t)l0 * g.plane * esz;
+    const size_t hoff = (size_t)(l0 + g.zoff) * g.n * g.n * esz;
+    if (host_src) CU(cudaMemcpy2DAsync(d0, g.pitch * esz, (const char *)host_src + hoff, g.n * esz, g.n * esz, rows, cudaMemcpyHostToDevice, stream));
+    if (host_dst) CU(cudaMemcpy2DAsync((char *)host_dst + hoff, g.n * esz, d0, g.pitch * esz, g.n * esz, rows, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     return EVO_OK;
 }
@@ -253,7 +322,7 @@ extern "C" int evo_problem_set_field(evo_problem *p, int level, int buf, int fie
     if (field < 0 || field >= p->desc.n_fields || (buf != EVO_BUF_SOL && buf != EVO_BUF_RHS))
         return fail(EVO_ERR_INVALID, "invalid field/buffer");
     const Geom &g = p->geom[level];
-    if (n_doubles != (size_t)g.n * g.n * g.nz * p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    if (n_doubles != (size_t)g.n * g.n * (g.dim == 3 ? g.n : 1) * p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
     CU(cudaSetDevice(p->desc.device));
     return copy_field(g, p->words, buf == EVO_BUF_SOL ? p->init_sol[field] : p->rhs0[field], host, nullptr, 0);
 }
@@ -368,7 +437,7 @@ template <typename T, int DIM, int NF> struct Launch {
     {
         if (DIM == 3) {
             double *planes = c->d_partials + (size_t)NF * ni * ni;
-            k_reduce_planes<<<(unsigned)((NF * ni + 7) / 8), 256, 0, s>>>(c->d_partials, NF, ni, planes);
+            k_reduce_planes<<<(unsigned)((NF * ni + 7) / 8), 256, 0, s>>>(c->d_partials, NF * ni, ni, planes);
             k_reduce_final<<<1, 32, 0, s>>>(planes, NF, ni, c->d_state);
             c->launch_counter += 2;
         } else {
@@ -392,10 +461,13 @@ template <typename T, int DIM, int NF> struct Launch {
             EV(reduce_rows(c, ni, s));
             return EVO_OK;
         }
-        if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s))
+        if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s)) {
+            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: residual needs the 7-point fast path");
             k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
+        }
         c->launch_counter++;
         if (norm) {
+            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: use evo_cycle_residual_plane_sums");
             const long long nrows = (long long)ni * (DIM == 3 ? ni : 1);
             k_row_sumsq<T, DIM, NF><<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
             c->launch_counter += 1;
@@ -444,6 +516,8 @@ template <typename T, int DIM, int NF> struct Launch {
             }
             if (reps == 0) { CU(cudaGetLastError()); return EVO_OK; }
         }
+        if (slab_level(c->p, l) && !(NU == 1 && op.mode == EVO_SMOOTH_JACOBI))
+            return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: only pointwise RB-GS / Jacobi on 7-point stencils");
         for (int rep = 0; rep < reps; ++rep) {
             if (op.mode == EVO_SMOOTH_JACOBI) {
                 // read the current slot, write the next slot, then `advance` (swap) the written fields
@@ -455,8 +529,10 @@ template <typename T, int DIM, int NF> struct Launch {
                 }
                 sp.color = -1;
                 auto src = fields_of<T>(cur, NF), dst = fields_of<T>(nxt, NF);
-                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, src, dst, rhs, s)))
+                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, src, dst, rhs, s))) {
+                    if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: Jacobi needs the 7-point fast path");
                     k_smooth<T, DIM, NF, NU><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], sp, src, dst, rhs);
+                }
                 c->launch_counter++;
                 for (int i = 0; i < NF; ++i)
                     if (written[i]) {
@@ -547,7 +623,9 @@ template <typename T, int DIM, int NF> struct Launch {
     static int restrict_(evo_cycle *c, const evo_op &op, cudaStream_t s)
     {
         const int l = op.level;
-        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        const Geom &gf = c->p->geom[l];
+        Geom gc = c->p->geom[l - 1];
+        if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
         auto src = fields_of<T>(c->lv[l].buf[op.src], NF), dst = fields_of<T>(c->lv[l - 1].buf[op.dst], NF);
         k_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->p->R, src, dst);
         c->launch_counter++;
@@ -561,6 +639,7 @@ template <typename T, int DIM, int NF> struct Launch {
         const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
+        if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction not supported");
         if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s))
             k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
         c->launch_counter++;
@@ -575,9 +654,12 @@ template <typename T, int DIM, int NF> struct Launch {
         auto src = fields_of<T>(c->lv[l - 1].buf[op.src], NF);
         auto dst = fields_of<T>(c->lv[l].buf[add ? EVO_BUF_SOL : op.dst], NF);
         if (add) {
-            if (!star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s))
+            if (!star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s)) {
+                if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: prolongation needs the fast path");
                 k_prolong<T, DIM, NF, true><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, op.omega);
+            }
         } else {
+            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: PROLONG_SET not supported");
             k_prolong<T, DIM, NF, false><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, 1.0);
         }
         c->launch_counter++;
@@ -587,6 +669,7 @@ template <typename T, int DIM, int NF> struct Launch {
 
     static int richardson(evo_cycle *c, const evo_op &op, cudaStream_t s)
     {
+        if (slab_level(c->p, op.level)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: Richardson steps not supported");
         // field by field: tmp = RHS_i - (A SOL)_i from the current values, then SOL_i += w * tmp
         const int l = op.level;
         const Geom &g = c->p->geom[l];
@@ -1010,7 +1093,7 @@ extern "C" int evo_cycle_destroy(evo_cycle *c)
     if (c->d_hist) cudaFree(c->d_hist);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_hist) cudaFreeHost(c->h_hist);
-    if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream); }
+    if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->own_stream) cudaStreamDestroy(c->stream); }
     evo_problem *p = c->p;
     delete c;
     if (--p->live_cycles == 0 && p->closed) free_problem(p);
@@ -1051,7 +1134,7 @@ extern "C" int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, 
     void *dev;
     EV(field_ptr(c, level, buf, field, &dev));
     const Geom &g = c->p->geom[level];
-    if (n_doubles != (size_t)g.n * g.n * g.nz * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    if (n_doubles != (size_t)g.n * g.n * (g.dim == 3 ? g.n : 1) * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
     CU(cudaSetDevice(c->p->desc.device));
     return copy_field(g, c->p->words, dev, nullptr, host, c->stream);
 }
@@ -1065,7 +1148,7 @@ extern "C" int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, 
         if (c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ)
             return fail(EVO_ERR_UNSUPPORTED, "the finest right-hand side is shared by all cycles: use evo_problem_set_field");
     const Geom &g = c->p->geom[level];
-    if (n_doubles != (size_t)g.n * g.n * g.nz * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
+    if (n_doubles != (size_t)g.n * g.n * (g.dim == 3 ? g.n : 1) * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
     CU(cudaSetDevice(c->p->desc.device));
     EV(copy_field(g, c->p->words, dev, host, nullptr, c->stream));
     if (buf == EVO_BUF_SOL && c->lv[level].slot[field])  // keep the boundary invariant of the jacobi slot
@@ -1081,6 +1164,76 @@ extern "C" int evo_cycle_residual_norm(evo_cycle *c, double *norm)
     CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *norm = sqrt(c->h_state->sum);
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_set_stream(evo_cycle *c, void *cuda_stream)
+{
+    if (!c) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    if (c->stream && c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_exec_ops(evo_cycle *c, const evo_op *ops, int n_ops, int zc_lo, int zc_hi)
+{
+    if (!c || (n_ops > 0 && !ops)) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    std::vector<evo_op> saved = c->ops;
+    c->ops.assign(ops, ops + n_ops);
+    int rc = validate_ops(c);
+    c->ops = saved;
+    EV(rc);
+    c->zc_lo = zc_lo; c->zc_hi = zc_hi;
+    for (int t = 0; t < n_ops && rc == EVO_OK; ++t) rc = dispatch_op(c, ops[t], c->stream);
+    c->zc_lo = c->zc_hi = -1;
+    return rc;
+}
+
+extern "C" int evo_cycle_buffer(evo_cycle *c, int level, int buf, int field, void **device_ptr)
+{
+    if (!c || !device_ptr) return fail(EVO_ERR_INVALID, "null argument");
+    return field_ptr(c, level, buf, field, device_ptr);
+}
+
+extern "C" int evo_cycle_residual_plane_sums(evo_cycle *c, double **device_sums, int *count)
+{
+    if (!c || !device_sums || !count) return fail(EVO_ERR_INVALID, "null argument");
+    const evo_problem_desc &d = c->p->desc;
+    if (d.dim != 3 || d.n_fields != 1 || d.scalar_words != 1) return fail(EVO_ERR_UNSUPPORTED, "3-D real scalar only");
+    CU(cudaSetDevice(d.device));
+    const int l = d.max_level;
+    const Geom &g = c->p->geom[l];
+    auto u = fields_of<double>(c->lv[l].buf[EVO_BUF_SOL], 1), f = fields_of<double>(c->lv[l].buf[EVO_BUF_RHS], 1),
+         r = fields_of<double>(c->lv[l].buf[EVO_BUF_RES], 1);
+    if (!star::try_residual_norm<double, 3, 1>(g, c->sten[l], u, f, r, c->d_partials, true, c->stream))
+        return fail(EVO_ERR_UNSUPPORTED, "residual fast path not applicable");
+    const int ni = g.n - 2, planes = g.zhi - g.zlo + 1;
+    double *psums = c->d_partials + (size_t)ni * planes;
+    // one warp per owned plane: canonical vecsum over its rows
+    k_reduce_planes<<<(unsigned)((planes + 7) / 8), 256, 0, c->stream>>>(c->d_partials, planes, ni, psums);
+    CU(cudaGetLastError());
+    *device_sums = psums;
+    *count = planes;
+    return EVO_OK;
+}
+
+__global__ void k_vecsum_out(const double *vals, int m, double *out)
+{
+    double s = warp_vecsum(vals, m);
+    if (threadIdx.x == 0) *out = s;
+}
+
+extern "C" int evo_cycle_vecsum(evo_cycle *c, const double *device_vals, int m, double *out)
+{
+    if (!c || !device_vals || !out || m < 0) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    k_vecsum_out<<<1, 32, 0, c->stream>>>(device_vals, m, &c->d_state->sum);
+    CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c->h_state->sum;
     return EVO_OK;
 }
 

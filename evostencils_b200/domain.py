@@ -1,0 +1,357 @@
+"""Domain decomposition of ONE grid over several GPUs: z-slabs, halo exchange between statements.
+
+Reference: the generated ExaStencils code can split a grid into blocks/fragments and exchanges ghost
+layers with MPI (`communicate Solution` statements, example_problems/lib/domain_onePatch.knowledge sets one
+block); every shipped configuration runs one block on one node.  Here the same lowered op
+list is executed slab-wise on N GPUs, one process per GPU, with `torch.distributed` (NCCL over NVLink) moving the
+ghost planes between statements.  The numerics are BIT-IDENTICAL to the undecomposed solve for any N:
+
+* every statement is evaluated per node with the same arithmetic, red-black half sweeps are order
+  independent within a colour, and ghost planes are refreshed before a statement reads them;
+* residual norms use the canonical reduction (rows -> planes -> total); the plane sums are all-gathered and
+  reduced in the canonical order on every rank.
+
+Layout (mirrors `evo_problem_set_slab`, csrc/evo_runtime.cu): level `lc` splits its inner planes evenly; a
+rank owning planes [a, b] of level l owns [2a-1, 2b] of level l+1 (the last rank also 2b+1).  Coarser levels
+are replicated: the restriction from level lc is computed plane-wise by the owners and all-gathered, and every
+rank runs the (tiny) coarse part of the cycle redundantly.  Each slab carries GHOST = 2 planes per side (one
+red-black sweep = two dependent half sweeps).
+
+`SlabLayout` and the exchange schedule are pure Python (tested on CPU with gloo); the statements themselves
+run only through the CUDA library (no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import oplist as ol
+
+GHOST = 2
+
+
+class SlabLayout:
+    """Ownership of global z planes per level and rank."""
+
+    def __init__(self, max_level: int, coarsest_distributed_level: int, world: int):
+        lc = coarsest_distributed_level
+        if lc < 5 or lc > max_level:
+            raise ValueError("coarsest distributed level must be in [5, max_level]")
+        inner = (1 << lc) - 1
+        if inner < 2 * world:
+            raise ValueError("too many ranks for the coarsest distributed level")
+        self.max_level, self.lc, self.world = max_level, lc, world
+        self.owned: Dict[int, List[Tuple[int, int]]] = {}
+        base, rem = divmod(inner, world)
+        rows = []
+        for r in range(world):
+            a = 1 + r * base + min(r, rem)
+            rows.append((a, a + base + (1 if r < rem else 0) - 1))
+        self.owned[lc] = rows
+        for l in range(lc + 1, max_level + 1):
+            rows = [(2 * a - 1, 2 * b + (1 if r == world - 1 else 0)) for r, (a, b) in enumerate(self.owned[l - 1])]
+            self.owned[l] = rows
+        # "virtual" ownership of the first replicated level: coarse planes Z whose fine planes 2Z-1..2Z+1 the rank
+        # holds (owned + one ghost plane)
+        self.owned[lc - 1] = [((a + 1) // 2, b // 2) for (a, b) in self.owned[lc]]
+
+    def distributed(self, level: int) -> bool:
+        return level >= self.lc
+
+    def local(self, level: int, rank: int) -> dict:
+        """Local array geometry of a distributed level (same numbers as evo_problem_slab_info)."""
+        a, b = self.owned[level][rank]
+        return {"zoff": a - GHOST, "nz": b - a + 1 + 2 * GHOST, "zlo": GHOST, "zhi": GHOST + b - a, "g0": a, "g1": b}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# what a statement needs / produces, in ghost planes: used to decide which exchanges to run
+def exchanges_after(op: ol.Op, layout: SlabLayout) -> List[Tuple[int, int]]:
+    """(level, buffer) pairs whose ghost planes must be refreshed after `op` ran on the owned planes."""
+    c, l = op.code, op.level
+    if c == ol.OP_SMOOTH and layout.distributed(l):
+        return [(l, ol.BUF_SOL)]
+    if c == ol.OP_RESIDUAL and layout.distributed(l):
+        return [(l, op.dst)]
+    if c == ol.OP_RESTRICT and layout.distributed(l - 1):
+        return [(l - 1, op.dst)]
+    if c == ol.OP_PROLONG_ADD and layout.distributed(l):
+        return [(l, ol.BUF_SOL)]
+    if c == ol.OP_COPY and layout.distributed(l):
+        return []
+    return []
+
+
+def check_supported(program: ol.Program, layout: SlabLayout):
+    ok = {ol.OP_ZERO, ol.OP_COPY, ol.OP_RESIDUAL, ol.OP_SMOOTH, ol.OP_RESTRICT, ol.OP_PROLONG_ADD, ol.OP_COARSE_SOLVE}
+    for op in program.ops:
+        if layout.distributed(op.level) and op.code not in ok:
+            raise ValueError(f"statement {op.code} on a distributed level is not supported by the slab decomposition")
+        if op.code == ol.OP_COARSE_SOLVE and layout.distributed(op.level):
+            raise ValueError("the coarse-grid solver must run on a replicated level")
+
+
+# --------------------------------------------------------------------------------------------------------------
+class _DevArray:
+    """`__cuda_array_interface__` view of a library-owned device array (zero copy into torch)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class SlabRank:
+    """One rank's slab problem + cycle on its GPU."""
+
+    def __init__(self, problem, program: ol.Program, rank: int, layout: SlabLayout, device: int, stream):
+        import torch
+        from .backend import DeviceProblem
+        self.torch = torch
+        self.rank, self.layout, self.device, self.stream = rank, layout, device, stream
+        self.problem = problem
+        with torch.cuda.device(device):
+            self.dp = DeviceProblem(problem, device, slab=(rank, layout.world, layout.lc))
+            self.cycle = self.dp.build(program)
+            self.cycle.set_stream(stream.cuda_stream)   # statements and exchanges share one stream per device
+            self.cycle.reset()
+        self.info = {l: self.dp.slab_info(l) for l in range(problem.min_level, problem.max_level + 1)}
+        self._c_ops = [(op, (ol.CEvoOp * 1)(op.to_c())) for op in program.ops]
+
+    def view(self, level: int, buf: int):
+        """torch view [planes, n, pitch] of the CURRENT device array of (level, buf)."""
+        i = self.info[level]
+        n = self.problem.nodes(level)
+        ptr = self.cycle.buffer_ptr(level, buf)
+        return self.torch.as_tensor(_DevArray(ptr, (i["nz"], n, i["pitch"])), device=f"cuda:{self.device}")
+
+    def close(self):
+        self.cycle.close()
+        self.dp.close()
+
+
+class LocalComm:
+    """All slabs live in this process (single-GPU emulation or one process driving several GPUs): copies."""
+
+    def __init__(self, ranks: Sequence[SlabRank]):
+        self.ranks = list(ranks)
+        self.world = len(ranks)
+
+    def halo(self, level: int, buf: int):
+        views = [r.view(level, buf) for r in self.ranks]
+        for r in range(self.world - 1):
+            lo, hi = self.ranks[r], self.ranks[r + 1]
+            il, ih = lo.info[level], hi.info[level]
+            # top owned planes of r -> bottom ghosts of r+1; bottom owned planes of r+1 -> top ghosts of r
+            views[r + 1][ih["zlo"] - GHOST:ih["zlo"]].copy_(views[r][il["zhi"] - GHOST + 1:il["zhi"] + 1])
+            views[r][il["zhi"] + 1:il["zhi"] + 1 + GHOST].copy_(views[r + 1][ih["zlo"]:ih["zlo"] + GHOST])
+
+    def gather_planes(self, level: int, buf: int, ranges: Sequence[Tuple[int, int]]):
+        """Replicated level: rank r computed planes ranges[r]; make every copy complete."""
+        views = [r.view(level, buf) for r in self.ranks]
+        for src, (a, b) in enumerate(ranges):
+            if b < a:
+                continue
+            for dst in range(self.world):
+                if dst != src:
+                    views[dst][a:b + 1].copy_(views[src][a:b + 1])
+
+    def gather_sums(self, parts: Sequence, sizes: Sequence[int]):
+        torch = self.ranks[0].torch
+        dev = parts[0].device
+        return torch.cat([p.to(dev) for p in parts])
+
+
+class DistComm:
+    """One slab per process: torch.distributed point-to-point (NCCL on GPUs; gloo in the CPU tests)."""
+
+    def __init__(self, rank_state, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.ranks = [rank_state]
+        self.rank, self.world, self.group = rank, world, group
+
+    def halo(self, level: int, buf: int):
+        dist = self.dist
+        me = self.ranks[0]
+        v, i = me.view(level, buf), me.info[level]
+        ops = []
+        if self.rank + 1 < self.world:
+            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - GHOST + 1:i["zhi"] + 1], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + GHOST], self.rank + 1, self.group))
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + GHOST], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - GHOST:i["zlo"]], self.rank - 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def gather_planes(self, level: int, buf: int, ranges: Sequence[Tuple[int, int]]):
+        v = self.ranks[0].view(level, buf)
+        works = []
+        for src, (a, b) in enumerate(ranges):
+            if b >= a:
+                works.append(self.dist.broadcast(v[a:b + 1], src=src, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def gather_sums(self, parts: Sequence, sizes: Sequence[int]):
+        torch = self.ranks[0].torch
+        mine = parts[0]
+        full = torch.empty(sum(sizes), dtype=mine.dtype, device=mine.device)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        works = []
+        full[offs[self.rank]:offs[self.rank + 1]].copy_(mine)
+        for src in range(self.world):
+            works.append(self.dist.broadcast(full[offs[src]:offs[src + 1]], src=src, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        return full
+
+
+class DomainOutcome:
+    def __init__(self, iterations, residuals, time_ms, exchanges):
+        self.iterations = iterations
+        self.residuals = np.asarray(residuals, dtype=np.float64)
+        self.initial_residual = float(residuals[0])
+        self.final_residual = float(residuals[-1])
+        self.time_ms = time_ms
+        self.exchanges = exchanges
+
+
+class DomainSolver:
+    """Runs the generated solver's outer loop (same semantics as evo_cycle_solve) slab-wise.
+
+    `ranks` are the slabs this process drives: all of them with :class:`LocalComm`, exactly one with
+    :class:`DistComm`."""
+
+    def __init__(self, problem, program: ol.Program, layout: SlabLayout, ranks: Sequence[SlabRank], comm):
+        check_supported(program, layout)
+        self.problem, self.program, self.layout = problem, program, layout
+        self.ranks, self.comm = list(ranks), comm
+        self.exchanges = 0
+        self.torch = self.ranks[0].torch
+
+    def _streams(self):
+        """Context: make every local slab's stream the current stream of its device."""
+        import contextlib
+        stack = contextlib.ExitStack()
+        seen = set()
+        for r in self.ranks:
+            if r.device not in seen:
+                seen.add(r.device)
+                stack.enter_context(self.torch.cuda.stream(r.stream))
+        return stack
+
+    # -- factory helpers -------------------------------------------------------------------------------
+    @classmethod
+    def emulate(cls, problem, program, world: int, lc: Optional[int] = None, devices: Optional[Sequence[int]] = None):
+        """All `world` slabs driven by this process (device list: one entry per slab, default all on cuda:0)."""
+        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world), world)
+        import torch
+        devices = list(devices) if devices is not None else [0] * world
+        streams = {dv: torch.cuda.Stream(dv) for dv in set(devices)}
+        ranks = [SlabRank(problem, program, r, layout, devices[r], streams[devices[r]]) for r in range(world)]
+        return cls(problem, program, layout, ranks, LocalComm(ranks))
+
+    @classmethod
+    def distributed(cls, problem, program, rank: int, world: int, device: int, lc: Optional[int] = None, group=None):
+        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world), world)
+        import torch
+        me = SlabRank(problem, program, rank, layout, device, torch.cuda.Stream(device))
+        return cls(problem, program, layout, [me], DistComm(me, rank, world, group))
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+    # -- execution -------------------------------------------------------------------------------------
+    def _run_op(self, idx: int):
+        op = self.program.ops[idx]
+        lay = self.layout
+        if op.code == ol.OP_RESTRICT and op.level == lay.lc:
+            # fine level distributed, coarse level replicated: owners compute their planes, then all-gather
+            ranges = lay.owned[lay.lc - 1]
+            for r in self.ranks:
+                a, b = ranges[r.rank]
+                if b >= a:
+                    r.cycle.exec_ops(r._c_ops[idx][1], 1, a, b)
+            self.comm.gather_planes(op.level - 1, op.dst, ranges)
+            self.exchanges += 1
+            return
+        for r in self.ranks:
+            r.cycle.exec_ops(r._c_ops[idx][1], 1)
+        for (lvl, buf) in exchanges_after(op, lay):
+            self.comm.halo(lvl, buf)
+            self.exchanges += 1
+
+    def cycle(self):
+        with self._streams():
+            for idx in range(len(self.program.ops)):
+                self._run_op(idx)
+
+    def residual_norm(self) -> float:
+        torch = self.torch
+        with self._streams():
+            parts = []
+            for r in self.ranks:
+                ptr, n = r.cycle.residual_plane_sums()
+                parts.append(torch.as_tensor(_DevArray(ptr, (n,)), device=f"cuda:{r.device}"))
+            top = self.problem.max_level
+            sizes = [b - a + 1 for (a, b) in self.layout.owned[top]]
+            full = self.comm.gather_sums(parts, sizes).contiguous()
+            assert full.numel() == self.problem.nodes(top) - 2
+            s = self.ranks[0].cycle.vecsum(full.data_ptr(), full.numel())
+        return math.sqrt(s)
+
+    def solve(self, tol: float, max_iters: int) -> DomainOutcome:
+        """`repeat until res < tol * res0 or it >= maxIts` (2D_FD_Poisson_fromL2.exa3:3-4), timed on the device."""
+        torch = self.torch
+        with self._streams():
+            for r in self.ranks:
+                r.cycle.reset()
+            # initial ghost planes of SOL / RHS come from the upload (every local plane was copied)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.exchanges = 0
+            for dv in {r.device for r in self.ranks}:
+                torch.cuda.synchronize(dv)
+            ev0.record()
+            hist = [self.residual_norm()]
+            it = 0
+            res0 = hist[0]
+            while it < max_iters and math.isfinite(hist[-1]):
+                self.cycle()
+                it += 1
+                hist.append(self.residual_norm())
+                if hist[-1] < tol * res0:
+                    break
+            ev1.record()
+            for dv in {r.device for r in self.ranks}:
+                torch.cuda.synchronize(dv)
+        return DomainOutcome(it, hist, ev0.elapsed_time(ev1), self.exchanges)
+
+    def gather_solution(self) -> np.ndarray:
+        """Dense finest-level solution assembled from the owned planes of the local slabs (tests)."""
+        p = self.problem
+        n = p.nodes(p.max_level)
+        out = np.full((n, n, n), np.nan)
+        for dv in {r.device for r in self.ranks}:
+            self.torch.cuda.synchronize(dv)
+        for r in self.ranks:
+            i = r.info[p.max_level]
+            v = r.view(p.max_level, ol.BUF_SOL)
+            lo, hi = i["zlo"], i["zhi"]
+            if r.rank == 0:
+                lo -= 1
+            if r.rank == self.layout.world - 1:
+                hi += 1
+            out[lo + i["zoff"]:hi + 1 + i["zoff"]] = v[lo:hi + 1, :, :n].cpu().numpy()
+        return out
+
+
+def default_lc(problem, world: int) -> int:
+    """Coarsest distributed level: keep at least 8 planes per rank, never below level 5 (33^3)."""
+    lc = 5
+    while ((1 << lc) - 1) < 8 * world:
+        lc += 1
+    return min(lc, problem.max_level)

@@ -173,6 +173,17 @@ int evo_problem_destroy(evo_problem *p);
  * `level`; n_doubles must be (2^level+1)^dim * scalar_words                                    */
 int evo_problem_set_field(evo_problem *p, int level, int buf, int field, const double *host, size_t n_doubles);
 
+/* -- domain decomposition of ONE grid over several GPUs (the reference's generated code can
+ *    split a grid into blocks/fragments but all shipped configurations use one, lib/domain_onePatch.knowledge).
+ *    z-slabs with nested ownership: level `coarsest_distributed_level` splits its inner planes evenly over the
+ *    ranks, a rank owning planes [a, b] of level l owns [2a-1, 2b] of level l+1 (the last rank also 2b+1);
+ *    coarser levels are replicated on every rank.  Each slab carries 2 ghost planes per side.  Must be called
+ *    before evo_problem_set_field / evo_cycle_build.  3-D real scalar problems only.                       */
+int evo_problem_set_slab(evo_problem *p, int rank, int world, int coarsest_distributed_level);
+/* info[0..7] = zoff (global index of local plane 0), local plane count, first owned local plane, last owned local
+ * plane, first owned global plane, last owned global plane, row pitch (entries), plane stride (entries)      */
+int evo_problem_slab_info(evo_problem *p, int level, long long info[8]);
+
 /* -- cycle = one lowered individual (replaces generate_cycle_function + java + make,
  *    exastencils.py:318-336, :381-415)                                                          */
 int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, const evo_level_operator *operators,
@@ -185,6 +196,20 @@ int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, double *hos
 int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, const double *host, size_t n_doubles);
 /* RES@finest = RHS - A*SOL and its L2 norm over inner nodes (gen_resNorm of the generated solver) */
 int evo_cycle_residual_norm(evo_cycle *c, double *norm);
+/* -- host-orchestrated execution (domain decomposition: halo exchanges happen between statements) ----------- */
+/* use `cuda_stream` (a cudaStream_t, e.g. torch's current stream) for everything the cycle enqueues         */
+int evo_cycle_set_stream(evo_cycle *c, void *cuda_stream);
+/* enqueue statements (no synchronisation).  zc_lo/zc_hi >= 0 restrict a RESTRICT statement to the coarse
+ * (local) planes [zc_lo, zc_hi]                                                                            */
+int evo_cycle_exec_ops(evo_cycle *c, const evo_op *ops, int n_ops, int zc_lo, int zc_hi);
+/* current device address of a field (the two slots of SOL swap after out-of-place statements)               */
+int evo_cycle_buffer(evo_cycle *c, int level, int buf, int field, void **device_ptr);
+/* RES@finest = RHS - A SOL on the owned planes + canonical per-plane sums of |r|^2: device array of
+ * `*count` doubles (one per owned plane, ascending)                                                        */
+int evo_cycle_residual_plane_sums(evo_cycle *c, double **device_sums, int *count);
+/* canonical vecsum (lane-strided + butterfly) of a device array, result on the host (synchronises)           */
+int evo_cycle_vecsum(evo_cycle *c, const double *device_vals, int m, double *out);
+
 /* measurement hook (bench.py roofline): launch the kernels of ONE statement `repeat` times on the
  * cycle's stream, bracketed by CUDA events; returns the average milliseconds per execution and the
  * number of kernel launches one execution makes.  The reference's counterpart is the per-function

@@ -1,0 +1,135 @@
+"""Host logic of the slab decomposition (no GPU): ownership arithmetic and the torch.distributed exchange
+schedule (gloo, world_size 2 and 3) on CPU tensors standing in for the device arrays."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from evostencils_b200 import cycles, domain, oplist as ol, problems
+
+
+@pytest.mark.parametrize("max_level,lc,world", [(9, 5, 2), (9, 5, 4), (9, 6, 8), (7, 5, 3), (6, 6, 5), (9, 5, 15)])
+def test_layout_partitions_every_level(max_level, lc, world):
+    lay = domain.SlabLayout(max_level, lc, world)
+    for l in range(lc, max_level + 1):
+        n = (1 << l) + 1
+        covered = []
+        for r in range(world):
+            a, b = lay.owned[l][r]
+            assert b - a + 1 >= domain.GHOST            # a slab can fill its neighbour's ghost planes
+            covered += list(range(a, b + 1))
+        assert covered == list(range(1, n - 1))         # inner planes, no gap, no overlap, ascending
+        if l > lc:
+            for r in range(world):                       # nested: fine planes over the rank's coarse planes
+                a, b = lay.owned[l - 1][r]
+                fa, fb = lay.owned[l][r]
+                assert fa == 2 * a - 1 and fb in (2 * b, 2 * b + 1)
+    # virtual ownership of the first replicated level covers its inner planes once and is computable locally
+    nc = (1 << (lc - 1)) + 1
+    covered = []
+    for r in range(world):
+        a, b = lay.owned[lc - 1][r]
+        fa, fb = lay.owned[lc][r]
+        covered += list(range(a, b + 1))
+        for z in range(a, b + 1):
+            assert fa - 1 <= 2 * z - 1 and 2 * z + 1 <= fb + 1   # needs one ghost plane at most
+    assert covered == list(range(1, nc - 1))
+
+
+def test_layout_rejects_bad_arguments():
+    with pytest.raises(ValueError):
+        domain.SlabLayout(6, 4, 2)
+    with pytest.raises(ValueError):
+        domain.SlabLayout(6, 5, 16)
+    with pytest.raises(ValueError):
+        domain.SlabLayout(6, 7, 2)
+
+
+def test_exchange_schedule_of_a_v_cycle():
+    prob = problems.Poisson3D(2, 7)
+    prog = cycles.v_cycle(prob, 2, 1, 1.25, True)
+    lay = domain.SlabLayout(7, 6, 2)
+    domain.check_supported(prog, lay)
+    ex = [e for op in prog.ops for e in domain.exchanges_after(op, lay)]
+    # per distributed level: 3 smoothing sweeps + correction (SOL), residual (RES); level 6 also receives RHS
+    assert ex.count((7, ol.BUF_SOL)) == 4 and ex.count((6, ol.BUF_SOL)) == 4
+    assert ex.count((7, ol.BUF_RES)) == 1 and ex.count((6, ol.BUF_RES)) == 1
+    assert ex.count((6, ol.BUF_RHS)) == 1
+    assert all(l >= 6 for l, _ in ex)
+
+
+class _FakeRank:
+    """CPU stand-in of SlabRank: global field g[z, y, x] = z*10000 + y*100 + x, ghosts poisoned."""
+
+    def __init__(self, rank, layout, level):
+        self.torch = torch
+        self.rank, self.device = rank, "cpu"
+        self.info = {level: layout.local(level, rank)}
+        i = self.info[level]
+        n = (1 << level) + 1
+        z = torch.arange(i["zoff"], i["zoff"] + i["nz"], dtype=torch.float64).view(-1, 1, 1)
+        y = torch.arange(n, dtype=torch.float64).view(1, -1, 1)
+        x = torch.arange(n, dtype=torch.float64).view(1, 1, -1)
+        self.expected = (z * 10000 + y * 100 + x).contiguous()
+        self.data = self.expected.clone()
+        self.data[: i["zlo"]] = -1.0
+        self.data[i["zhi"] + 1:] = -1.0
+
+    def view(self, level, buf):
+        return self.data
+
+
+def _worker(rank, world, port, level, lc):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lay = domain.SlabLayout(level, lc, world)
+        me = _FakeRank(rank, lay, level)
+        comm = domain.DistComm(me, rank, world)
+        comm.halo(level, ol.BUF_SOL)
+        i = me.info[level]
+        lo = i["zlo"] - (domain.GHOST if rank > 0 else 0)
+        hi = i["zhi"] + (domain.GHOST if rank < world - 1 else 0)
+        assert torch.equal(me.data[lo:hi + 1], me.expected[lo:hi + 1])
+        # outer ghosts of the first / last rank have no neighbour: untouched
+        if rank == 0:
+            assert (me.data[: i["zlo"]] == -1.0).all()
+        if rank == world - 1:
+            assert (me.data[i["zhi"] + 1:] == -1.0).all()
+        # replicated-level gather: every rank computed its own plane range
+        nc = (1 << (lc - 1)) + 1
+        full = torch.zeros(nc, 4, 4, dtype=torch.float64)
+        a, b = lay.owned[lc - 1][rank]
+        full[a:b + 1] = torch.arange(a, b + 1, dtype=torch.float64).view(-1, 1, 1)
+        me.data = full
+        comm.gather_planes(lc - 1, ol.BUF_RHS, lay.owned[lc - 1])
+        want = torch.arange(nc, dtype=torch.float64).view(-1, 1, 1).expand(nc, 4, 4).clone()
+        want[0] = 0.0
+        want[-1] = 0.0
+        assert torch.equal(full, want)
+        # plane sums all-gather in rank order
+        sizes = [q - p + 1 for (p, q) in lay.owned[level]]
+        p, q = lay.owned[level][rank]
+        mine = torch.arange(p, q + 1, dtype=torch.float64)
+        got = comm.gather_sums([mine], sizes)
+        assert torch.equal(got, torch.arange(1, (1 << level), dtype=torch.float64))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_halo_exchange(world):
+    mp.spawn(_worker, args=(world, _free_port(), 6, 5), nprocs=world, join=True)
