@@ -316,6 +316,73 @@ def run_ours(args, rank, world, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
+# ONE evaluation spread over the GPUs (z-slab domain decomposition, halo exchange over NCCL).
+# Strong scaling; results are bit-identical to the single-GPU evaluation (tests/test_gpu_domain.py).
+def run_domain(args, rank, world, local_rank):
+    import torch
+    from evostencils_b200 import domain
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prob, prog = make_workload(args.workload)
+    s = prob.settings
+    slabs = world if world > 1 else max(1, args.slabs)
+    if world > 1:
+        solver = domain.DomainSolver.distributed(prob, prog, rank, world, local_rank, lc=args.lc or None)
+    else:
+        solver = domain.DomainSolver.emulate(prob, prog, slabs, lc=args.lc or None)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        out = solver.solve(s.tol, s.max_iters)
+    barrier()
+    t_dev = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = solver.solve(s.tol, s.max_iters)
+        t_dev += out.time_ms
+    barrier()
+    t_wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = float(t.item())
+    value = args.steps / (t_dev * 1e-3)
+    ndof = float((prob.nodes(prob.max_level) - 2) ** prob.dim)
+    cf = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters)[1]
+    if rank == 0:
+        cfg = workload_config(args.workload, prob, world)
+        cfg["parallelism"] = (f"z-slab domain decomposition x{slabs} "
+                              f"({'NCCL send/recv' if world > 1 else 'slabs emulated on one GPU'}), "
+                              f"levels < {solver.layout.lc} replicated")
+        line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "iterations_per_eval": out.iterations, "convergence_factor": cf,
+                "residuals_last": float(out.residuals[-1]),
+                "ms_per_cycle": t_dev / args.steps / max(out.iterations, 1),
+                "cycle_gdof_s": ndof * out.iterations * args.steps / (t_dev * 1e-3) / 1e9,
+                "halo_exchanges_per_eval": out.exchanges, "wall_s_timed_region": t_wall, "clocks": clocks,
+                "e2e": None, "gpu_launches": None, "roofline": None, "cpu_baseline": None,
+                "note": "secondary mode (--domain): the default bench line is the population-sharded one"}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # BASELINE.json configs[4]: one G3P generation = 256 evolved cycles, half on Poisson 2D (levels 5..9),
 # half on LinearElasticity (levels 4..8), individuals sharded round-robin over the GPUs
 # (reference: optimization/program.py:534-535 distributes `i % nprocs == rank`).
@@ -462,6 +529,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch kernels directly (host-side solver loop) so that ncu can see them; not a bench value")
+    ap.add_argument("--domain", action="store_true",
+                    help="strong scaling: ONE evaluation decomposed into z-slabs over the GPUs (SURVEY.md 8e.2)")
+    ap.add_argument("--slabs", type=int, default=2, help="--domain on one GPU: number of emulated slabs")
+    ap.add_argument("--lc", type=int, default=0, help="--domain: coarsest distributed level (default: automatic)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -470,6 +541,8 @@ def main():
         run_population(args, rank, world, local_rank)
     elif args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.domain:
+        run_domain(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -560,11 +560,209 @@ static bool try_smooth_point(int, const Geom &g, const OpSten &st, const SmoothP
         return false;
     }
 }
-template <typename T, int DIM, int NF>
-static bool try_residual_restrict(int, const Geom &, const Geom &, const OpSten &, const TransferW &, Fields<T>, Fields<T>,
-                                  Fields<T>, cudaStream_t)
+#ifndef EVO_RR_CY
+#define EVO_RR_CY 4
+#define EVO_RR_CX 32
+#endif
+// ---------------------------------------------------------------------------------------------
+// Fused RHS@(l-1) = R (f - A u), 3-D 7-point operator, dense 27-point restriction: the fine residual never
+// reaches HBM (16 B/fine DOF read + 1 B written instead of 24 + 9 for the two separate statements).
+// A CTA owns CY x CX coarse nodes and streams over a chunk of coarse planes.  u and f planes of the fine tile
+// (+ halo) arrive by TMA into shared-memory rings, issued a full step (two fine planes) ahead, so HBM stays
+// busy while the CTA computes.  Per coarse plane Z the two new fine residual planes 2Z, 2Z+1 are computed from
+// shared memory into a 5-slot residual ring (plane 2Z-1 is kept from the previous step; x-even and x-odd columns
+// are stored separately so that the stride-2 reads of the restriction are conflict free), then the coarse
+// values are formed by adding the 27 terms in ascending stencil-table order like the generic kernel.  Per node the
+// arithmetic is that of k3_residual_rows / k_restrict -> bit-identical.  The residual is 0 on the boundary layer
+// (only x = 0 / n-1 can be touched: 2Y+-1 and 2Z+-1 are inner for inner coarse nodes).  z-slab aware.
+template <int CY, int CX>
+struct RrCfg {
+    static constexpr int RROWS = 2 * CY + 1;                       // fine residual rows of the tile
+    static constexpr int NPAIR = CX + 1;                           // column pairs (fine x = 2X0-2+2j, +1), j = 0 .. CX
+    static constexpr int ITEMS = RROWS * NPAIR;                    // one thread per (row, pair), fixed for the whole stream
+    static constexpr int NT = (ITEMS + 31) / 32 * 32;
+    static constexpr int LX = 2 * CX + 4;                          // box width: fine x = 2*X0-2 .. 2*X0+2*CX+1 (even start)
+    static constexpr int ULY = 2 * CY + 3, FLY = RROWS;            // box rows of u (halo) and f
+    static constexpr int NU = 6, NF = 4, NR = 5;                   // ring depths (planes)
+    static constexpr int USTRIDE = (LX * ULY * 8 + 127) / 128 * 16, FSTRIDE = (LX * FLY * 8 + 127) / 128 * 16;   // doubles
+    static constexpr int RA = CX + 1, RB = CX;                     // odd-x (2X-1, first) / even-x (2X, at offset RA) entries per row
+    static constexpr int RPITCH = RA + RB + 1;                     // doubles per residual row
+    static constexpr int RSTRIDE = RROWS * RPITCH;
+    static constexpr size_t SMEM = ((size_t)NU * USTRIDE + (size_t)NF * FSTRIDE + (size_t)NR * RSTRIDE) * 8;
+};
+
+template <int CY, int CX>
+__global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(const __grid_constant__ CUtensorMap umap,
+                                                                             const __grid_constant__ CUtensorMap fmap,
+                                                                             const Geom gf, const Geom gc, const Star7 c,
+                                                                             const DenseW R, double *__restrict__ dst,
+                                                                             const int zchunk)
 {
-    return false;
+    using C = RrCfg<CY, CX>;
+    extern __shared__ __align__(128) double rr_smem[];
+    __shared__ __align__(8) uint64_t ubar[C::NU], fbar[C::NF];
+    double *uring = rr_smem, *fring = rr_smem + (size_t)C::NU * C::USTRIDE, *rring = fring + (size_t)C::NF * C::FSTRIDE;
+    const int tid = threadIdx.x;
+    const int X0 = 1 + blockIdx.x * CX, Y0 = 1 + blockIdx.y * CY;
+    const int Za = gc.zlo + blockIdx.z * zchunk, Zb = min(Za + zchunk - 1, gc.zhi);
+    const int xb = 2 * X0 - 2, yub = 2 * Y0 - 2, yfb = 2 * Y0 - 1;   // box origins (fine coordinates)
+    const int nfi = gf.n - 2, nci = gc.n - 2;
+    const int zr0 = 2 * (Za + gc.zoff) - gf.zoff - 1;                // first / last fine residual plane (local)
+    const int zr1 = 2 * (Zb + gc.zoff) - gf.zoff + 1;
+    const int q0 = zr0 - 1, qmax = zr1 + 1;                           // u planes q0 .. qmax, f planes zr0 .. zr1
+
+    if (tid == 0) {
+        for (int i = 0; i < C::NU; ++i) mbar_init(&ubar[i], 1);
+        for (int i = 0; i < C::NF; ++i) mbar_init(&fbar[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    int u_issued = q0 - 1, f_issued = zr0 - 1;   // only thread 0 uses these
+    auto issue_u = [&](int upto) {
+        for (upto = min(upto, qmax); u_issued < upto;) {
+            const int q = ++u_issued, sl = (q - q0) % C::NU;
+            mbar_expect_tx(&ubar[sl], C::LX * C::ULY * 8);
+            tma_load_plane(uring + (size_t)sl * C::USTRIDE, &umap, xb, yub, q, &ubar[sl]);
+        }
+    };
+    auto issue_f = [&](int upto) {
+        for (upto = min(upto, zr1); f_issued < upto;) {
+            const int q = ++f_issued, sl = (q - zr0) % C::NF;
+            mbar_expect_tx(&fbar[sl], C::LX * C::FLY * 8);
+            tma_load_plane(fring + (size_t)sl * C::FSTRIDE, &fmap, xb, yfb, q, &fbar[sl]);
+        }
+    };
+    auto wait_u = [&](int q) { mbar_wait(&ubar[(q - q0) % C::NU], (uint32_t)(((q - q0) / C::NU) & 1)); };
+    auto wait_f = [&](int q) { mbar_wait(&fbar[(q - zr0) % C::NF], (uint32_t)(((q - zr0) / C::NF) & 1)); };
+    if (tid == 0) {
+        issue_u(q0 + C::NU - 1);
+        issue_f(zr0 + C::NF - 1);
+    }
+
+    // this thread's residual item: row r, column pair j -> fine x = xa = 2(X0+j-1) (even-x array entry j-1, at
+    // offset RA) and xa + 1 = 2(X0+j)-1 (odd-x array entry j); the pair is 16-byte aligned in the box (column 2j)
+    const bool active = tid < C::ITEMS;
+    const int r = active ? tid / C::NPAIR : 0, j = active ? tid - (tid / C::NPAIR) * C::NPAIR : 0;
+    const int xa = xb + 2 * j, yy = yfb + r;
+    const bool ok_a = active && j >= 1 && xa <= nfi && yy <= nfi;       // j = 0: x = 2X0-2 belongs to the left neighbour
+    const bool ok_b = active && xa + 1 <= nfi && yy <= nfi;
+    const int ou = (r + 1) * C::LX + 2 * j, of = r * C::LX + 2 * j;
+    const int oxm = ou - (j >= 1 ? 1 : 0);                               // left neighbour of the pair (unused for j = 0)
+    const int res_a = r * C::RPITCH + C::RA + j - 1, res_b = r * C::RPITCH + j;
+    double2 um = make_double2(0.0, 0.0), u0 = um;
+
+    // residual of fine plane p for this thread's pair; um / u0 hold the centre pairs of planes p-1 / p
+    auto residual_plane = [&](int p) {
+        const double *s0 = uring + (size_t)((p - q0) % C::NU) * C::USTRIDE;
+        const double *sp = uring + (size_t)((p + 1 - q0) % C::NU) * C::USTRIDE;
+        const double *fp = fring + (size_t)((p - zr0) % C::NF) * C::FSTRIDE;
+        double *rs = rring + (size_t)(p % C::NR) * C::RSTRIDE;
+        if (active) {
+            const double2 up = *reinterpret_cast<const double2 *>(sp + ou);
+            const double2 ym = *reinterpret_cast<const double2 *>(s0 + ou - C::LX);
+            const double2 yp = *reinterpret_cast<const double2 *>(s0 + ou + C::LX);
+            const double2 fv = *reinterpret_cast<const double2 *>(fp + of);
+            const double xm = s0[oxm], xp = s0[ou + 2];
+            double sa = 0.0, sb = 0.0;
+            sa = sa + c.zm * um.x;  sb = sb + c.zm * um.y;
+            sa = sa + c.ym * ym.x;  sb = sb + c.ym * ym.y;
+            sa = sa + c.xm * xm;    sb = sb + c.xm * u0.x;
+            sa = sa + c.c * u0.x;   sb = sb + c.c * u0.y;
+            sa = sa + c.xp * u0.y;  sb = sb + c.xp * xp;
+            sa = sa + c.yp * yp.x;  sb = sb + c.yp * yp.y;
+            sa = sa + c.zp * up.x;  sb = sb + c.zp * up.y;
+            if (j >= 1) rs[res_a] = ok_a ? fv.x - sa : 0.0;
+            rs[res_b] = ok_b ? fv.y - sb : 0.0;
+            um = u0;
+            u0 = up;
+        }
+    };
+
+    // prologue: fine residual plane zr0 (= 2 Za - 1)
+    wait_u(q0); wait_u(q0 + 1); wait_u(q0 + 2); wait_f(zr0);
+    if (active) {
+        um = *reinterpret_cast<const double2 *>(uring + ou);
+        u0 = *reinterpret_cast<const double2 *>(uring + (size_t)C::USTRIDE + ou);
+    }
+    residual_plane(zr0);
+    __syncthreads();
+    if (tid == 0) { fence_proxy_async(); issue_u(zr0 + C::NU - 1); issue_f(zr0 + C::NF); }
+
+    for (int Z = Za; Z <= Zb; ++Z) {
+        const int zf = zr0 + 1 + 2 * (Z - Za);
+        wait_u(zf + 1); wait_f(zf);
+        residual_plane(zf);
+        wait_u(zf + 2); wait_f(zf + 1);
+        residual_plane(zf + 1);
+        __syncthreads();   // residual planes complete; u planes <= zf and f planes <= zf+1 are dead
+        if (tid == 0) { fence_proxy_async(); issue_u(zf + C::NU); issue_f(zf + 1 + C::NF); }
+        if (tid < CY * CX) {
+            const double *pm = rring + (size_t)((zf - 1) % C::NR) * C::RSTRIDE;
+            const double *p0 = rring + (size_t)(zf % C::NR) * C::RSTRIDE;
+            const double *pp = rring + (size_t)((zf + 1) % C::NR) * C::RSTRIDE;
+            const int ry = tid / CX, rx = tid - ry * CX;
+            const int X = X0 + rx, Y = Y0 + ry;
+            if (X <= nci && Y <= nci) {
+                double acc = 0.0;
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const double *pl = dz == 0 ? pm : (dz == 1 ? p0 : pp);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const double *row = pl + (2 * ry + dy) * C::RPITCH;
+                        acc = acc + R.w[dz * 9 + dy * 3 + 0] * row[rx];             // fine x = 2X - 1
+                        acc = acc + R.w[dz * 9 + dy * 3 + 1] * row[C::RA + rx];     // fine x = 2X
+                        acc = acc + R.w[dz * 9 + dy * 3 + 2] * row[rx + 1];         // fine x = 2X + 1
+                    }
+                }
+                dst[(long long)Z * gc.plane + (long long)Y * gc.pitch + X] = acc;
+            }
+        }
+        // no second barrier: the next step writes residual planes zf+2, zf+3 into ring slots distinct from
+        // zf-1 .. zf+1 (5 slots); slot (zf-1) % 5 is only rewritten after the next step's barrier
+    }
+}
+
+template <typename T, int DIM, int NF>
+static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, const OpSten &st, const TransferW &R, Fields<T> u,
+                                  Fields<T> f, Fields<T> dst, cudaStream_t s)
+{
+    if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
+        Star7 c;
+        if (gf.n < 33 || R.nnz != 27 || !match_star7(st.s[0][0], &c) || get_encode_tiled() == nullptr) return false;
+        DenseW W;
+        for (int q = 0; q < 27; ++q) W.w[(R.oz[q] + 1) * 9 + (R.oy[q] + 1) * 3 + (R.ox[q] + 1)] = R.w[q];
+        constexpr int CY = EVO_RR_CY, CX = EVO_RR_CX;
+        using C = RrCfg<CY, CX>;
+        constexpr int NT = C::NT;
+        CUtensorMap um, fm;
+        if (!make_plane_map(&um, gf, u.p[0], C::LX, C::ULY) || !make_plane_map(&fm, gf, f.p[0], C::LX, C::FLY)) return false;
+        static int occ = 0;
+        if (occ == 0) {
+            if (cudaFuncSetAttribute(k3_residual_restrict_tma<CY, CX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+                return false;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_residual_restrict_tma<CY, CX>, NT, C::SMEM) != cudaSuccess || occ < 1) occ = 1;
+        }
+        const int nci = gc.n - 2, planes = gc.zhi - gc.zlo + 1;
+        if (planes <= 0) return true;
+        const int tx = (nci + CX - 1) / CX, ty = (nci + CY - 1) / CY;
+        // z chunks: minimise (waves) x (coarse planes per chunk + pipeline fill); a chunk recomputes one fine plane
+        const long long slots = (long long)occ * sm_count;
+        int best = 1;
+        double best_cost = 1e300;
+        for (int ch = 1; ch <= 32 && (ch == 1 || ch * 8 <= planes); ++ch) {
+            const int zc = (planes + ch - 1) / ch;
+            const long long ctas = (long long)tx * ty * ((planes + zc - 1) / zc);
+            const double cost = (double)((ctas + slots - 1) / slots) * (zc + 3);
+            if (cost < best_cost) { best_cost = cost; best = ch; }
+        }
+        const int zchunk = (planes + best - 1) / best;
+        const int chunks = (planes + zchunk - 1) / zchunk;
+        k3_residual_restrict_tma<CY, CX><<<dim3(tx, ty, chunks), NT, C::SMEM, s>>>(um, fm, gf, gc, c, W, dst.p[0], zchunk);
+        return cudaGetLastError() == cudaSuccess;
+    } else {
+        return false;
+    }
 }
 template <typename T, int DIM, int NF>
 static bool try_prolong_add(int, const Geom &gf, const Geom &gc, const TransferW &P, Fields<T> src, Fields<T> dst, double weight,

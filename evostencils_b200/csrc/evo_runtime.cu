@@ -143,7 +143,7 @@ struct evo_cycle {
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
     bool use_while_graph;
-    int zc_lo = -1, zc_hi = -1;  // coarse plane override of RESTRICT (domain decomposition)
+    int zc_lo = -1, zc_hi = -1;  // plane range override of the statement's destination level (domain decomposition)
     bool own_stream = true;
     bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
                              // (convergence test) need not be stored
@@ -450,7 +450,8 @@ template <typename T, int DIM, int NF> struct Launch {
 
     static int residual(evo_cycle *c, int l, bool norm, cudaStream_t s)
     {
-        const Geom &g = c->p->geom[l];
+        Geom g = c->p->geom[l];
+        if (c->zc_lo >= 0 && !norm) { g.zlo = c->zc_lo; g.zhi = c->zc_hi; }   // domain decomposition: include ghost planes
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              r = fields_of<T>(c->lv[l].buf[EVO_BUF_RES], NF);
         const int ni = g.n - 2;
@@ -636,12 +637,15 @@ template <typename T, int DIM, int NF> struct Launch {
     static int residual_restrict(evo_cycle *c, const evo_op &op, cudaStream_t s)
     {
         const int l = op.level;
-        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        const Geom &gf = c->p->geom[l];
+        Geom gc = c->p->geom[l - 1];
+        if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
-        if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction not supported");
-        if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s))
+        if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
+            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
             k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
+        }
         c->launch_counter++;
         CU(cudaGetLastError());
         return EVO_OK;
@@ -650,7 +654,9 @@ template <typename T, int DIM, int NF> struct Launch {
     static int prolong(evo_cycle *c, const evo_op &op, bool add, cudaStream_t s)
     {
         const int l = op.level;
-        const Geom &gf = c->p->geom[l], &gc = c->p->geom[l - 1];
+        Geom gf = c->p->geom[l];
+        const Geom &gc = c->p->geom[l - 1];
+        if (c->zc_lo >= 0) { gf.zlo = c->zc_lo; gf.zhi = c->zc_hi; }   // domain decomposition: include ghost planes
         auto src = fields_of<T>(c->lv[l - 1].buf[op.src], NF);
         auto dst = fields_of<T>(c->lv[l].buf[add ? EVO_BUF_SOL : op.dst], NF);
         if (add) {

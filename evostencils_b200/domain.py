@@ -67,25 +67,92 @@ class SlabLayout:
 
 
 # --------------------------------------------------------------------------------------------------------------
-# what a statement needs / produces, in ghost planes: used to decide which exchanges to run
-def exchanges_after(op: ol.Op, layout: SlabLayout) -> List[Tuple[int, int]]:
-    """(level, buffer) pairs whose ghost planes must be refreshed after `op` ran on the owned planes."""
-    c, l = op.code, op.level
-    if c == ol.OP_SMOOTH and layout.distributed(l):
-        return [(l, ol.BUF_SOL)]
-    if c == ol.OP_RESIDUAL and layout.distributed(l):
-        return [(l, op.dst)]
-    if c == ol.OP_RESTRICT and layout.distributed(l - 1):
-        return [(l - 1, op.dst)]
-    if c == ol.OP_PROLONG_ADD and layout.distributed(l):
-        return [(l, ol.BUF_SOL)]
-    if c == ol.OP_COPY and layout.distributed(l):
-        return []
-    return []
+# Ghost-plane validity tracking.  valid[(level, buf)] = number of ghost planes per side that hold the neighbour's
+# current values.  A statement run on the owned planes extended by e ghost planes recomputes what the neighbour
+# computes (same inputs, same arithmetic -> same bits) and saves an exchange.  The schedule depends only on the op
+# list, so every rank takes the same decisions (the exchanges are collective).
+INF = 99
+
+
+class Step:
+    """One scheduled action: ('halo', level, buf) or ('op', index, extension) or ('gather', index)."""
+    __slots__ = ("kind", "a", "b")
+
+    def __init__(self, kind, a, b=0):
+        self.kind, self.a, self.b = kind, a, b
+
+    def __repr__(self):
+        return f"Step({self.kind}, {self.a}, {self.b})"
+
+
+def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int], int]) -> List[Step]:
+    """Plan one pass over the op list; `valid` is updated in place (carry it from cycle to cycle)."""
+    steps: List[Step] = []
+    dist_ = layout.distributed
+
+    def v(l, b):
+        return INF if not dist_(l) else valid.get((l, b), 0)
+
+    def need(l, b, depth):
+        if v(l, b) < depth:
+            steps.append(Step("halo", l, b))
+            valid[(l, b)] = GHOST
+
+    for idx, op in enumerate(program.ops):
+        c, l = op.code, op.level
+        if c == ol.OP_RESTRICT and l == layout.lc:
+            need(l, op.src, 1)
+            steps.append(Step("gather", idx))
+            continue
+        if c == ol.OP_RESIDUAL_RESTRICT and dist_(l):
+            # coarse plane Z reads fine residual planes 2Z-1..2Z+1, i.e. SOL planes 2Z-2..2Z+2
+            need(l, ol.BUF_SOL, 2)
+            need(l, ol.BUF_RHS, 1)
+            if l == layout.lc:
+                steps.append(Step("gather", idx))
+            else:
+                steps.append(Step("op", idx, 0))
+                valid[(l - 1, ol.BUF_RHS)] = 0
+            continue
+        if not dist_(l):
+            steps.append(Step("op", idx, -1))
+            continue
+        if c == ol.OP_SMOOTH:
+            if op.mode == ol.MODE_REDBLACK:
+                need(l, ol.BUF_SOL, 2)
+                need(l, ol.BUF_RHS, 1)
+            else:
+                need(l, ol.BUF_SOL, 1)
+            steps.append(Step("op", idx, 0))
+            valid[(l, ol.BUF_SOL)] = 0
+        elif c == ol.OP_RESIDUAL:
+            need(l, ol.BUF_SOL, 1)
+            e = max(0, min(v(l, ol.BUF_SOL) - 1, v(l, ol.BUF_RHS), 1))
+            steps.append(Step("op", idx, e))
+            valid[(l, op.dst)] = e
+        elif c == ol.OP_RESTRICT:
+            need(l, op.src, 1)
+            steps.append(Step("op", idx, 0))
+            valid[(l - 1, op.dst)] = 0
+        elif c == ol.OP_PROLONG_ADD:
+            need(l - 1, op.src, 1)
+            e = 2 if (v(l, ol.BUF_SOL) >= 2 and v(l - 1, op.src) >= 2) else (1 if v(l, ol.BUF_SOL) >= 1 else 0)
+            steps.append(Step("op", idx, e))
+            valid[(l, ol.BUF_SOL)] = e
+        elif c == ol.OP_ZERO:
+            steps.append(Step("op", idx, 0))
+            valid[(l, op.dst)] = INF
+        elif c == ol.OP_COPY:
+            steps.append(Step("op", idx, 0))
+            valid[(l, op.dst)] = v(l, op.src)
+        else:
+            raise ValueError(f"statement {c} on a distributed level is not supported by the slab decomposition")
+    return steps
 
 
 def check_supported(program: ol.Program, layout: SlabLayout):
-    ok = {ol.OP_ZERO, ol.OP_COPY, ol.OP_RESIDUAL, ol.OP_SMOOTH, ol.OP_RESTRICT, ol.OP_PROLONG_ADD, ol.OP_COARSE_SOLVE}
+    ok = {ol.OP_ZERO, ol.OP_COPY, ol.OP_RESIDUAL, ol.OP_SMOOTH, ol.OP_RESTRICT, ol.OP_PROLONG_ADD, ol.OP_COARSE_SOLVE,
+          ol.OP_RESIDUAL_RESTRICT}
     for op in program.ops:
         if layout.distributed(op.level) and op.code not in ok:
             raise ValueError(f"statement {op.code} on a distributed level is not supported by the slab decomposition")
@@ -117,6 +184,13 @@ class SlabRank:
             self.cycle.reset()
         self.info = {l: self.dp.slab_info(l) for l in range(problem.min_level, problem.max_level + 1)}
         self._c_ops = [(op, (ol.CEvoOp * 1)(op.to_c())) for op in program.ops]
+
+    def extended(self, level: int, e: int) -> Tuple[int, int]:
+        """Owned local plane range extended by e ghost planes, clipped to the inner planes of the global grid."""
+        i = self.info[level]
+        n = self.problem.nodes(level)
+        zin0, zin1 = max(0, 1 - i["zoff"]), min(i["nz"] - 1, n - 2 - i["zoff"])
+        return max(i["zlo"] - e, zin0), min(i["zhi"] + e, zin1)
 
     def view(self, level: int, buf: int):
         """torch view [planes, n, pitch] of the CURRENT device array of (level, buf)."""
@@ -231,6 +305,8 @@ class DomainSolver:
         self.ranks, self.comm = list(ranks), comm
         self.exchanges = 0
         self.torch = self.ranks[0].torch
+        self._plans = {}
+        self._reset_validity()
 
     def _streams(self):
         """Context: make every local slab's stream the current stream of its device."""
@@ -266,33 +342,59 @@ class DomainSolver:
             r.close()
 
     # -- execution -------------------------------------------------------------------------------------
-    def _run_op(self, idx: int):
-        op = self.program.ops[idx]
+    def _run(self, st: Step):
         lay = self.layout
-        if op.code == ol.OP_RESTRICT and op.level == lay.lc:
+        if st.kind == "halo":
+            self.comm.halo(st.a, st.b)
+            self.exchanges += 1
+        elif st.kind == "gather":
             # fine level distributed, coarse level replicated: owners compute their planes, then all-gather
+            op = self.program.ops[st.a]
             ranges = lay.owned[lay.lc - 1]
             for r in self.ranks:
                 a, b = ranges[r.rank]
                 if b >= a:
-                    r.cycle.exec_ops(r._c_ops[idx][1], 1, a, b)
-            self.comm.gather_planes(op.level - 1, op.dst, ranges)
+                    r.cycle.exec_ops(r._c_ops[st.a][1], 1, a, b)
+            self.comm.gather_planes(op.level - 1, ol.BUF_RHS if op.code == ol.OP_RESIDUAL_RESTRICT else op.dst, ranges)
             self.exchanges += 1
-            return
-        for r in self.ranks:
-            r.cycle.exec_ops(r._c_ops[idx][1], 1)
-        for (lvl, buf) in exchanges_after(op, lay):
-            self.comm.halo(lvl, buf)
-            self.exchanges += 1
+        else:
+            op = self.program.ops[st.a]
+            for r in self.ranks:
+                if st.b > 0:
+                    lo, hi = r.extended(op.level, st.b)
+                    r.cycle.exec_ops(r._c_ops[st.a][1], 1, lo, hi)
+                else:
+                    r.cycle.exec_ops(r._c_ops[st.a][1], 1)
 
     def cycle(self):
+        plan = self._plans.get(self._valid_key())
+        if plan is None:
+            key = self._valid_key()
+            valid = dict(self.valid)
+            plan = (schedule(self.program, self.layout, valid), valid)
+            self._plans[key] = plan
+        steps, after = plan
         with self._streams():
-            for idx in range(len(self.program.ops)):
-                self._run_op(idx)
+            for st in steps:
+                self._run(st)
+        self.valid = dict(after)
+
+    def _valid_key(self):
+        return tuple(sorted(self.valid.items()))
+
+    def _reset_validity(self):
+        top = self.problem.max_level
+        self.valid = {(top, ol.BUF_SOL): GHOST, (top, ol.BUF_RHS): GHOST}   # the upload filled every local plane
 
     def residual_norm(self) -> float:
         torch = self.torch
         with self._streams():
+            top_ = self.problem.max_level
+            if self.valid.get((top_, ol.BUF_SOL), 0) < 1:
+                self.comm.halo(top_, ol.BUF_SOL)
+                self.exchanges += 1
+                self.valid[(top_, ol.BUF_SOL)] = GHOST
+            self.valid[(top_, ol.BUF_RES)] = 0
             parts = []
             for r in self.ranks:
                 ptr, n = r.cycle.residual_plane_sums()
@@ -310,7 +412,7 @@ class DomainSolver:
         with self._streams():
             for r in self.ranks:
                 r.cycle.reset()
-            # initial ghost planes of SOL / RHS come from the upload (every local plane was copied)
+            self._reset_validity()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.exchanges = 0
             for dv in {r.device for r in self.ranks}:

@@ -199,8 +199,9 @@ int evo_cycle_residual_norm(evo_cycle *c, double *norm);
 /* -- host-orchestrated execution (domain decomposition: halo exchanges happen between statements) ----------- */
 /* use `cuda_stream` (a cudaStream_t, e.g. torch's current stream) for everything the cycle enqueues         */
 int evo_cycle_set_stream(evo_cycle *c, void *cuda_stream);
-/* enqueue statements (no synchronisation).  zc_lo/zc_hi >= 0 restrict a RESTRICT statement to the coarse
- * (local) planes [zc_lo, zc_hi]                                                                            */
+/* enqueue statements (no synchronisation).  zc_lo/zc_hi >= 0 override the (local) plane range the statement
+ * writes: coarse planes of RESTRICT, planes of RESIDUAL / PROLONG_ADD (to include ghost planes whose inputs
+ * are valid and save an exchange)                                                                          */
 int evo_cycle_exec_ops(evo_cycle *c, const evo_op *ops, int n_ops, int zc_lo, int zc_hi);
 /* current device address of a field (the two slots of SOL swap after out-of-place statements)               */
 int evo_cycle_buffer(evo_cycle *c, int level, int buf, int field, void **device_ptr);

@@ -53,6 +53,22 @@ def test_w_cycle_and_default_lc(cuda_backend):
         dd.close()
 
 
+@pytest.mark.parametrize("world,lc", [(2, 5), (3, 6), (2, 7)])
+def test_fused_residual_restrict_in_slabs(cuda_backend, world, lc):
+    from evostencils_b200 import lowering
+    prob = problems.Poisson3D(2, 7)
+    prog = lowering.optimise(cycles.default_solver_cycle(prob))
+    assert any(o.code == ol.OP_RESIDUAL_RESTRICT for o in prog.ops)
+    ref, ref_sol = _reference(cuda_backend, prob, prog)
+    dd = domain.DomainSolver.emulate(prob, prog, world, lc)
+    try:
+        out = dd.solve(prob.settings.tol, prob.settings.max_iters)
+        assert out.iterations == ref.iterations and np.array_equal(out.residuals, ref.residuals)
+        assert np.array_equal(dd.gather_solution(), ref_sol)
+    finally:
+        dd.close()
+
+
 def test_unsupported_statements_are_refused(cuda_backend):
     prob = problems.Poisson3D(2, 6)
     prog = cycles.v_cycle(prob, 1, 1, 1.0, True)

@@ -200,6 +200,37 @@ def test_fused_residual_restrict(cuda_backend, oracle_mod):
         _fields_equal(gc, oc, prob, [l - 1], bufs=(ol.BUF_RHS,))
 
 
+@pytest.mark.parametrize("max_level", [5, 6])
+def test_fused_residual_restrict_streaming_kernel(cuda_backend, oracle_mod, max_level):
+    """3-D 7-point fast path (n >= 33): fine residual planes staged in shared memory, never written."""
+    prob = problems.Poisson3D(2, max_level)
+    z = (0, 0, 0)
+    ops = []
+    for l in range(max_level, 4, -1):
+        ops += [ol.Op(ol.OP_SMOOTH, l, mode=ol.MODE_REDBLACK, omega=1.25, unknowns=((0, z),)),
+                ol.Op(ol.OP_RESIDUAL_RESTRICT, l, dst=ol.BUF_RHS, src=ol.BUF_RES)]
+    gc, oc, *_ = _pair(cuda_backend, oracle_mod, prob, cycles.build_program(prob, ops))
+    gc.apply(1)
+    oc.apply(1)
+    _fields_equal(gc, oc, prob, range(4, max_level), bufs=(ol.BUF_RHS,))
+    assert np.abs(gc.get_field(4, ol.BUF_RHS)).max() > 0
+
+
+def test_fused_cycle_gives_the_same_fitness(cuda_backend, oracle_mod):
+    from evostencils_b200 import lowering
+    prob = problems.Poisson3D(2, 6)
+    plain = cycles.default_solver_cycle(prob)
+    fused = lowering.optimise(plain)
+    assert any(o.code == ol.OP_RESIDUAL_RESTRICT for o in fused.ops)
+    dev = cuda_backend.DeviceProblem(prob)
+    s = prob.settings
+    a = dev.build(plain).solve(s.tol, s.max_iters, 1)
+    b = dev.build(fused).solve(s.tol, s.max_iters, 1)
+    assert a.iterations == b.iterations and np.array_equal(a.residuals, b.residuals)
+    ref = oracle_mod.OracleProblem(prob).build(fused).solve(s.tol, s.max_iters, 1)
+    assert np.array_equal(b.residuals, ref.residuals)
+
+
 def test_divergent_cycle_reports_like_reference(cuda_backend, oracle_mod):
     """Over-relaxed Jacobi diverges: same iteration count / status handling on both paths."""
     prob = problems.Poisson2D(3, 5)
