@@ -43,7 +43,9 @@ def measured_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(name: str):
+def make_workload(name: str, fuse: bool = True):
+    """The problem and its `generate solver` cycle, lowered the way the drop-in ProgramGenerator lowers it
+    (program_generator.py: fuse=True -> lowering.optimise merges residual + restriction where the residual is dead)."""
     if name == "poisson3d_513":
         prob = problems.Poisson3D(2, 9)
     elif name == "poisson3d_257":
@@ -56,7 +58,11 @@ def make_workload(name: str):
         prob = problems.Poisson2D(5, 12)
     else:
         raise SystemExit(f"unknown workload {name}")
-    return prob, cycles.default_solver_cycle(prob)
+    prog = cycles.default_solver_cycle(prob)
+    if fuse:
+        from evostencils_b200 import lowering
+        prog = lowering.optimise(prog)
+    return prob, prog
 
 
 class ClockSampler:

@@ -560,10 +560,6 @@ static bool try_smooth_point(int, const Geom &g, const OpSten &st, const SmoothP
         return false;
     }
 }
-#ifndef EVO_RR_CY
-#define EVO_RR_CY 4
-#define EVO_RR_CX 32
-#endif
 // ---------------------------------------------------------------------------------------------
 // Fused RHS@(l-1) = R (f - A u), 3-D 7-point operator, dense 27-point restriction: the fine residual never
 // reaches HBM (16 B/fine DOF read + 1 B written instead of 24 + 9 for the two separate statements).
@@ -580,7 +576,9 @@ struct RrCfg {
     static constexpr int RROWS = 2 * CY + 1;                       // fine residual rows of the tile
     static constexpr int NPAIR = CX + 1;                           // column pairs (fine x = 2X0-2+2j, +1), j = 0 .. CX
     static constexpr int ITEMS = RROWS * NPAIR;                    // one thread per (row, pair), fixed for the whole stream
-    static constexpr int NT = (ITEMS + 31) / 32 * 32;
+    static constexpr int RT = (ITEMS + 31) / 32 * 32;              // residual threads (producer warps)
+    static constexpr int CT = CY * CX;                             // restriction threads (consumer warps), one coarse node each
+    static constexpr int NT = RT + CT;
     static constexpr int LX = 2 * CX + 4;                          // box width: fine x = 2*X0-2 .. 2*X0+2*CX+1 (even start)
     static constexpr int ULY = 2 * CY + 3, FLY = RROWS;            // box rows of u (halo) and f
     static constexpr int NU = 6, NF = 4, NR = 5;                   // ring depths (planes)
@@ -589,8 +587,18 @@ struct RrCfg {
     static constexpr int RPITCH = RA + RB + 1;                     // doubles per residual row
     static constexpr int RSTRIDE = RROWS * RPITCH;
     static constexpr size_t SMEM = ((size_t)NU * USTRIDE + (size_t)NF * FSTRIDE + (size_t)NR * RSTRIDE) * 8;
+    static_assert(CT % 32 == 0, "whole consumer warps");
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Warp-specialised: RT producer threads compute residual planes (one (row, column pair) each, the centre values of
+// planes p-1, p, p+1 stay in registers while streaming), CT consumer threads form the coarse values.  The
+// 27-term dependent sum of a coarse node (~500 cycles of latency) then overlaps the producers' next step.
+// Named barriers: 1 = producers only (u/f ring slots dead -> next TMA), 2/3 = residual planes of step k ready
+// (producers arrive, consumers wait), 4/5 = consumers finished step k (producers wait before step k+2 reuses the
+// residual ring slots).
 template <int CY, int CX>
 __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(const __grid_constant__ CUtensorMap umap,
                                                                              const __grid_constant__ CUtensorMap fmap,
@@ -605,11 +613,9 @@ __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(co
     const int tid = threadIdx.x;
     const int X0 = 1 + blockIdx.x * CX, Y0 = 1 + blockIdx.y * CY;
     const int Za = gc.zlo + blockIdx.z * zchunk, Zb = min(Za + zchunk - 1, gc.zhi);
-    const int xb = 2 * X0 - 2, yub = 2 * Y0 - 2, yfb = 2 * Y0 - 1;   // box origins (fine coordinates)
+    const int nsteps = Zb - Za + 1;
     const int nfi = gf.n - 2, nci = gc.n - 2;
-    const int zr0 = 2 * (Za + gc.zoff) - gf.zoff - 1;                // first / last fine residual plane (local)
-    const int zr1 = 2 * (Zb + gc.zoff) - gf.zoff + 1;
-    const int q0 = zr0 - 1, qmax = zr1 + 1;                           // u planes q0 .. qmax, f planes zr0 .. zr1
+    const int zr0 = 2 * (Za + gc.zoff) - gf.zoff - 1;                // first fine residual plane (local index)
 
     if (tid == 0) {
         for (int i = 0; i < C::NU; ++i) mbar_init(&ubar[i], 1);
@@ -617,7 +623,46 @@ __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(co
         fence_mbar_init();
     }
     __syncthreads();
-    int u_issued = q0 - 1, f_issued = zr0 - 1;   // only thread 0 uses these
+
+    if (tid >= C::RT) {
+        // ---------------- consumers: coarse node (X, Y) of every coarse plane of the chunk ----------------
+        const int t = tid - C::RT;
+        const int ry = t / CX, rx = t - ry * CX;
+        const int X = X0 + rx, Y = Y0 + ry;
+        const bool ok = X <= nci && Y <= nci;
+        const int o = (2 * ry) * C::RPITCH + rx;
+        int sm = zr0 % C::NR;                                         // ring slot of fine plane 2Z-1
+        double *out = dst + (long long)Za * gc.plane + (long long)Y * gc.pitch + X;
+        for (int k = 0; k < nsteps; ++k) {
+            const int s0 = sm + 1 >= C::NR ? sm + 1 - C::NR : sm + 1, sp = sm + 2 >= C::NR ? sm + 2 - C::NR : sm + 2;
+            named_bar_sync(2 + (k & 1), C::NT);
+            if (ok) {
+                double acc = 0.0;
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const double *pl = rring + (dz == 0 ? sm : (dz == 1 ? s0 : sp)) * C::RSTRIDE + o;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const double *row = pl + dy * C::RPITCH;
+                        acc = acc + R.w[dz * 9 + dy * 3 + 0] * row[0];           // fine x = 2X - 1
+                        acc = acc + R.w[dz * 9 + dy * 3 + 1] * row[C::RA];       // fine x = 2X
+                        acc = acc + R.w[dz * 9 + dy * 3 + 2] * row[1];           // fine x = 2X + 1
+                    }
+                }
+                *out = acc;
+            }
+            out += gc.plane;
+            sm = sp;                                                  // plane 2Z+1 is plane 2(Z+1)-1
+            if (k + 2 < nsteps) named_bar_arrive(4 + (k & 1), C::NT);
+        }
+        return;
+    }
+
+    // ---------------- producers ----------------
+    const int xb = 2 * X0 - 2, yub = 2 * Y0 - 2, yfb = 2 * Y0 - 1;   // box origins (fine coordinates)
+    const int zr1 = zr0 + 2 * nsteps;                                 // last fine residual plane
+    const int q0 = zr0 - 1, qmax = zr1 + 1;                           // u planes q0 .. qmax, f planes zr0 .. zr1
+    int u_issued = q0 - 1, f_issued = zr0 - 1;                        // only thread 0 uses these
     auto issue_u = [&](int upto) {
         for (upto = min(upto, qmax); u_issued < upto;) {
             const int q = ++u_issued, sl = (q - q0) % C::NU;
@@ -632,8 +677,6 @@ __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(co
             tma_load_plane(fring + (size_t)sl * C::FSTRIDE, &fmap, xb, yfb, q, &fbar[sl]);
         }
     };
-    auto wait_u = [&](int q) { mbar_wait(&ubar[(q - q0) % C::NU], (uint32_t)(((q - q0) / C::NU) & 1)); };
-    auto wait_f = [&](int q) { mbar_wait(&fbar[(q - zr0) % C::NF], (uint32_t)(((q - zr0) / C::NF) & 1)); };
     if (tid == 0) {
         issue_u(q0 + C::NU - 1);
         issue_f(zr0 + C::NF - 1);
@@ -648,21 +691,22 @@ __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(co
     const bool ok_b = active && xa + 1 <= nfi && yy <= nfi;
     const int ou = (r + 1) * C::LX + 2 * j, of = r * C::LX + 2 * j;
     const int oxm = ou - (j >= 1 ? 1 : 0);                               // left neighbour of the pair (unused for j = 0)
-    const int res_a = r * C::RPITCH + C::RA + j - 1, res_b = r * C::RPITCH + j;
+    const int res_a = r * C::RPITCH + C::RA + (j >= 1 ? j - 1 : 0), res_b = r * C::RPITCH + j;
     double2 um = make_double2(0.0, 0.0), u0 = um;
 
-    // residual of fine plane p for this thread's pair; um / u0 hold the centre pairs of planes p-1 / p
-    auto residual_plane = [&](int p) {
-        const double *s0 = uring + (size_t)((p - q0) % C::NU) * C::USTRIDE;
-        const double *sp = uring + (size_t)((p + 1 - q0) % C::NU) * C::USTRIDE;
-        const double *fp = fring + (size_t)((p - zr0) % C::NF) * C::FSTRIDE;
-        double *rs = rring + (size_t)(p % C::NR) * C::RSTRIDE;
+    // ring cursors: slot / phase of the next u plane (p+1) and f plane (p) to wait for, slots of planes p and residual p
+    int su = 1, sun = 2, sun_ph = 0, sf = 0, sf_ph = 0, sr = zr0 % C::NR;
+    // residual of the next fine plane p for this thread's pair; um / u0 hold the centre pairs of planes p-1 / p
+    auto residual_plane = [&]() {
+        mbar_wait(&ubar[sun], (uint32_t)sun_ph);
+        mbar_wait(&fbar[sf], (uint32_t)sf_ph);
         if (active) {
-            const double2 up = *reinterpret_cast<const double2 *>(sp + ou);
-            const double2 ym = *reinterpret_cast<const double2 *>(s0 + ou - C::LX);
-            const double2 yp = *reinterpret_cast<const double2 *>(s0 + ou + C::LX);
-            const double2 fv = *reinterpret_cast<const double2 *>(fp + of);
-            const double xm = s0[oxm], xp = s0[ou + 2];
+            const double *s0 = uring + su * C::USTRIDE + ou;
+            const double2 up = *reinterpret_cast<const double2 *>(uring + sun * C::USTRIDE + ou);
+            const double2 ym = *reinterpret_cast<const double2 *>(s0 - C::LX);
+            const double2 yp = *reinterpret_cast<const double2 *>(s0 + C::LX);
+            const double2 fv = *reinterpret_cast<const double2 *>(fring + sf * C::FSTRIDE + of);
+            const double xm = s0[oxm - ou], xp = s0[2];
             double sa = 0.0, sb = 0.0;
             sa = sa + c.zm * um.x;  sb = sb + c.zm * um.y;
             sa = sa + c.ym * ym.x;  sb = sb + c.ym * ym.y;
@@ -671,56 +715,70 @@ __global__ void __launch_bounds__(RrCfg<CY, CX>::NT) k3_residual_restrict_tma(co
             sa = sa + c.xp * u0.y;  sb = sb + c.xp * xp;
             sa = sa + c.yp * yp.x;  sb = sb + c.yp * yp.y;
             sa = sa + c.zp * up.x;  sb = sb + c.zp * up.y;
+            double *rs = rring + sr * C::RSTRIDE;
             if (j >= 1) rs[res_a] = ok_a ? fv.x - sa : 0.0;
             rs[res_b] = ok_b ? fv.y - sb : 0.0;
             um = u0;
             u0 = up;
         }
+        su = sun;
+        if (++sun == C::NU) { sun = 0; sun_ph ^= 1; }
+        if (++sf == C::NF) { sf = 0; sf_ph ^= 1; }
+        if (++sr == C::NR) sr = 0;
     };
 
-    // prologue: fine residual plane zr0 (= 2 Za - 1)
-    wait_u(q0); wait_u(q0 + 1); wait_u(q0 + 2); wait_f(zr0);
+    // prologue: fine residual plane zr0 (= 2 Za - 1); planes q0, q0+1 feed the register window
+    mbar_wait(&ubar[0], 0u);
+    mbar_wait(&ubar[1], 0u);
     if (active) {
         um = *reinterpret_cast<const double2 *>(uring + ou);
         u0 = *reinterpret_cast<const double2 *>(uring + (size_t)C::USTRIDE + ou);
     }
-    residual_plane(zr0);
-    __syncthreads();
+    residual_plane();
+    named_bar_sync(1, C::RT);
     if (tid == 0) { fence_proxy_async(); issue_u(zr0 + C::NU - 1); issue_f(zr0 + C::NF); }
 
-    for (int Z = Za; Z <= Zb; ++Z) {
-        const int zf = zr0 + 1 + 2 * (Z - Za);
-        wait_u(zf + 1); wait_f(zf);
-        residual_plane(zf);
-        wait_u(zf + 2); wait_f(zf + 1);
-        residual_plane(zf + 1);
-        __syncthreads();   // residual planes complete; u planes <= zf and f planes <= zf+1 are dead
+    for (int k = 0; k < nsteps; ++k) {
+        const int zf = zr0 + 1 + 2 * k;
+        if (k >= 2) named_bar_sync(4 + (k & 1), C::NT);   // consumers are done with the residual ring slots of step k-2
+        residual_plane();
+        residual_plane();
+        named_bar_arrive(2 + (k & 1), C::NT);             // residual planes zf, zf+1 are in the ring
+        named_bar_sync(1, C::RT);                         // u planes <= zf and f planes <= zf+1 are dead
         if (tid == 0) { fence_proxy_async(); issue_u(zf + C::NU); issue_f(zf + 1 + C::NF); }
-        if (tid < CY * CX) {
-            const double *pm = rring + (size_t)((zf - 1) % C::NR) * C::RSTRIDE;
-            const double *p0 = rring + (size_t)(zf % C::NR) * C::RSTRIDE;
-            const double *pp = rring + (size_t)((zf + 1) % C::NR) * C::RSTRIDE;
-            const int ry = tid / CX, rx = tid - ry * CX;
-            const int X = X0 + rx, Y = Y0 + ry;
-            if (X <= nci && Y <= nci) {
-                double acc = 0.0;
-#pragma unroll
-                for (int dz = 0; dz < 3; ++dz) {
-                    const double *pl = dz == 0 ? pm : (dz == 1 ? p0 : pp);
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const double *row = pl + (2 * ry + dy) * C::RPITCH;
-                        acc = acc + R.w[dz * 9 + dy * 3 + 0] * row[rx];             // fine x = 2X - 1
-                        acc = acc + R.w[dz * 9 + dy * 3 + 1] * row[C::RA + rx];     // fine x = 2X
-                        acc = acc + R.w[dz * 9 + dy * 3 + 2] * row[rx + 1];         // fine x = 2X + 1
-                    }
-                }
-                dst[(long long)Z * gc.plane + (long long)Y * gc.pitch + X] = acc;
-            }
-        }
-        // no second barrier: the next step writes residual planes zf+2, zf+3 into ring slots distinct from
-        // zf-1 .. zf+1 (5 slots); slot (zf-1) % 5 is only rewritten after the next step's barrier
     }
+}
+
+template <int CY, int CX>
+static bool launch_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, const Star7 &c, const DenseW &W, const double *u,
+                                     const double *f, double *dst, cudaStream_t s)
+{
+    using C = RrCfg<CY, CX>;
+    CUtensorMap um, fm;
+    if (!make_plane_map(&um, gf, u, C::LX, C::ULY) || !make_plane_map(&fm, gf, f, C::LX, C::FLY)) return false;
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaFuncSetAttribute(k3_residual_restrict_tma<CY, CX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+            return false;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_residual_restrict_tma<CY, CX>, C::NT, C::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    }
+    const int nci = gc.n - 2, planes = gc.zhi - gc.zlo + 1;
+    if (planes <= 0) return true;
+    const int tx = (nci + CX - 1) / CX, ty = (nci + CY - 1) / CY;
+    // z chunks: minimise (waves) x (coarse planes per chunk + pipeline fill); a chunk recomputes one fine plane
+    const long long slots = (long long)occ * sm_count;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int ch = 1; ch <= 32 && (ch == 1 || ch * 8 <= planes); ++ch) {
+        const int zc = (planes + ch - 1) / ch;
+        const long long ctas = (long long)tx * ty * ((planes + zc - 1) / zc);
+        const double cost = (double)((ctas + slots - 1) / slots) * (zc + 3);
+        if (cost < best_cost) { best_cost = cost; best = ch; }
+    }
+    const int zchunk = (planes + best - 1) / best;
+    const int chunks = (planes + zchunk - 1) / zchunk;
+    k3_residual_restrict_tma<CY, CX><<<dim3(tx, ty, chunks), C::NT, C::SMEM, s>>>(um, fm, gf, gc, c, W, dst, zchunk);
+    return cudaGetLastError() == cudaSuccess;
 }
 
 template <typename T, int DIM, int NF>
@@ -732,34 +790,18 @@ static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, 
         if (gf.n < 33 || R.nnz != 27 || !match_star7(st.s[0][0], &c) || get_encode_tiled() == nullptr) return false;
         DenseW W;
         for (int q = 0; q < 27; ++q) W.w[(R.oz[q] + 1) * 9 + (R.oy[q] + 1) * 3 + (R.ox[q] + 1)] = R.w[q];
-        constexpr int CY = EVO_RR_CY, CX = EVO_RR_CX;
-        using C = RrCfg<CY, CX>;
-        constexpr int NT = C::NT;
-        CUtensorMap um, fm;
-        if (!make_plane_map(&um, gf, u.p[0], C::LX, C::ULY) || !make_plane_map(&fm, gf, f.p[0], C::LX, C::FLY)) return false;
-        static int occ = 0;
-        if (occ == 0) {
-            if (cudaFuncSetAttribute(k3_residual_restrict_tma<CY, CX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
-                return false;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_residual_restrict_tma<CY, CX>, NT, C::SMEM) != cudaSuccess || occ < 1) occ = 1;
+        static int variant = -1;
+        if (variant < 0) {
+            const char *e = getenv("EVO_RR_VARIANT");
+            variant = e ? atoi(e) : 0;
         }
-        const int nci = gc.n - 2, planes = gc.zhi - gc.zlo + 1;
-        if (planes <= 0) return true;
-        const int tx = (nci + CX - 1) / CX, ty = (nci + CY - 1) / CY;
-        // z chunks: minimise (waves) x (coarse planes per chunk + pipeline fill); a chunk recomputes one fine plane
-        const long long slots = (long long)occ * sm_count;
-        int best = 1;
-        double best_cost = 1e300;
-        for (int ch = 1; ch <= 32 && (ch == 1 || ch * 8 <= planes); ++ch) {
-            const int zc = (planes + ch - 1) / ch;
-            const long long ctas = (long long)tx * ty * ((planes + zc - 1) / zc);
-            const double cost = (double)((ctas + slots - 1) / slots) * (zc + 3);
-            if (cost < best_cost) { best_cost = cost; best = ch; }
+        switch (variant) {
+        case 1: return launch_residual_restrict<2, 64>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
+        case 2: return launch_residual_restrict<4, 64>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
+        case 3: return launch_residual_restrict<8, 32>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
+        case 4: return launch_residual_restrict<2, 32>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
+        default: return launch_residual_restrict<4, 32>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
         }
-        const int zchunk = (planes + best - 1) / best;
-        const int chunks = (planes + zchunk - 1) / zchunk;
-        k3_residual_restrict_tma<CY, CX><<<dim3(tx, ty, chunks), NT, C::SMEM, s>>>(um, fm, gf, gc, c, W, dst.p[0], zchunk);
-        return cudaGetLastError() == cudaSuccess;
     } else {
         return false;
     }

@@ -143,6 +143,8 @@ struct evo_cycle {
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
     bool use_while_graph;
+    bool pingpong = false;                               // the WHILE body holds two cycles (see build_solver_graph)
+    bool odd_swap[EVO_MAX_LEVELS][EVO_MAX_FIELDS] = {};  // levels whose SOL ends in the [next] slot after one cycle
     int zc_lo = -1, zc_hi = -1;  // plane range override of the statement's destination level (domain decomposition)
     bool own_stream = true;
     bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
@@ -946,10 +948,16 @@ static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store
 
 // all statements of the cycle function, then restore the canonical jacobi-slot assignment so that a
 // replay (next outer iteration) starts from the same pointers
+static int enqueue_cycle_ops(evo_cycle *c, cudaStream_t s)
+{
+    for (const evo_op &op : c->ops) EV(dispatch_op(c, op, s));
+    return EVO_OK;
+}
+
 static int enqueue_cycle(evo_cycle *c, cudaStream_t s)
 {
     evo_problem *p = c->p;
-    for (const evo_op &op : c->ops) EV(dispatch_op(c, op, s));
+    EV(enqueue_cycle_ops(c, s));
     const size_t esz = sizeof(double) * p->words;
     for (int l = p->desc.min_level; l <= p->desc.max_level; ++l)
         for (int i = 0; i < p->desc.n_fields; ++i)
@@ -1286,6 +1294,36 @@ __global__ void k_set_while_condition(cudaGraphConditionalHandle handle, const S
     if (threadIdx.x == 0 && blockIdx.x == 0) cudaGraphSetConditional(handle, st->done ? 0u : 1u);
 }
 
+// after an odd cycle of a ping-pong body: continue with the second half (IF node) and the loop only if not done
+__global__ void k_set_two_conditions(cudaGraphConditionalHandle a, cudaGraphConditionalHandle b, const SolveState *st)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned v = st->done ? 0u : 1u;
+        cudaGraphSetConditional(a, v);
+        cudaGraphSetConditional(b, v);
+    }
+}
+// after the loop: an odd number of cycles leaves the solution in the [next] slots
+__global__ void k_set_odd_condition(cudaGraphConditionalHandle h, const SolveState *st)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) cudaGraphSetConditional(h, (unsigned)(st->it & 1));
+}
+
+static int graph_leaves(cudaGraph_t g, std::vector<cudaGraphNode_t> &leaves)
+{
+    size_t n_nodes = 0;
+    CU(cudaGraphGetNodes(g, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    CU(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+    leaves.clear();
+    for (cudaGraphNode_t nd : nodes) {
+        size_t nd_dep = 0;
+        CU(cudaGraphNodeGetDependentNodes(nd, nullptr, &nd_dep));
+        if (nd_dep == 0) leaves.push_back(nd);
+    }
+    return EVO_OK;
+}
+
 static int ensure_hist(evo_cycle *c, int max_iters)
 {
     if (c->hist_cap >= max_iters + 1) return EVO_OK;
@@ -1354,16 +1392,110 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     cudaGraph_t body = cp.conditional.phGraph_out[0];
     c->launch_counter = 0;
     CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_cycle(c, s);
+    // Out-of-place statements (jacobi slots, the streaming RB-GS kernel) swap SOL and its [next] slot.  A cycle
+    // with an odd number of swaps on a level ends in the other buffer: instead of copying it back every cycle
+    // (2 x 8 B/DOF of pure overhead) the loop body holds TWO cycles -- the second one, inside an IF node, runs
+    // with the roles of the buffers exchanged and ends in the canonical assignment again.
+    rc = enqueue_cycle_ops(c, s);
+    bool odd = false;
+    for (int l = c->p->desc.min_level; l <= c->p->desc.max_level; ++l)
+        for (int i = 0; i < c->p->desc.n_fields; ++i) {
+            c->odd_swap[l][i] = c->lv[l].swapped[i];
+            odd = odd || c->lv[l].swapped[i];
+        }
+    static const bool no_pingpong = getenv("EVO_NO_PINGPONG") != nullptr;
+    c->pingpong = odd && !no_pingpong && rc == EVO_OK;
+    if (rc == EVO_OK && !c->pingpong) {
+        // restore the canonical assignment by copying (no-op when nothing is swapped)
+        std::vector<evo_op> none;
+        std::swap(none, c->ops);
+        rc = enqueue_cycle(c, s);
+        std::swap(none, c->ops);
+    }
     if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
+    cudaGraphConditionalHandle h_if = 0;
     if (rc == EVO_OK) {
         k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 1);
-        k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
         c->launch_counter += 2;
+        if (!c->pingpong) k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
     }
+    c->kernels_per_cycle = c->launch_counter;
     e = cudaStreamEndCapture(s, nullptr);
     if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "body capture: %s", cudaGetErrorString(e)); }
+    if (c->pingpong) {
+        std::vector<cudaGraphNode_t> bl;
+        EV(graph_leaves(body, bl));
+        CU(cudaGraphConditionalHandleCreate(&h_if, g, 0, cudaGraphCondAssignDefault));
+        cudaGraphNode_t setc;
+        {
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            void *args[3] = {(void *)&handle, (void *)&h_if, (void *)&c->d_state};
+            kp.func = (void *)k_set_two_conditions;
+            kp.gridDim = dim3(1);
+            kp.blockDim = dim3(32);
+            kp.kernelParams = args;
+            CU(cudaGraphAddKernelNode(&setc, body, bl.data(), bl.size(), &kp));
+        }
+        cudaGraphNodeParams ip = {cudaGraphNodeTypeConditional};
+        ip.type = cudaGraphNodeTypeConditional;
+        ip.conditional.handle = h_if;
+        ip.conditional.type = cudaGraphCondTypeIf;
+        ip.conditional.size = 1;
+        cudaGraphNode_t inode;
+        CU(cudaGraphAddNode(&inode, body, &setc, 1, &ip));
+        cudaGraph_t second = ip.conditional.phGraph_out[0];
+        CU(cudaStreamBeginCaptureToGraph(s, second, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_cycle_ops(c, s);
+        bool still = false;
+        for (int l = c->p->desc.min_level; l <= c->p->desc.max_level; ++l)
+            for (int i = 0; i < c->p->desc.n_fields; ++i) still = still || c->lv[l].swapped[i];
+        if (rc == EVO_OK && still) rc = fail(EVO_ERR_INVALID, "ping-pong body did not return to the canonical slots");
+        if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
+        if (rc == EVO_OK) {
+            k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 1);
+            k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
+        }
+        e = cudaStreamEndCapture(s, nullptr);
+        if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "second body capture: %s", cudaGetErrorString(e)); }
+        // epilogue: after an odd number of cycles copy the solution back into the canonical buffers (once per solve)
+        cudaGraphConditionalHandle h_odd;
+        CU(cudaGraphConditionalHandleCreate(&h_odd, g, 0, cudaGraphCondAssignDefault));
+        cudaGraphNode_t seto;
+        {
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            void *args[2] = {(void *)&h_odd, (void *)&c->d_state};
+            kp.func = (void *)k_set_odd_condition;
+            kp.gridDim = dim3(1);
+            kp.blockDim = dim3(32);
+            kp.kernelParams = args;
+            CU(cudaGraphAddKernelNode(&seto, g, &wnode, 1, &kp));
+        }
+        cudaGraphNodeParams op = {cudaGraphNodeTypeConditional};
+        op.type = cudaGraphNodeTypeConditional;
+        op.conditional.handle = h_odd;
+        op.conditional.type = cudaGraphCondTypeIf;
+        op.conditional.size = 1;
+        cudaGraphNode_t onode;
+        CU(cudaGraphAddNode(&onode, g, &seto, 1, &op));
+        cudaGraph_t fix = op.conditional.phGraph_out[0];
+        CU(cudaStreamBeginCaptureToGraph(s, fix, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        const size_t esz = sizeof(double) * c->p->words;
+        cudaError_t ce = cudaSuccess;
+        {
+            // the data of an odd solve lives where the pointers were after the FIRST cycle: slot <-> SOL exchanged
+            for (int l = c->p->desc.min_level; l <= c->p->desc.max_level && ce == cudaSuccess; ++l)
+                for (int i = 0; i < c->p->desc.n_fields && ce == cudaSuccess; ++i)
+                    if (c->odd_swap[l][i])
+                        ce = cudaMemcpyAsync(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i], (size_t)c->p->geom[l].total * esz,
+                                             cudaMemcpyDeviceToDevice, s);
+        }
+        e = cudaStreamEndCapture(s, nullptr);
+        if (ce != cudaSuccess || e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "epilogue capture failed"); }
+    }
     c->kernels_per_cycle = c->launch_counter;
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, g, 0);
