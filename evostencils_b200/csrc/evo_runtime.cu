@@ -860,7 +860,21 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
         fas::Lin2 L;
         if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
         if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing slot for the FAS coarse solver");
-        fas::k2_fas_coarse<<<1, 1024, 0, s>>>(c->p->geom[l], L, gamma, (double *)c->lv[l].buf[EVO_BUF_SOL][0],
+        const Geom &g = c->p->geom[l];
+        if ((long long)(g.n - 2) * (g.n - 2) > 4096) {
+            // a "coarsest" grid too large for one CTA (BASELINE config 4097^2 has 257^2 there): one launch per sweep
+            // over all SMs, ping-pong between the two SOL slots; the per-node arithmetic is that of k2_fas_coarse
+            const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
+            for (int t = 0; t < op.count; ++t) {
+                fas::k2_fas_smooth<<<row_grid(g), BX, 0, s>>>(g, L, gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                                             (double *)c->lv[l].slot[0], f, 1, 1, op.omega, -1);
+                c->launch_counter++;
+                swap_slot(l);
+            }
+            CU(cudaGetLastError());
+            return EVO_OK;
+        }
+        fas::k2_fas_coarse<<<1, 1024, 0, s>>>(g, L, gamma, (double *)c->lv[l].buf[EVO_BUF_SOL][0],
                                               (double *)c->lv[l].slot[0], (const double *)c->lv[l].buf[EVO_BUF_RHS][0], op.count, op.omega);
         c->launch_counter++;
         CU(cudaGetLastError());
