@@ -758,4 +758,105 @@ __global__ void __launch_bounds__(1024) k2_smooth_rowseq_win(const Geom g, const
     }
 }
 
+// Pipelined version: the 2k colour passes of k consecutive sweeps run concurrently, pass p two rows behind pass
+// p-1 (row y of a pass reads rows y-1 (already updated by this pass), y, y+1 (updated by the previous pass one
+// step earlier): exactly the values the sequential sweeps would see).  Each pass is a group of warps of the one
+// CTA; a step is one __syncthreads.  Rows stream through a shared-memory window once (cp.async in, 16-byte stores
+// out when a row has left the last pass), so k sweeps cost (n + 4k) row steps instead of 2k n.
+template <int NF>
+__global__ void __launch_bounds__(1024) k2_smooth_rowseq_pipe(const Geom g, const __grid_constant__ OpSten st, const double omega,
+                                                              Fields<double> u, Fields<double> rhs, const int sweeps)
+{
+    extern __shared__ __align__(16) double win[];   // [W slots][2*NF arrays][pitch]
+    const int n = g.n, pitch = g.pitch;
+    const int chunks = pitch / 2;                    // 16-byte chunks per row
+    const int P = 2 * sweeps, W = 2 * P + 3;
+    const int G = ((1024 / P) / 32) * 32;            // threads per pass (whole warps); the rest only moves data
+    const int grp = threadIdx.x / G, lt = threadIdx.x - grp * G;
+    auto arr = [&](int row, int a) { return win + ((size_t)(row % W) * 2 * NF + a) * pitch; };
+    auto fetch = [&](int row) {
+        if (row >= 0 && row <= n - 1)
+            for (int t = threadIdx.x; t < 2 * NF * chunks; t += 1024) {
+                const int a = t / chunks, c = t - a * chunks;
+                const double *src = (a < NF ? u.p[a] : rhs.p[a - NF]) + (long long)row * pitch + 2 * c;
+                cp_async16(arr(row, a) + 2 * c, src);
+            }
+        cp_async_commit();
+    };
+    auto store_row = [&](int row) {
+        for (int t = threadIdx.x; t < NF * chunks; t += 1024) {
+            const int a = t / chunks, c = t - a * chunks;
+            *reinterpret_cast<double2 *>(u.p[a] + (long long)row * pitch + 2 * c) = *reinterpret_cast<const double2 *>(arr(row, a) + 2 * c);
+        }
+    };
+    // the local matrix (diagonal entries of the blocks) is the same at every anchor: factor it once
+    double M0[NF][NF];
+#pragma unroll
+    for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int m = 0; m < NF; ++m) M0[a][m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const Sten &sj = st.s[a][j];
+            for (int q = 0; q < sj.nnz; ++q)
+                if (sj.ox[q] == 0 && sj.oy[q] == 0) {
+#pragma unroll
+                    for (int m = 0; m < NF; ++m)
+                        if (m == j) M0[a][m] = M0[a][m] + sj.re[q];
+                }
+        }
+    DenseLU<double, NF> lu;
+    dense_factor<double, NF>(M0, lu);
+    fetch(0); fetch(1); fetch(2);
+    const int last = (n - 2) + 2 * (P - 1);
+    for (int y = 1; y <= last; ++y) {
+        fetch(y + 2);
+        cp_async_wait<1>();      // everything but the newest group (row y+2) has landed
+        __syncthreads();         // ... for all threads; the previous step's updates are visible
+        const int yb = y - 2 * (P - 1) - 1;   // left the last pass in the previous step
+        if (yb >= 1) store_row(yb);
+        const int yr = y - 2 * grp;
+        if (grp < P && yr >= 1 && yr <= n - 2) {
+            const int color = grp & 1;
+            const double *up[3][NF];
+            double *uc[NF];
+            const double *fr[NF];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+                up[0][j] = arr(yr - 1, j); up[1][j] = arr(yr, j); up[2][j] = arr(yr + 1, j);
+                uc[j] = arr(yr, j);
+                fr[j] = arr(yr, NF + j);
+            }
+            for (int t = lt;; t += G) {
+                const int x = 1 + 2 * t + ((1 + yr + color) & 1);
+                if (x > n - 2) break;
+                double b[NF];
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        const Sten &sj = st.s[a][j];
+                        for (int q = 0; q < sj.nnz; ++q)
+                            if (!(sj.ox[q] == 0 && sj.oy[q] == 0)) sacc = sacc + sj.re[q] * up[sj.oy[q] + 1][j][x + sj.ox[q]];
+                    }
+                    b[a] = fr[a][x] - sacc;
+                }
+                if (NF == 1) b[0] = b[0] * lu.inv[0];
+                else dense_solve<double, NF>(lu, b);
+#pragma unroll
+                for (int a = 0; a < NF; ++a) {
+                    const double old = uc[a][x];
+                    uc[a][x] = old + omega * (b[a] - old);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    store_row(n - 2);
+}
+
 }  // namespace evo

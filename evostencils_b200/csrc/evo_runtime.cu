@@ -556,7 +556,21 @@ template <typename T, int DIM, int NF> struct Launch {
                                 if (sp.field[a] != a || sp.off[a][0] || sp.off[a][1] || sp.off[a][2]) canonical = false;
                             const size_t smem = (size_t)5 * 2 * NF * g.pitch * sizeof(double);
                             static const bool disabled = getenv("EVO_ROWSEQ_GLOBAL") != nullptr;
-                            if (canonical && !disabled && smem <= 200 * 1024) {
+                            static const bool no_pipe = getenv("EVO_ROWSEQ_NOPIPE") != nullptr;
+                            // pipelined passes: as many of the remaining sweeps as the window fits (<= 4)
+                            int k = std::min(reps - rep, 4);
+                            while (k > 0 && (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double) > 200 * 1024) --k;
+                            if (canonical && !disabled && !no_pipe && k > 0) {
+                                static bool attr_p = false;
+                                if (!attr_p) {
+                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                    attr_p = true;
+                                }
+                                const size_t sm2 = (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double);
+                                k2_smooth_rowseq_pipe<NF><<<1, 1024, sm2, s>>>(g, c->sten[l], sp.omega, u, rhs, k);
+                                done = true;
+                                rep += k - 1;
+                            } else if (canonical && !disabled && smem <= 200 * 1024) {
                                 static bool attr = false;
                                 if (!attr) {
                                     CU(cudaFuncSetAttribute(k2_smooth_rowseq_win<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -861,7 +875,41 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
         if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
         if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing slot for the FAS coarse solver");
         const Geom &g = c->p->geom[l];
-        if ((long long)(g.n - 2) * (g.n - 2) > 4096) {
+        static const int cgs_mode = getenv("EVO_FAS_CGS") ? atoi(getenv("EVO_FAS_CGS")) : 0;   // 0 auto, 1 one CTA (smem), 2 launches
+        if (cgs_mode == 0 && g.n <= 65) {   // 129^2: 200 graph-launched sweeps over all SMs are faster (measured)
+            // rows split over a cluster of 8 CTAs (distributed shared memory halos, one cluster barrier per sweep)
+            const int cs = 8, ni = g.n - 2, rp = (ni + cs - 1) / cs;
+            const int npt = (rp * ni + 511) / 512;
+            const size_t smem = (size_t)2 * (rp + 2) * (g.n + 1) * sizeof(double);
+            auto kern = npt <= 1 ? fas::k2_fas_coarse_cluster<1> : fas::k2_fas_coarse_cluster<4>;
+            if (npt <= 4) {
+                static bool attr1 = false, attr4 = false;
+                bool &attr = npt <= 1 ? attr1 : attr4;
+                if (!attr) {
+                    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    attr = true;
+                }
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(cs);
+                cfg.blockDim = dim3(512);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                double *ua = (double *)c->lv[l].buf[EVO_BUF_SOL][0];
+                const double *fa = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
+                int cnt = op.count;
+                double om = op.omega, gm = gamma;
+                CU(cudaLaunchKernelEx(&cfg, kern, g, L, gm, ua, fa, cnt, om));
+                c->launch_counter++;
+                return EVO_OK;
+            }
+        }
+        if ((long long)(g.n - 2) * (g.n - 2) > 4096 || cgs_mode == 2) {
             // a "coarsest" grid too large for one CTA (BASELINE config 4097^2 has 257^2 there): one launch per sweep
             // over all SMs, ping-pong between the two SOL slots; the per-node arithmetic is that of k2_fas_coarse
             const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
@@ -871,6 +919,21 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
                 c->launch_counter++;
                 swap_slot(l);
             }
+            CU(cudaGetLastError());
+            return EVO_OK;
+        }
+        static const bool global_cgs = getenv("EVO_FAS_CGS_GLOBAL") != nullptr;
+        if (!global_cgs && g.n <= 65) {
+            // both slots in shared memory, up to 4 nodes per thread in flight
+            const size_t smem = (size_t)2 * (g.n + 1) * g.n * sizeof(double);
+            static bool attr = false;
+            if (!attr) {
+                CU(cudaFuncSetAttribute(fas::k2_fas_coarse_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 66 * 65 * 8));
+                attr = true;
+            }
+            fas::k2_fas_coarse_smem<4><<<1, 1024, smem, s>>>(g, L, gamma, (double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                                             (const double *)c->lv[l].buf[EVO_BUF_RHS][0], op.count, op.omega);
+            c->launch_counter++;
             CU(cudaGetLastError());
             return EVO_OK;
         }

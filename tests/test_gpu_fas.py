@@ -26,10 +26,12 @@ def test_fas_cycle_parity(cuda_backend, oracle_mod, newton_steps, red_black):
     assert fitness.fas_fitness(a.residuals, a.time_ms)[1:] == fitness.fas_fitness(b.residuals, b.time_ms)[1:]
 
 
-def test_fas_large_coarsest_grid_uses_multi_cta_sweeps(cuda_backend, oracle_mod):
-    """BASELINE config shape (5 levels, coarsest grid far too large for one CTA): the coarse solver runs one
-    launch per Newton-Jacobi sweep instead of the single-CTA kernel -- same arithmetic, same bits."""
-    prob = problems.FAS2D(7, 9)
+@pytest.mark.parametrize("lo,hi", [(7, 9), (8, 10), (5, 7)])
+def test_fas_large_coarsest_grid_uses_multi_cta_sweeps(cuda_backend, oracle_mod, lo, hi):
+    """Coarsest grids beyond one SM: rows split over a thread-block cluster with distributed-shared-memory halos
+    (<= 129^2), or one launch per Newton-Jacobi sweep (BASELINE config shape: 257^2 below 4097^2) -- same
+    arithmetic, same bits."""
+    prob = problems.FAS2D(lo, hi)
     prog = cycles.fas_v_cycle(prob)
     gc = cuda_backend.DeviceProblem(prob).build(prog)
     oc = oracle_mod.OracleProblem(prob).build(prog)
@@ -37,7 +39,7 @@ def test_fas_large_coarsest_grid_uses_multi_cta_sweeps(cuda_backend, oracle_mod)
     b = oc.solve(prob.settings.tol, 6, 1)
     assert a.iterations == b.iterations == 6
     assert np.array_equal(a.residuals, b.residuals)
-    for l in (7, 8, 9):
+    for l in range(lo, hi + 1):
         assert np.array_equal(gc.get_field(l, ol.BUF_SOL), oc.get_field(l, ol.BUF_SOL)), l
 
 
