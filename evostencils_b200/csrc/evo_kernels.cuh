@@ -758,105 +758,140 @@ __global__ void __launch_bounds__(1024) k2_smooth_rowseq_win(const Geom g, const
     }
 }
 
+// dense 3x3 coefficient tables of the NF x NF blocks (table order p = (dy+1)*3 + (dx+1)); zero = no entry
+template <int NF> struct Dense9 { double w[NF][NF][9]; };
+
 // Pipelined version: the 2k colour passes of k consecutive sweeps run concurrently, pass p two rows behind pass
 // p-1 (row y of a pass reads rows y-1 (already updated by this pass), y, y+1 (updated by the previous pass one
 // step earlier): exactly the values the sequential sweeps would see).  Each pass is a group of warps of the one
 // CTA; a step is one __syncthreads.  Rows stream through a shared-memory window once (cp.async in, 16-byte stores
 // out when a row has left the last pass), so k sweeps cost (n + 4k) row steps instead of 2k n.
+constexpr int ROWSEQ_NT = 512;   // 2 CTAs (or other kernels of a population) fit beside it on an SM
 template <int NF>
-__global__ void __launch_bounds__(1024) k2_smooth_rowseq_pipe(const Geom g, const __grid_constant__ OpSten st, const double omega,
-                                                              Fields<double> u, Fields<double> rhs, const int sweeps)
+__global__ void __launch_bounds__(ROWSEQ_NT, 2) k2_smooth_rowseq_pipe(const Geom g, const __grid_constant__ OpSten st, const __grid_constant__ Dense9<NF> dn,
+                                                              const double omega, Fields<double> u, Fields<double> rhs, const int sweeps)
 {
     extern __shared__ __align__(16) double win[];   // [W slots][2*NF arrays][pitch]
     const int n = g.n, pitch = g.pitch;
     const int chunks = pitch / 2;                    // 16-byte chunks per row
     const int P = 2 * sweeps, W = 2 * P + 3;
-    const int G = ((1024 / P) / 32) * 32;            // threads per pass (whole warps); the rest only moves data
+    const int SL = 2 * NF * pitch;                   // doubles per window slot
+    const int G = ((ROWSEQ_NT / P) / 32) * 32;       // threads per pass (whole warps); the rest only moves data
     const int grp = threadIdx.x / G, lt = threadIdx.x - grp * G;
-    auto arr = [&](int row, int a) { return win + ((size_t)(row % W) * 2 * NF + a) * pitch; };
-    auto fetch = [&](int row) {
-        if (row >= 0 && row <= n - 1)
-            for (int t = threadIdx.x; t < 2 * NF * chunks; t += 1024) {
-                const int a = t / chunks, c = t - a * chunks;
-                const double *src = (a < NF ? u.p[a] : rhs.p[a - NF]) + (long long)row * pitch + 2 * c;
-                cp_async16(arr(row, a) + 2 * c, src);
-            }
+    // step-invariant part of this thread's share of a row transfer (<= 3 chunks in, <= 2 chunks out per thread)
+    const double *in_src[3];
+    int in_off[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int t = threadIdx.x + k * ROWSEQ_NT;
+        in_src[k] = nullptr;
+        in_off[k] = 0;
+        if (t < 2 * NF * chunks) {
+            const int a = t / chunks, c = t - a * chunks;
+            in_src[k] = (a < NF ? u.p[a] : rhs.p[a - NF]) + 2 * c;
+            in_off[k] = a * pitch + 2 * c;
+        }
+    }
+    double *out_dst[2];
+    int out_off[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int t = threadIdx.x + k * ROWSEQ_NT;
+        out_dst[k] = nullptr;
+        out_off[k] = 0;
+        if (t < NF * chunks) {
+            const int a = t / chunks, c = t - a * chunks;
+            out_dst[k] = u.p[a] + 2 * c;
+            out_off[k] = a * pitch + 2 * c;
+        }
+    }
+    auto fetch = [&](int row, int slot) {
+        if (row <= n - 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (in_src[k]) cp_async16(win + slot * SL + in_off[k], in_src[k] + (long long)row * pitch);
+        }
         cp_async_commit();
     };
-    auto store_row = [&](int row) {
-        for (int t = threadIdx.x; t < NF * chunks; t += 1024) {
-            const int a = t / chunks, c = t - a * chunks;
-            *reinterpret_cast<double2 *>(u.p[a] + (long long)row * pitch + 2 * c) = *reinterpret_cast<const double2 *>(arr(row, a) + 2 * c);
-        }
+    auto store_row = [&](int row, int slot) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (out_dst[k])
+                *reinterpret_cast<double2 *>(out_dst[k] + (long long)row * pitch) = *reinterpret_cast<const double2 *>(win + slot * SL + out_off[k]);
     };
     // the local matrix (diagonal entries of the blocks) is the same at every anchor: factor it once
     double M0[NF][NF];
 #pragma unroll
     for (int a = 0; a < NF; ++a)
 #pragma unroll
-        for (int m = 0; m < NF; ++m) M0[a][m] = 0.0;
-#pragma unroll
-    for (int a = 0; a < NF; ++a)
-#pragma unroll
-        for (int j = 0; j < NF; ++j) {
-            const Sten &sj = st.s[a][j];
-            for (int q = 0; q < sj.nnz; ++q)
-                if (sj.ox[q] == 0 && sj.oy[q] == 0) {
-#pragma unroll
-                    for (int m = 0; m < NF; ++m)
-                        if (m == j) M0[a][m] = M0[a][m] + sj.re[q];
-                }
-        }
+        for (int m = 0; m < NF; ++m) M0[a][m] = dn.w[a][m][4];
     DenseLU<double, NF> lu;
     dense_factor<double, NF>(M0, lu);
-    fetch(0); fetch(1); fetch(2);
+    fetch(0, 0); fetch(1, 1); fetch(2, 2);
     const int last = (n - 2) + 2 * (P - 1);
+    // window slots (row % W), advanced by one per step: row y+2 (fetch), this pass's row yr = y - 2 grp, and the row
+    // that left the last pass in the previous step, yb = y - 2 (P-1) - 1
+    int s_fetch = 3 % W;
+    int s_r = ((1 - 2 * grp) % W + W) % W;
+    int s_b = ((1 - 2 * (P - 1) - 1) % W + W) % W;
     for (int y = 1; y <= last; ++y) {
-        fetch(y + 2);
+        fetch(y + 2, s_fetch);
         cp_async_wait<1>();      // everything but the newest group (row y+2) has landed
         __syncthreads();         // ... for all threads; the previous step's updates are visible
-        const int yb = y - 2 * (P - 1) - 1;   // left the last pass in the previous step
-        if (yb >= 1) store_row(yb);
+        const int yb = y - 2 * (P - 1) - 1;
+        if (yb >= 1) store_row(yb, s_b);
         const int yr = y - 2 * grp;
         if (grp < P && yr >= 1 && yr <= n - 2) {
             const int color = grp & 1;
-            const double *up[3][NF];
-            double *uc[NF];
-            const double *fr[NF];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                up[0][j] = arr(yr - 1, j); up[1][j] = arr(yr, j); up[2][j] = arr(yr + 1, j);
-                uc[j] = arr(yr, j);
-                fr[j] = arr(yr, NF + j);
-            }
+            const int s_m = s_r == 0 ? W - 1 : s_r - 1, s_p = s_r + 1 == W ? 0 : s_r + 1;
+            const double *rm = win + s_m * SL, *r0 = win + s_r * SL, *rp = win + s_p * SL;   // field j at + j * pitch
+            double *uc = win + s_r * SL;
+            const double *fr = r0 + NF * pitch;
             for (int t = lt;; t += G) {
                 const int x = 1 + 2 * t + ((1 + yr + color) & 1);
                 if (x > n - 2) break;
+                // all neighbour values first (independent loads), then the sums in table order; absent entries
+                // (coefficient 0) are skipped by a uniform branch, so the arithmetic is that of the sparse loop
+                double nbv[NF][9];
+#pragma unroll
+                for (int j = 0; j < NF; ++j) {
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        nbv[j][dx] = rm[j * pitch + x + dx - 1];
+                        nbv[j][3 + dx] = r0[j * pitch + x + dx - 1];
+                        nbv[j][6 + dx] = rp[j * pitch + x + dx - 1];
+                    }
+                }
                 double b[NF];
 #pragma unroll
                 for (int a = 0; a < NF; ++a) {
                     double sacc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < NF; ++j) {
-                        const Sten &sj = st.s[a][j];
-                        for (int q = 0; q < sj.nnz; ++q)
-                            if (!(sj.ox[q] == 0 && sj.oy[q] == 0)) sacc = sacc + sj.re[q] * up[sj.oy[q] + 1][j][x + sj.ox[q]];
-                    }
-                    b[a] = fr[a][x] - sacc;
+                    for (int j = 0; j < NF; ++j)
+#pragma unroll
+                        for (int p = 0; p < 9; ++p) {
+                            if (p == 4) continue;
+                            const double cf = dn.w[a][j][p];
+                            if (cf != 0.0) sacc = sacc + cf * nbv[j][p];
+                        }
+                    b[a] = fr[a * pitch + x] - sacc;
                 }
                 if (NF == 1) b[0] = b[0] * lu.inv[0];
                 else dense_solve<double, NF>(lu, b);
 #pragma unroll
                 for (int a = 0; a < NF; ++a) {
-                    const double old = uc[a][x];
-                    uc[a][x] = old + omega * (b[a] - old);
+                    const double old = nbv[a][4];
+                    uc[a * pitch + x] = old + omega * (b[a] - old);
                 }
             }
         }
+        if (++s_fetch == W) s_fetch = 0;
+        if (++s_r == W) s_r = 0;
+        if (++s_b == W) s_b = 0;
     }
     cp_async_wait<0>();
     __syncthreads();
-    store_row(n - 2);
+    store_row(n - 2, (n - 2) % W);
 }
 
 }  // namespace evo

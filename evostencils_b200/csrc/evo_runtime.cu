@@ -560,14 +560,25 @@ template <typename T, int DIM, int NF> struct Launch {
                             // pipelined passes: as many of the remaining sweeps as the window fits (<= 4)
                             int k = std::min(reps - rep, 4);
                             while (k > 0 && (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double) > 200 * 1024) --k;
-                            if (canonical && !disabled && !no_pipe && k > 0) {
+                            Dense9<NF> dn;
+                            bool dense_ok = true;
+                            for (int a = 0; a < NF; ++a)
+                                for (int j = 0; j < NF; ++j) {
+                                    for (int q = 0; q < 9; ++q) dn.w[a][j][q] = 0.0;
+                                    const Sten &sj = c->sten[l].s[a][j];
+                                    for (int q = 0; q < sj.nnz; ++q) {
+                                        if (sj.oz[q] != 0 || sj.im[q] != 0.0 || sj.re[q] == 0.0) dense_ok = false;
+                                        dn.w[a][j][(sj.oy[q] + 1) * 3 + (sj.ox[q] + 1)] = sj.re[q];
+                                    }
+                                }
+                            if (canonical && !disabled && !no_pipe && k > 0 && dense_ok) {
                                 static bool attr_p = false;
                                 if (!attr_p) {
                                     CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                                     attr_p = true;
                                 }
                                 const size_t sm2 = (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double);
-                                k2_smooth_rowseq_pipe<NF><<<1, 1024, sm2, s>>>(g, c->sten[l], sp.omega, u, rhs, k);
+                                k2_smooth_rowseq_pipe<NF><<<1, ROWSEQ_NT, sm2, s>>>(g, c->sten[l], dn, sp.omega, u, rhs, k);
                                 done = true;
                                 rep += k - 1;
                             } else if (canonical && !disabled && smem <= 200 * 1024) {
