@@ -303,6 +303,248 @@ __global__ void __launch_bounds__(NT) k3_rbgs_stream(const __grid_constant__ CUt
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lean single-sweep variant of k3_rbgs_stream (S = 2): the same tiles, TMA ring, stages and lane mapping, but the
+// z loop carries no index arithmetic -- per work item one 32-bit shared-memory byte offset (+8 when the right node
+// of the pair is the active one), ring-slot bases advanced incrementally, ld/st.shared with immediate neighbour
+// offsets, the copy-out offsets fixed per thread.  (The generic kernel spent ~80 % of its issue slots on integer
+// and uniform-datapath instructions: ncu profiles/r1_c_*.)
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ double lds_f64_off(uint32_t addr)
+{
+    double v;
+    if constexpr (OFF >= 0) asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    else asm volatile("ld.shared.f64 %0, [%1+-%2];" : "=d"(v) : "r"(addr), "n"(-OFF));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+constexpr int RB_LEAN_NP = 5;   // ring depth of the lean kernel: planes t-2 .. t+2 (6 = two planes of TMA prefetch: no gain measured)
+template <int TY, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256 && TY <= 8) ? 5 : 1) k3_rbgs_lean(const __grid_constant__ CUtensorMap umap, const double *__restrict__ f,
+                                                   double *__restrict__ uout, const Geom g, const Star7 c, const double inv_c,
+                                                   const double omega, const int tz)
+{
+    using R = RbCfg<2, TY, NT>;
+    using C0 = StageCfg<2, TY, NT, 0>;
+    using C1 = StageCfg<2, TY, NT, 1>;
+    constexpr int H = R::H, LX = R::LX, LY = R::LY, NP = RB_LEAN_NP, PSTRIDE = R::PSTRIDE;
+    constexpr int PF = NP - 4;   // planes of TMA prefetch beyond t+1 (ring: planes t-2 .. t+1+PF)
+    constexpr int R0 = C0::ROUNDS, R1 = C1::ROUNDS, TOT = R0 + R1;
+    constexpr uint32_t PLANE_BYTES = LX * LY * 8, PB = PSTRIDE * 8;
+    constexpr int OUTR = (RB_TX * TY + NT - 1) / NT;
+    static_assert(TOT <= 32, "validity bit masks are 32 bits wide");
+    extern __shared__ __align__(128) double ring[];
+    __shared__ __align__(8) uint64_t bars[NP];
+
+    const int n = g.n;
+    const int x0 = 1 + blockIdx.x * RB_TX, y0 = 1 + blockIdx.y * TY;
+    const int za = g.zlo + blockIdx.z * tz, zb = min(za + tz - 1, g.zhi);
+    const int xb = x0 - H - 1, yb = y0 - H;  // global coordinates of local (0, 0); xb is even
+    const int pbase = za - H;                // first plane ever loaded (may be < 0: zero filled, never used)
+    const int tid = threadIdx.x;
+    const uint32_t ring_u32 = smem_u32(ring);
+
+    if (tid == 0) {
+        for (int i = 0; i < NP; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    // work items (the mapping of rb_setup): byte offset of the pair's left node in a plane, its global in-plane
+    // offset, validity of the left / right node, colour parity of the left node for even z
+    uint32_t loff[TOT];
+    int goff[TOT];
+    unsigned v0 = 0u, v1 = 0u, par = 0u;
+    auto setup = [&](auto cfg, int base, int sidx) {
+        using C = decltype(cfg);
+#pragma unroll
+        for (int j = 0; j < C::ROUNDS; ++j) {
+            const int i = tid + NT * j;
+            const int grp = i >> 4, l16 = i & 15;
+            const int rp = grp / C::CH, ch = grp - rp * C::CH;
+            const int ry = 2 * rp + (l16 >> 3), kx = ch * 8 + (l16 & 7);
+            const int y = y0 - C::E + ry, xw = x0 - C::E + 2 * kx;
+            const bool ok = i < C::ITEMS && kx < C::NPX && ry < C::ROWS && y >= 1 && y <= n - 2;
+            loff[base + j] = (uint32_t)(((y - yb) * LX + (xw - xb)) * 8);
+            goff[base + j] = y * g.pitch + xw;
+            if (ok && xw >= 1 && xw <= n - 2) v0 |= 1u << (base + j);
+            if (ok && xw + 1 >= 1 && xw + 1 <= n - 2) v1 |= 1u << (base + j);
+            if ((xw + y + sidx) & 1) par |= 1u << (base + j);
+        }
+    };
+    setup(C0{}, 0, 0);
+    setup(C1{}, R0, 1);
+    // validity masks for q = (z + zpar) & 1 of the item's plane: active node = left iff its colour is even
+    const unsigned okq0 = (~par & v0) | (par & v1), okq1 = (~par & v1) | (par & v0);
+    // copy-out: fixed (row, x) elements of the tile per thread
+    uint32_t co_s[OUTR];
+    int co_g[OUTR];
+#pragma unroll
+    for (int k = 0; k < OUTR; ++k) {
+        const int e = tid + k * NT;
+        const int ry = e / RB_TX, rx = e - ry * RB_TX;
+        const bool ok = e < RB_TX * TY && x0 + rx <= n - 2 && y0 + ry <= n - 2;
+        co_s[k] = (uint32_t)(((ry + H) * LX + rx + H + 1) * 8);
+        co_g[k] = ok ? (y0 + ry) * g.pitch + x0 + rx : -1;
+    }
+    __syncthreads();
+
+    auto slot_of = [&](int p) { return (p - pbase) % NP; };
+    auto issue = [&](int p) {  // one thread
+        const int sl = slot_of(p);
+        mbar_expect_tx(&bars[sl], PLANE_BYTES);
+        tma_load_plane(ring + (size_t)sl * PSTRIDE, &umap, xb, yb, p, &bars[sl]);
+    };
+    const int t0 = za - 1, t1 = zb + 1;       // stage 0 works on plane t, stage 1 on plane t-1
+    const int pmax = min(zb + H, g.nz - 1);   // last plane that is ever read
+    if (tid == 0) {
+        for (int p = pbase; p <= min(t0 + PF, pmax); ++p) issue(p);
+    }
+    const int lo0 = max(za - 1, g.zin0), hi0 = min(zb + 1, g.zin1);   // planes stage 0 updates (halo recomputation)
+    // The z loop is unrolled by two (v = (t - t0) & 1): the colour parity of a plane alternates, so per v every
+    // item has a loop-invariant byte offset of its active node, validity bit and right-hand-side offset.
+    uint32_t off[2][TOT];
+    int fsel[2][TOT];
+    unsigned okv[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const unsigned q0 = (unsigned)(t0 + v + g.zpar) & 1u;
+        const unsigned pp0 = q0 ? ~par : par, pp1 = q0 ? par : ~par;     // stage 0 works on plane t, stage 1 on t-1
+        const unsigned m0 = (1u << R0) - 1u;
+        okv[v] = ((q0 ? okq1 : okq0) & m0) | ((q0 ? okq0 : okq1) & ~m0);
+#pragma unroll
+        for (int j = 0; j < TOT; ++j) {
+            const unsigned p = ((j < R0 ? pp0 : pp1) >> j) & 1u;
+            off[v][j] = loff[j] + (p << 3);
+            fsel[v][j] = (int)p;
+        }
+    }
+    // right-hand-side pointers of the items for the NEXT load (stage 0: plane t, stage 1: plane t-1), advanced per step
+    const double *fptr[TOT];
+#pragma unroll
+    for (int j = 0; j < TOT; ++j) fptr[j] = f + (long long)(j < R0 ? t0 : t0 - 1) * g.plane + goff[j];
+    double fbuf[2][TOT];      // right-hand sides of the current step (index v) and of the next one (1 - v)
+#pragma unroll
+    for (int i = 0; i < TOT; ++i) { fbuf[0][i] = 0.0; fbuf[1][i] = 0.0; }
+    {   // right-hand sides of the first step
+        const bool in0 = t0 >= lo0 && t0 <= hi0, in1 = t0 - 1 >= za && t0 - 1 <= zb;
+#pragma unroll
+        for (int j = 0; j < TOT; ++j) {
+            if ((j < R0 ? in0 : in1) && ((okv[0] >> j) & 1u)) fbuf[0][j] = __ldg(fptr[j] + fsel[0][j]);
+            fptr[j] += g.plane;
+        }
+    }
+    int sl = slot_of(t0);                      // ring slot of plane t
+    for (int p = pbase; p <= min(t0, pmax); ++p) mbar_wait(&bars[slot_of(p)], 0u);
+    int wsl = slot_of(t0 + 1), wph = ((t0 + 1 - pbase) / NP) & 1;   // mbarrier slot / phase of plane t+1
+
+    for (int tt = t0; tt <= t1; tt += 2) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int t = tt + v;
+            if (t > t1) break;
+            if (t < t1) {   // right-hand sides of the next step: issued now, consumed one step later (latency hidden)
+                const bool in0 = t + 1 >= lo0 && t + 1 <= hi0, in1 = t >= za && t <= zb;
+#pragma unroll
+                for (int j = 0; j < TOT; ++j) {
+                    if ((j < R0 ? in0 : in1) && ((okv[1 - v] >> j) & 1u)) fbuf[1 - v][j] = __ldg(fptr[j] + fsel[1 - v][j]);
+                    fptr[j] += g.plane;
+                }
+            }
+            if (t + 1 <= pmax) mbar_wait(&bars[wsl], (uint32_t)wph);
+            if (tid == 0 && t + 1 + PF <= pmax) {
+                fence_proxy_async();           // generic-proxy accesses of the recycled slot completed before the last barrier
+                issue(t + 1 + PF);
+            }
+            const int s_m1 = sl == 0 ? NP - 1 : sl - 1, s_m2 = s_m1 == 0 ? NP - 1 : s_m1 - 1, s_p1 = sl + 1 == NP ? 0 : sl + 1;
+            const uint32_t b_t = ring_u32 + sl * PB, b_m1 = ring_u32 + s_m1 * PB, b_m2 = ring_u32 + s_m2 * PB, b_p1 = ring_u32 + s_p1 * PB;
+            if (t >= lo0 && t <= hi0) {        // stage 0: first colour on plane t
+#pragma unroll
+                for (int j = 0; j < R0; ++j)
+                    if ((okv[v] >> j) & 1u) {
+                        const uint32_t o = off[v][j];
+                        const uint32_t ac = b_t + o;
+                        double sum = 0.0;
+                        sum = sum + c.zm * lds_f64(b_m1 + o);
+                        sum = sum + c.ym * lds_f64_off<-LX * 8>(ac);
+                        sum = sum + c.xm * lds_f64_off<-8>(ac);
+                        sum = sum + c.xp * lds_f64_off<8>(ac);
+                        sum = sum + c.yp * lds_f64_off<LX * 8>(ac);
+                        sum = sum + c.zp * lds_f64(b_p1 + o);
+                        const double xs = (fbuf[v][j] - sum) * inv_c;
+                        const double old = lds_f64(ac);
+                        sts_f64(ac, old + omega * (xs - old));
+                    }
+            }
+            __syncthreads();
+            if (t - 1 >= za && t - 1 <= zb) {  // stage 1: second colour on plane t-1, then the plane is final
+#pragma unroll
+                for (int j = R0; j < TOT; ++j)
+                    if ((okv[v] >> j) & 1u) {
+                        const uint32_t o = off[v][j];
+                        const uint32_t ac = b_m1 + o;
+                        double sum = 0.0;
+                        sum = sum + c.zm * lds_f64(b_m2 + o);
+                        sum = sum + c.ym * lds_f64_off<-LX * 8>(ac);
+                        sum = sum + c.xm * lds_f64_off<-8>(ac);
+                        sum = sum + c.xp * lds_f64_off<8>(ac);
+                        sum = sum + c.yp * lds_f64_off<LX * 8>(ac);
+                        sum = sum + c.zp * lds_f64(b_t + o);
+                        const double xs = (fbuf[v][j] - sum) * inv_c;
+                        const double old = lds_f64(ac);
+                        sts_f64(ac, old + omega * (xs - old));
+                    }
+                __syncthreads();
+                double *op = uout + (long long)(t - 1) * g.plane;
+#pragma unroll
+                for (int k = 0; k < OUTR; ++k)
+                    if (co_g[k] >= 0) op[co_g[k]] = lds_f64(b_m1 + co_s[k]);
+            } else {
+                __syncthreads();
+            }
+            // no barrier needed here: the slot the next step's TMA recycles (plane t-2) was last read by stage 1
+            // above, i.e. before that stage's barrier; the store loop reads a different slot
+            sl = s_p1;
+            if (++wsl == NP) { wsl = 0; wph ^= 1; }
+        }
+    }
+}
+
+template <int TY, int NT>
+static bool launch_rbgs_lean(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout,
+                             double omega, cudaStream_t s)
+{
+    using R = RbCfg<2, TY, NT>;
+    CUtensorMap map;
+    if (!make_plane_map(&map, g, u, R::LX, R::LY)) return false;
+    const size_t smem = (size_t)RB_LEAN_NP * R::PSTRIDE * 8;
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaFuncSetAttribute(k3_rbgs_lean<TY, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_lean<TY, NT>, NT, smem) != cudaSuccess || occ < 1) occ = 1;
+    }
+    const int inner = g.n - 2, planes = g.zhi - g.zlo + 1;
+    const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + TY - 1) / TY;
+    const long long slots = (long long)occ * sm_count;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int slabs = 1; slabs <= 16 && (slabs == 1 || slabs * 8 <= planes); ++slabs) {
+        const int tzc = (planes + slabs - 1) / slabs;
+        const long long ctas = (long long)tx * ty * ((planes + tzc - 1) / tzc);
+        const double waves = (double)((ctas + slots - 1) / slots);
+        const double cost = waves * (tzc + 6);
+        if (cost < best_cost) { best_cost = cost; best = slabs; }
+    }
+    const int tz = (planes + best - 1) / best;
+    const int slabs = (planes + tz - 1) / tz;
+    k3_rbgs_lean<TY, NT><<<dim3(tx, ty, slabs), NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
+    return cudaGetLastError() == cudaSuccess;
+}
+
 template <int S, int TY, int NT>
 static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout,
                                double omega, cudaStream_t s)
@@ -355,7 +597,13 @@ static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Field
             if (variant == 5) return launch_rbgs_stream<2, 12, 256>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 6) return launch_rbgs_stream<2, 6, 128>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 7) return launch_rbgs_stream<2, 4, 128>(sm_count, g, c, up, fp, op, omega, s);
-            return launch_rbgs_stream<2, 8, 256>(sm_count, g, c, up, fp, op, omega, s);   // best measured: 68 % of HBM peak
+            if (variant == 10) return launch_rbgs_lean<8, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 11) return launch_rbgs_lean<16, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 12) return launch_rbgs_lean<32, 256>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 13) return launch_rbgs_lean<16, 512>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 14) return launch_rbgs_lean<8, 128>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 20) return launch_rbgs_stream<2, 8, 256>(sm_count, g, c, up, fp, op, omega, s);   // generic multi-stage kernel: 65-68 %
+            return launch_rbgs_lean<8, 256>(sm_count, g, c, up, fp, op, omega, s);   // best measured: 73 % of HBM peak
         }
         if (sweeps == 2) {
             if (variant == 1) return launch_rbgs_stream<4, 32, 512>(sm_count, g, c, up, fp, op, omega, s);
