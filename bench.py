@@ -285,8 +285,14 @@ def run_ours(args, rank, world, local_rank):
         ms, n_launch = cyc.profile_op(sm_op, repeat=10)
         alg_bytes = 24.0 * ndof                      # read u, f, write u per full sweep
         achieved = alg_bytes / (ms * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this size
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         roof = {"bound": "hbm", "kernel": "RB-GS sweep, finest level (both colours)", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": ms, "launches_per_sweep": n_launch,
                 "smoother_gdof_s": ndof / (ms * 1e-3) / 1e9}
         other = {}

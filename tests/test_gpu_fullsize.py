@@ -1,0 +1,85 @@
+"""Parity at BASELINE.json's full sizes.  The C/OpenMP oracle still finishes a few cycles at these sizes in seconds
+on the GPU box's host cores, so the first iterations are compared bit for bit; the rest is covered by
+size-independent properties (exact discrete solution, two different kernel paths giving identical histories)."""
+import numpy as np
+import pytest
+
+from evostencils_b200 import cycles, domain, lowering, oplist as ol, problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def poisson513():
+    return problems.Poisson3D(2, 9)
+
+
+def test_poisson3d_513_first_iterations_bit_exact(cuda_backend, oracle_mod, poisson513):
+    prob = poisson513
+    prog = lowering.optimise(cycles.default_solver_cycle(prob))      # what the drop-in generator lowers to (fused)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    a = gc.solve(prob.settings.tol, 2, 1)
+    b = oc.solve(prob.settings.tol, 2, 1)
+    assert a.iterations == b.iterations == 2
+    assert np.array_equal(a.residuals, b.residuals)
+    gc.close()
+
+
+def test_poisson3d_513_full_solve_properties(cuda_backend, poisson513):
+    prob = poisson513
+    s = prob.settings
+    dev = cuda_backend.DeviceProblem(prob)
+    plain = cycles.default_solver_cycle(prob)
+    fused = lowering.optimise(plain)
+    a = dev.build(fused).solve(s.tol, s.max_iters, 1)
+    # h-independent multigrid convergence: same iteration count as on 65^3 .. 129^3 (tests/test_gpu_parity.py)
+    assert a.status == 0 and 8 <= a.iterations <= 10
+    assert a.residuals[-1] < s.tol * a.residuals[0]
+    assert np.all(np.diff(a.residuals) < 0)
+    # two different kernel paths (fused residual+restriction vs the two statements) -> identical histories
+    c2 = dev.build(plain)
+    b = c2.solve(s.tol, s.max_iters, 1)      # the fields keep the final state
+    assert a.iterations == b.iterations and np.array_equal(a.residuals, b.residuals)
+    # the boundary function x^2 - y^2/2 - z^2/2 is a harmonic quadratic: the 7-point operator is exact for it, so the
+    # discrete solution is the function itself
+    u = c2.get_field(prob.max_level, ol.BUF_SOL)
+    n = prob.nodes(prob.max_level)
+    x = np.linspace(0.0, 1.0, n)
+    exact = x[None, None, :] ** 2 - 0.5 * x[None, :, None] ** 2 - 0.5 * x[:, None, None] ** 2
+    assert np.abs(u - exact).max() < 1e-10
+
+
+def test_poisson3d_257_three_slabs_identical(cuda_backend):
+    prob = problems.Poisson3D(2, 8)
+    prog = lowering.optimise(cycles.default_solver_cycle(prob))
+    s = prob.settings
+    ref = cuda_backend.DeviceProblem(prob).build(prog).solve(s.tol, s.max_iters, 1)
+    dd = domain.DomainSolver.emulate(prob, prog, 3, 6)
+    try:
+        out = dd.solve(s.tol, s.max_iters)
+        assert out.iterations == ref.iterations and np.array_equal(out.residuals, ref.residuals)
+    finally:
+        dd.close()
+
+
+def test_fas_4097_first_iterations_bit_exact(cuda_backend, oracle_mod):
+    prob = problems.FAS2D(8, 12)
+    prog = cycles.fas_v_cycle(prob)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    a = gc.solve(prob.settings.tol, 3, 1)
+    b = oc.solve(prob.settings.tol, 3, 1)
+    assert a.iterations == b.iterations == 3
+    assert np.array_equal(a.residuals, b.residuals)
+
+
+def test_poisson2d_4097_first_iterations_bit_exact(cuda_backend, oracle_mod):
+    prob = problems.Poisson2D(5, 12)
+    prog = lowering.optimise(cycles.default_solver_cycle(prob))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    a = gc.solve(prob.settings.tol, 100, 1)
+    b = oc.solve(prob.settings.tol, 100, 1)
+    assert a.iterations == b.iterations and a.iterations < 12
+    assert np.array_equal(a.residuals, b.residuals)
