@@ -28,7 +28,8 @@ EXPORTED_SYMBOLS = (
     "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm", "evo_cycle_profile_op",
     "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
     "evo_problem_set_slab", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
-    "evo_cycle_residual_plane_sums", "evo_cycle_vecsum",
+    "evo_cycle_residual_plane_sums", "evo_cycle_vecsum", "evo_cycle_vecsum_async", "evo_cycle_read_sum",
+    "evo_cycle_swap_slots",
 )
 
 _lib = None
@@ -79,6 +80,9 @@ def load_library(path: Optional[str] = None):
     lib.evo_cycle_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.evo_cycle_residual_plane_sums.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.evo_cycle_vecsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.evo_cycle_vecsum_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.evo_cycle_read_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.evo_cycle_swap_slots.argtypes = [C.c_void_p, C.c_int]
     if lib.evo_abi_version() != ol.ABI_VERSION:
         raise BackendError("ABI version mismatch between the Python host and libevostencils_b200.so")
     if path == LIB_PATH:
@@ -210,6 +214,17 @@ class DeviceCycle:
         v = C.c_double()
         _check(self._lib, self._lib.evo_cycle_vecsum(self._h, C.c_void_p(device_ptr), m, C.byref(v)), "evo_cycle_vecsum")
         return float(v.value)
+
+    def vecsum_async(self, device_ptr: int, m: int):
+        _check(self._lib, self._lib.evo_cycle_vecsum_async(self._h, C.c_void_p(device_ptr), m), "evo_cycle_vecsum_async")
+
+    def read_sum(self) -> float:
+        v = C.c_double()
+        _check(self._lib, self._lib.evo_cycle_read_sum(self._h, C.byref(v)), "evo_cycle_read_sum")
+        return float(v.value)
+
+    def swap_slots(self, level: int):
+        _check(self._lib, self._lib.evo_cycle_swap_slots(self._h, level), "evo_cycle_swap_slots")
 
     def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0) -> SolveOutcome:
         prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)

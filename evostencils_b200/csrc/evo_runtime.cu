@@ -1339,6 +1339,42 @@ extern "C" int evo_cycle_vecsum(evo_cycle *c, const double *device_vals, int m, 
     return EVO_OK;
 }
 
+// stream-ordered variant for captured execution: the sum stays on the device (SolveState::sum) until
+// evo_cycle_read_sum copies it out
+extern "C" int evo_cycle_vecsum_async(evo_cycle *c, const double *device_vals, int m)
+{
+    if (!c || !device_vals || m < 0) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    k_vecsum_out<<<1, 32, 0, c->stream>>>(device_vals, m, &c->d_state->sum);
+    CU(cudaGetLastError());
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_read_sum(evo_cycle *c, double *out)
+{
+    if (!c || !out) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c->h_state->sum;
+    return EVO_OK;
+}
+
+// exchange SOL and its [next] slot on the host side (after replaying a captured cycle an odd number of times the
+// data lives in the other buffer)
+extern "C" int evo_cycle_swap_slots(evo_cycle *c, int level)
+{
+    if (!c || level < c->p->desc.min_level || level > c->p->desc.max_level) return fail(EVO_ERR_INVALID, "invalid argument");
+    for (int i = 0; i < c->p->desc.n_fields; ++i) {
+        if (!c->lv[level].slot[i]) return fail(EVO_ERR_INVALID, "level %d has no [next] slot", level);
+        bool cor_alias = c->lv[level].buf[EVO_BUF_COR][i] == c->lv[level].buf[EVO_BUF_SOL][i];
+        std::swap(c->lv[level].buf[EVO_BUF_SOL][i], c->lv[level].slot[i]);
+        if (cor_alias) c->lv[level].buf[EVO_BUF_COR][i] = c->lv[level].buf[EVO_BUF_SOL][i];
+        c->lv[level].swapped[i] = !c->lv[level].swapped[i];
+    }
+    return EVO_OK;
+}
+
 extern "C" int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, double *ms_per_exec, int64_t *launches_per_exec)
 {
     if (!c || !op || repeat < 1) return fail(EVO_ERR_INVALID, "null argument");

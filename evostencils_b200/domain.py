@@ -338,6 +338,14 @@ class DomainSolver:
         return cls(problem, program, layout, [me], DistComm(me, rank, world, group))
 
     def close(self):
+        # captured graphs hold NCCL work: release them (and wait for the device) before the communicator goes away
+        if getattr(self, "_graphs", None):
+            for dv in {r.device for r in self.ranks}:
+                self.torch.cuda.synchronize(dv)
+            self._graphs = None
+            self._keep = None
+            import gc
+            gc.collect()
         for r in self.ranks:
             r.close()
 
@@ -365,6 +373,18 @@ class DomainSolver:
                     r.cycle.exec_ops(r._c_ops[st.a][1], 1, lo, hi)
                 else:
                     r.cycle.exec_ops(r._c_ops[st.a][1], 1)
+
+    def _run_cycle_eager(self):
+        plan = self._plans.get(self._valid_key())
+        if plan is None:
+            key = self._valid_key()
+            valid = dict(self.valid)
+            plan = (schedule(self.program, self.layout, valid), valid)
+            self._plans[key] = plan
+        steps, after = plan
+        for st in steps:
+            self._run(st)
+        self.valid = dict(after)
 
     def cycle(self):
         plan = self._plans.get(self._valid_key())
@@ -405,6 +425,91 @@ class DomainSolver:
             assert full.numel() == self.problem.nodes(top) - 2
             s = self.ranks[0].cycle.vecsum(full.data_ptr(), full.numel())
         return math.sqrt(s)
+
+    # -- captured execution: one CUDA graph per iteration (kernels + NCCL exchanges) -------------------------------
+    def _norm_partial(self):
+        """Residual on the owned planes + plane sums + all-gather + canonical total, all stream ordered; the sum is
+        read with read_sum() afterwards."""
+        torch = self.torch
+        top = self.problem.max_level
+        if self.valid.get((top, ol.BUF_SOL), 0) < 1:
+            self.comm.halo(top, ol.BUF_SOL)
+            self.exchanges += 1
+            self.valid[(top, ol.BUF_SOL)] = GHOST
+        self.valid[(top, ol.BUF_RES)] = 0
+        parts = []
+        for r in self.ranks:
+            ptr, n = r.cycle.residual_plane_sums()
+            parts.append(torch.as_tensor(_DevArray(ptr, (n,)), device=f"cuda:{r.device}"))
+        sizes = [b - a + 1 for (a, b) in self.layout.owned[top]]
+        full = self.comm.gather_sums(parts, sizes).contiguous()
+        self._keep = full                      # the captured graph reads this buffer on every replay
+        self.ranks[0].cycle.vecsum_async(full.data_ptr(), full.numel())
+
+    def _canonical_validity(self):
+        top = self.problem.max_level
+        self.valid = {(top, ol.BUF_SOL): GHOST, (top, ol.BUF_RHS): GHOST}
+
+    def _capture(self):
+        """Two graphs: an iteration starting from the canonical buffer assignment (A) and one starting from the
+        assignment A leaves behind (B); statements that work out of place exchange SOL and its [next] slot."""
+        torch = self.torch
+        if len(self.ranks) != 1:
+            raise RuntimeError("captured execution is for one slab per process")
+        r = self.ranks[0]
+        levels = range(self.layout.lc, self.problem.max_level + 1)
+        self._graphs = []
+        before = {l: r.cycle.buffer_ptr(l, ol.BUF_SOL) for l in levels}
+        for k in range(2):
+            g = torch.cuda.CUDAGraph()
+            self._canonical_validity()
+            with torch.cuda.graph(g, stream=r.stream):
+                self._run_cycle_eager()
+                self._norm_partial()
+            self._graphs.append(g)
+            if k == 0:
+                self._flipping = [l for l in levels if r.cycle.buffer_ptr(l, ol.BUF_SOL) != before[l]]
+                if not self._flipping:
+                    self._graphs.append(g)     # nothing swaps: one graph serves every iteration
+                    break
+        after = {l: r.cycle.buffer_ptr(l, ol.BUF_SOL) for l in levels}
+        if after != before:
+            raise RuntimeError("two cycles did not return to the canonical buffer assignment")
+
+    def solve_captured(self, tol: float, max_iters: int) -> DomainOutcome:
+        """Same loop as solve(), each iteration one graph launch (host cost per iteration: a launch and a read-back
+        instead of ~60 statement / exchange calls).  NCCL communicators must exist (run solve() once before)."""
+        torch = self.torch
+        r = self.ranks[0]
+        with self._streams():
+            if getattr(self, "_odd", False):   # undo the host-side exchange of the previous (odd) solve
+                for l in self._flipping:
+                    r.cycle.swap_slots(l)
+                self._odd = False
+            if not getattr(self, "_graphs", None):
+                self._capture()
+            r.cycle.reset()
+            self._reset_validity()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.exchanges = 0
+            torch.cuda.synchronize(r.device)
+            ev0.record()
+            hist = [self.residual_norm()]
+            it = 0
+            while it < max_iters and math.isfinite(hist[-1]):
+                self._graphs[it & 1].replay()
+                it += 1
+                hist.append(math.sqrt(r.cycle.read_sum()))
+                if hist[-1] < tol * hist[0]:
+                    break
+            ev1.record()
+            torch.cuda.synchronize(r.device)
+            if it & 1:
+                for l in self._flipping:   # the data of an odd solve lives in the other buffers
+                    r.cycle.swap_slots(l)
+                self._odd = True
+            self._canonical_validity()
+        return DomainOutcome(it, hist, ev0.elapsed_time(ev1), self.exchanges)
 
     def solve(self, tol: float, max_iters: int) -> DomainOutcome:
         """`repeat until res < tol * res0 or it >= maxIts` (2D_FD_Poisson_fromL2.exa3:3-4), timed on the device."""
@@ -452,8 +557,10 @@ class DomainSolver:
 
 
 def default_lc(problem, world: int) -> int:
-    """Coarsest distributed level: keep at least 8 planes per rank, never below level 5 (33^3)."""
-    lc = 5
-    while ((1 << lc) - 1) < 8 * world:
+    """Coarsest distributed level: only the two finest levels are split (measured at 513^3 on 2 GPUs: lc = 8 31.3 ms,
+    7 31.9 ms, 5 36.2 ms per evaluation -- exchanges on small levels cost more than computing them redundantly),
+    at least 8 planes per rank, never below level 5 (33^3)."""
+    lc = max(5, problem.max_level - 1)
+    while lc < problem.max_level and ((1 << lc) - 1) < 8 * world:
         lc += 1
     return min(lc, problem.max_level)

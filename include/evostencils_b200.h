@@ -211,6 +211,13 @@ int evo_cycle_residual_plane_sums(evo_cycle *c, double **device_sums, int *count
 /* canonical vecsum (lane-strided + butterfly) of a device array, result on the host (synchronises)           */
 int evo_cycle_vecsum(evo_cycle *c, const double *device_vals, int m, double *out);
 
+/* stream-ordered pieces of the above for execution captured in a CUDA graph by the host (domain.py): the sum
+ * stays on the device until evo_cycle_read_sum (which synchronises); evo_cycle_swap_slots exchanges SOL and its
+ * [next] slot on the host side after an odd number of replays of a captured cycle                          */
+int evo_cycle_vecsum_async(evo_cycle *c, const double *device_vals, int m);
+int evo_cycle_read_sum(evo_cycle *c, double *out);
+int evo_cycle_swap_slots(evo_cycle *c, int level);
+
 /* measurement hook (bench.py roofline): launch the kernels of ONE statement `repeat` times on the
  * cycle's stream, bracketed by CUDA events; returns the average milliseconds per execution and the
  * number of kernel launches one execution makes.  The reference's counterpart is the per-function
