@@ -316,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
         from evostencils_b200 import domain
         cyc.close()
         solver = domain.DomainSolver.distributed(prob, prog, rank, world, local_rank)
+        solver.overlap = not args.domain_no_overlap
         dd_solve = solver.solve if args.domain_eager else solver.solve_captured
         o3 = solver.solve(s.tol, s.max_iters)          # creates the NCCL communicators (not capturable)
         for _ in range(2):
@@ -331,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
         t_dd = float(t.item())
         dd_info = {"value": args.steps / (t_dd * 1e-3), "unit": "evals/s", "scaling": "strong", "ms_per_eval": t_dd / args.steps,
                    "iterations": o3.iterations, "identical_history": bool(np.array_equal(o3.residuals, out.residuals)),
-                   "halo_exchanges_per_eval": o3.exchanges, "levels_distributed": f"{prob.max_level}..{solver.layout.lc}",
+                   "halo_exchanges_per_eval": o3.exchanges, "overlap": solver.overlap, "levels_distributed": f"{prob.max_level}..{solver.layout.lc}",
                    "note": "ONE evaluation split into z-slabs over all GPUs, NCCL send/recv halos; "
                            + ("host-orchestrated statements" if args.domain_eager else
                               "each iteration (kernels + exchanges) replayed as one CUDA graph")}
@@ -383,6 +384,7 @@ def run_domain(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    solver.overlap = not args.domain_no_overlap
     dd_solve = solver.solve if (args.domain_eager or world == 1) else solver.solve_captured
     out = solver.solve(s.tol, s.max_iters)
     for _ in range(args.warmup):
@@ -560,6 +562,8 @@ def run_population(args, rank, world, local_rank):
 
 
 def main():
+    # NCCL kernels of the halo exchanges should not queue behind the thousands of CTAs of an interior sweep
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -573,6 +577,8 @@ def main():
                     help="launch kernels directly (host-side solver loop) so that ncu can see them; not a bench value")
     ap.add_argument("--domain", action="store_true",
                     help="strong scaling: ONE evaluation decomposed into z-slabs over the GPUs (SURVEY.md 8e.2)")
+    ap.add_argument("--domain-no-overlap", action="store_true",
+                    help="domain decomposition: exchange after the whole sweep instead of boundary planes first")
     ap.add_argument("--domain-eager", action="store_true", help="domain decomposition without CUDA-graph capture")
     ap.add_argument("--no-domain", action="store_true", help="N > 1: skip the additional domain-decomposed measurement")
     ap.add_argument("--slabs", type=int, default=2, help="--domain on one GPU: number of emulated slabs")

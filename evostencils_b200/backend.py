@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
     "evo_problem_set_slab", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
     "evo_cycle_residual_plane_sums", "evo_cycle_vecsum", "evo_cycle_vecsum_async", "evo_cycle_read_sum",
-    "evo_cycle_swap_slots",
+    "evo_cycle_swap_slots", "evo_cycle_exec_part",
 )
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library(path: Optional[str] = None):
     lib.evo_cycle_vecsum_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.evo_cycle_read_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.evo_cycle_swap_slots.argtypes = [C.c_void_p, C.c_int]
+    lib.evo_cycle_exec_part.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.c_int, C.c_int]
     if lib.evo_abi_version() != ol.ABI_VERSION:
         raise BackendError("ABI version mismatch between the Python host and libevostencils_b200.so")
     if path == LIB_PATH:
@@ -198,6 +199,9 @@ class DeviceCycle:
 
     def exec_ops(self, c_ops, n: int, zc_lo: int = -1, zc_hi: int = -1):
         _check(self._lib, self._lib.evo_cycle_exec_ops(self._h, c_ops, n, zc_lo, zc_hi), "evo_cycle_exec_ops")
+
+    def exec_part(self, c_op, z_lo: int, z_hi: int, no_swap: bool):
+        _check(self._lib, self._lib.evo_cycle_exec_part(self._h, c_op, z_lo, z_hi, 1 if no_swap else 0), "evo_cycle_exec_part")
 
     def buffer_ptr(self, level: int, buf: int, field: int = 0) -> int:
         p = C.c_void_p()

@@ -528,6 +528,7 @@ static bool launch_rbgs_lean(int sm_count, const Geom &g, const Star7 &c, const 
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_lean<TY, NT>, NT, smem) != cudaSuccess || occ < 1) occ = 1;
     }
     const int inner = g.n - 2, planes = g.zhi - g.zlo + 1;
+    if (planes <= 0) return true;
     const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + TY - 1) / TY;
     const long long slots = (long long)occ * sm_count;
     int best = 1;
@@ -559,6 +560,7 @@ static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, cons
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_stream<S, TY, NT>, NT, smem) != cudaSuccess || occ < 1) occ = 1;
     }
     const int inner = g.n - 2, planes = g.zhi - g.zlo + 1;
+    if (planes <= 0) return true;
     const int tx = (inner + RB_TX - 1) / RB_TX, ty = (inner + TY - 1) / TY;
     // z slabs: minimise (waves) x (planes per slab + pipeline fill) over 1..16 slabs
     const long long slots = (long long)occ * sm_count;
@@ -802,6 +804,7 @@ static bool try_smooth_point(int, const Geom &g, const OpSten &st, const SmoothP
         // only the out-of-place Jacobi sweep (colour passes of RB-GS go through the streaming kernel)
         if (sp.color >= 0 || src.p[0] == dst.p[0] || g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
         const int ni = g.n - 2;
+        if (g.zhi < g.zlo) return true;
         k3_jacobi_rows<<<dim3((ni + 7) / 8, g.zhi - g.zlo + 1), 256, 0, s>>>(g, c, 1.0 / c.c, sp.omega, src.p[0], rhs.p[0], dst.p[0]);
         return cudaGetLastError() == cudaSuccess;
     } else {

@@ -145,6 +145,7 @@ struct evo_cycle {
     bool use_while_graph;
     bool pingpong = false;                               // the WHILE body holds two cycles (see build_solver_graph)
     bool odd_swap[EVO_MAX_LEVELS][EVO_MAX_FIELDS] = {};  // levels whose SOL ends in the [next] slot after one cycle
+    bool part_no_swap = false;   // partial execution of an out-of-place statement: leave SOL / [next] unexchanged
     int zc_lo = -1, zc_hi = -1;  // plane range override of the statement's destination level (domain decomposition)
     bool own_stream = true;
     bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
@@ -502,6 +503,8 @@ template <typename T, int DIM, int NF> struct Launch {
                 return fail(EVO_ERR_UNSUPPORTED, "local system without an unknown at the anchor node for field %d", i);
         auto rhs = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
         int reps = op.count > 1 ? op.count : 1;
+        Geom gsub = g;   // domain decomposition: a sub-range of the owned planes (boundary planes first, interior later)
+        if (c->zc_lo >= 0 && slab_level(c->p, l)) { gsub.zlo = c->zc_lo; gsub.zhi = c->zc_hi; }
         if (NU == 1 && op.mode == EVO_SMOOTH_REDBLACK && c->lv[l].slot[0] && star::rbgs_stream_applicable<T, DIM, NF>(g, c->sten[l])) {
             // fused streaming kernel: up to 2 sweeps per pass, out of place into the [next] slot
             while (reps > 0) {
@@ -509,8 +512,9 @@ template <typename T, int DIM, int NF> struct Launch {
                 static const bool fuse2 = getenv("EVO_RB_FUSE2") != nullptr;
                 const int k = (fuse2 && reps >= 2) ? 2 : 1;
                 auto src = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), dst = fields_of<T>(c->lv[l].slot, NF);
-                if (!star::try_rbgs_stream<T, DIM, NF>(c->p->sm_count, g, c->sten[l], src, rhs, dst, op.omega, k, s)) break;
+                if (!star::try_rbgs_stream<T, DIM, NF>(c->p->sm_count, gsub, c->sten[l], src, rhs, dst, op.omega, k, s)) break;
                 c->launch_counter++;
+                if (c->part_no_swap) { reps -= k; continue; }
                 bool cor_alias = c->lv[l].buf[EVO_BUF_COR][0] == c->lv[l].buf[EVO_BUF_SOL][0];
                 std::swap(c->lv[l].buf[EVO_BUF_SOL][0], c->lv[l].slot[0]);
                 if (cor_alias) c->lv[l].buf[EVO_BUF_COR][0] = c->lv[l].buf[EVO_BUF_SOL][0];
@@ -532,13 +536,13 @@ template <typename T, int DIM, int NF> struct Launch {
                 }
                 sp.color = -1;
                 auto src = fields_of<T>(cur, NF), dst = fields_of<T>(nxt, NF);
-                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, src, dst, rhs, s))) {
+                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, gsub, c->sten[l], sp, src, dst, rhs, s))) {
                     if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: Jacobi needs the 7-point fast path");
                     k_smooth<T, DIM, NF, NU><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], sp, src, dst, rhs);
                 }
                 c->launch_counter++;
                 for (int i = 0; i < NF; ++i)
-                    if (written[i]) {
+                    if (written[i] && !c->part_no_swap) {
                         bool cor_alias = c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].buf[EVO_BUF_SOL][i];
                         std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
                         c->lv[l].swapped[i] = !c->lv[l].swapped[i];
@@ -1297,7 +1301,34 @@ extern "C" int evo_cycle_exec_ops(evo_cycle *c, const evo_op *ops, int n_ops, in
 extern "C" int evo_cycle_buffer(evo_cycle *c, int level, int buf, int field, void **device_ptr)
 {
     if (!c || !device_ptr) return fail(EVO_ERR_INVALID, "null argument");
+    if (buf == EVO_BUF_NEXT) {   // the [next] slot of SOL (target of out-of-place statements)
+        const evo_problem_desc &d = c->p->desc;
+        if (level < d.min_level || level > d.max_level || field < 0 || field >= d.n_fields || !c->lv[level].slot[field])
+            return fail(EVO_ERR_INVALID, "no [next] slot on level %d", level);
+        *device_ptr = c->lv[level].slot[field];
+        return EVO_OK;
+    }
     return field_ptr(c, level, buf, field, device_ptr);
+}
+
+// one statement on the local planes [z_lo, z_hi] only; with EVO_PART_NO_SWAP an out-of-place smoother leaves SOL and
+// its [next] slot unexchanged, so that further parts of the same statement (and the halo exchange of the planes
+// already written) can follow; the last part is executed without the flag
+extern "C" int evo_cycle_exec_part(evo_cycle *c, const evo_op *op, int z_lo, int z_hi, int flags)
+{
+    if (!c || !op) return fail(EVO_ERR_INVALID, "null argument");
+    if (op->level < c->p->desc.min_level || op->level > c->p->desc.max_level) return fail(EVO_ERR_INVALID, "invalid level");
+    CU(cudaSetDevice(c->p->desc.device));
+    c->zc_lo = z_lo; c->zc_hi = z_hi;
+    c->part_no_swap = (flags & EVO_PART_NO_SWAP) != 0;
+    int rc = z_hi >= z_lo ? dispatch_op(c, *op, c->stream) : EVO_OK;
+    if (z_hi < z_lo && !c->part_no_swap) {   // empty last part: only the exchange of the slots
+        c->zc_lo = 1; c->zc_hi = 0;
+        rc = dispatch_op(c, *op, c->stream);
+    }
+    c->zc_lo = c->zc_hi = -1;
+    c->part_no_swap = false;
+    return rc;
 }
 
 extern "C" int evo_cycle_residual_plane_sums(evo_cycle *c, double **device_sums, int *count)

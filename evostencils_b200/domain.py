@@ -85,7 +85,7 @@ class Step:
         return f"Step({self.kind}, {self.a}, {self.b})"
 
 
-def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int], int]) -> List[Step]:
+def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int], int], overlap: bool = False) -> List[Step]:
     """Plan one pass over the op list; `valid` is updated in place (carry it from cycle to cycle)."""
     steps: List[Step] = []
     dist_ = layout.distributed
@@ -123,8 +123,13 @@ def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int
                 need(l, ol.BUF_RHS, 1)
             else:
                 need(l, ol.BUF_SOL, 1)
-            steps.append(Step("op", idx, 0))
-            valid[(l, ol.BUF_SOL)] = 0
+            if overlap:
+                # boundary planes, then their exchange travels while the interior planes are swept
+                steps.append(Step("smooth_overlapped", idx))
+                valid[(l, ol.BUF_SOL)] = GHOST
+            else:
+                steps.append(Step("op", idx, 0))
+                valid[(l, ol.BUF_SOL)] = 0
         elif c == ol.OP_RESIDUAL:
             need(l, ol.BUF_SOL, 1)
             e = max(0, min(v(l, ol.BUF_SOL) - 1, v(l, ol.BUF_RHS), 1))
@@ -220,6 +225,13 @@ class LocalComm:
             views[r + 1][ih["zlo"] - GHOST:ih["zlo"]].copy_(views[r][il["zhi"] - GHOST + 1:il["zhi"] + 1])
             views[r][il["zhi"] + 1:il["zhi"] + 1 + GHOST].copy_(views[r + 1][ih["zlo"]:ih["zlo"] + GHOST])
 
+    def halo_start(self, level: int, buf: int):
+        self.halo(level, buf)      # copies on the one stream: nothing to overlap in the emulation
+        return []
+
+    def halo_finish(self, reqs):
+        pass
+
     def gather_planes(self, level: int, buf: int, ranges: Sequence[Tuple[int, int]]):
         """Replicated level: rank r computed planes ranges[r]; make every copy complete."""
         views = [r.view(level, buf) for r in self.ranks]
@@ -259,6 +271,25 @@ class DistComm:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+
+    def halo_start(self, level: int, buf: int):
+        """Post the exchange of (level, buf) -- buf may be BUF_NEXT, the target of an out-of-place smoother -- and return
+        the requests; the current stream's work enqueued so far is what the sends wait for."""
+        dist = self.dist
+        me = self.ranks[0]
+        v, i = me.view(level, buf), me.info[level]
+        ops = []
+        if self.rank + 1 < self.world:
+            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - GHOST + 1:i["zhi"] + 1], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + GHOST], self.rank + 1, self.group))
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + GHOST], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - GHOST:i["zlo"]], self.rank - 1, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def halo_finish(self, reqs):
+        for req in reqs:
+            req.wait()
 
     def gather_planes(self, level: int, buf: int, ranges: Sequence[Tuple[int, int]]):
         v = self.ranks[0].view(level, buf)
@@ -306,6 +337,7 @@ class DomainSolver:
         self.exchanges = 0
         self.torch = self.ranks[0].torch
         self._plans = {}
+        self.overlap = False        # sweep the boundary planes first and exchange them while the interior is swept
         self._reset_validity()
 
     def _streams(self):
@@ -365,6 +397,26 @@ class DomainSolver:
                     r.cycle.exec_ops(r._c_ops[st.a][1], 1, a, b)
             self.comm.gather_planes(op.level - 1, ol.BUF_RHS if op.code == ol.OP_RESIDUAL_RESTRICT else op.dst, ranges)
             self.exchanges += 1
+        elif st.kind == "smooth_overlapped":
+            op = self.program.ops[st.a]
+            lvl = op.level
+            target = ol.BUF_NEXT if self._out_of_place(op) else ol.BUF_SOL
+            for r in self.ranks:
+                i = r.info[lvl]
+                if i["zhi"] - i["zlo"] + 1 < 2 * GHOST + 1:
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"], i["zhi"], True)
+                else:
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"], i["zlo"] + GHOST - 1, True)
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zhi"] - GHOST + 1, i["zhi"], True)
+            reqs = self.comm.halo_start(lvl, target)
+            self.exchanges += 1
+            for r in self.ranks:
+                i = r.info[lvl]
+                if i["zhi"] - i["zlo"] + 1 < 2 * GHOST + 1:
+                    r.cycle.exec_part(r._c_ops[st.a][1], 1, 0, False)          # only the exchange of the slots
+                else:
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"] + GHOST, i["zhi"] - GHOST, False)
+            self.comm.halo_finish(reqs)
         else:
             op = self.program.ops[st.a]
             for r in self.ranks:
@@ -379,7 +431,7 @@ class DomainSolver:
         if plan is None:
             key = self._valid_key()
             valid = dict(self.valid)
-            plan = (schedule(self.program, self.layout, valid), valid)
+            plan = (schedule(self.program, self.layout, valid, self.overlap), valid)
             self._plans[key] = plan
         steps, after = plan
         for st in steps:
@@ -391,7 +443,7 @@ class DomainSolver:
         if plan is None:
             key = self._valid_key()
             valid = dict(self.valid)
-            plan = (schedule(self.program, self.layout, valid), valid)
+            plan = (schedule(self.program, self.layout, valid, self.overlap), valid)
             self._plans[key] = plan
         steps, after = plan
         with self._streams():
@@ -399,8 +451,13 @@ class DomainSolver:
                 self._run(st)
         self.valid = dict(after)
 
+    @staticmethod
+    def _out_of_place(op: ol.Op) -> bool:
+        """Pointwise smoothers on distributed levels write the [next] slot (Jacobi and the streaming RB-GS kernel)."""
+        return op.code == ol.OP_SMOOTH
+
     def _valid_key(self):
-        return tuple(sorted(self.valid.items()))
+        return (self.overlap,) + tuple(sorted(self.valid.items()))
 
     def _reset_validity(self):
         top = self.problem.max_level

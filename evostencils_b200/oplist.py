@@ -23,6 +23,7 @@ STENCIL_POINTS = 27
 
 # evo_buffer
 BUF_SOL, BUF_RHS, BUF_RES, BUF_COR, BUF_APX = 0, 1, 2, 3, 4
+BUF_NEXT = 100   # evo_cycle_buffer only: the [next] slot of SOL
 BUF_NAMES = {BUF_SOL: "SOL", BUF_RHS: "RHS", BUF_RES: "RES", BUF_COR: "COR", BUF_APX: "APX"}
 
 # evo_opcode

@@ -50,7 +50,9 @@ enum evo_status {
  *   COR  = gen_error_<field>     (aliases SOL below the finest level; the lowering resolves that)
  *   APX  = FAS restricted fine solution (exastencils_FAS.py:121-136)                     */
 enum evo_buffer { EVO_BUF_SOL = 0, EVO_BUF_RHS = 1, EVO_BUF_RES = 2, EVO_BUF_COR = 3, EVO_BUF_APX = 4,
-                  EVO_BUF_COUNT = 5 };
+                  EVO_BUF_COUNT = 5,
+                  EVO_BUF_NEXT = 100 /* evo_cycle_buffer only: the [next] slot of SOL */ };
+#define EVO_PART_NO_SWAP 1
 
 /* ---------------------------------------------------------------- op codes
  * One op == one statement the reference's emitter would print (exastencils.py:684-925);
@@ -203,6 +205,9 @@ int evo_cycle_set_stream(evo_cycle *c, void *cuda_stream);
  * writes: coarse planes of RESTRICT, planes of RESIDUAL / PROLONG_ADD (to include ghost planes whose inputs
  * are valid and save an exchange)                                                                          */
 int evo_cycle_exec_ops(evo_cycle *c, const evo_op *ops, int n_ops, int zc_lo, int zc_hi);
+/* one statement on the local planes [z_lo, z_hi] (boundary planes first, interior while the halo travels);
+ * EVO_PART_NO_SWAP: an out-of-place smoother does not yet exchange SOL and its [next] slot                   */
+int evo_cycle_exec_part(evo_cycle *c, const evo_op *op, int z_lo, int z_hi, int flags);
 /* current device address of a field (the two slots of SOL swap after out-of-place statements)               */
 int evo_cycle_buffer(evo_cycle *c, int level, int buf, int field, void **device_ptr);
 /* RES@finest = RHS - A SOL on the owned planes + canonical per-plane sums of |r|^2: device array of

@@ -69,6 +69,23 @@ def test_fused_residual_restrict_in_slabs(cuda_backend, world, lc):
         dd.close()
 
 
+@pytest.mark.parametrize("world,lc,red_black", [(2, 6, True), (3, 5, True), (2, 6, False)])
+def test_boundary_first_execution_is_identical(cuda_backend, world, lc, red_black):
+    """overlap mode: every smoothing statement runs on the boundary planes first, then (while the halo travels) on the
+    interior; the partial launches and the deferred exchange of SOL and its [next] slot must not change a bit."""
+    prob = problems.Poisson3D(2, 7)
+    prog = cycles.v_cycle(prob, 2, 1, 1.25 if red_black else 0.8, red_black)
+    ref, ref_sol = _reference(cuda_backend, prob, prog)
+    dd = domain.DomainSolver.emulate(prob, prog, world, lc)
+    dd.overlap = True
+    try:
+        out = dd.solve(prob.settings.tol, prob.settings.max_iters)
+        assert out.iterations == ref.iterations and np.array_equal(out.residuals, ref.residuals)
+        assert np.array_equal(dd.gather_solution(), ref_sol)
+    finally:
+        dd.close()
+
+
 def test_unsupported_statements_are_refused(cuda_backend):
     prob = problems.Poisson3D(2, 6)
     prog = cycles.v_cycle(prob, 1, 1, 1.0, True)
