@@ -421,9 +421,21 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
     evo_problem *p = c->p;
     const int nf = p->desc.n_fields, hi = p->desc.max_level;
     const size_t esz = sizeof(double) * p->words;
-    // zero everything we own (boundary layers of the coarse fields must be 0 and are never written)
-    CU(cudaMemsetAsync(c->slab, 0, c->slab_bytes, s));
+    // zero everything we own (boundary layers of the coarse fields must be 0 and are never written) -- except the
+    // finest SOL arrays and their [next] slots, which are overwritten by the initial guess right below
     const size_t fb = (size_t)p->geom[hi].total * esz;
+    std::vector<std::pair<char *, size_t>> skip;
+    for (int i = 0; i < nf; ++i) {
+        skip.push_back({(char *)c->lv[hi].buf[EVO_BUF_SOL][i], fb});
+        if (c->lv[hi].slot[i]) skip.push_back({(char *)c->lv[hi].slot[i], fb});
+    }
+    std::sort(skip.begin(), skip.end());
+    char *cur = (char *)c->slab, *end = (char *)c->slab + c->slab_bytes;
+    for (const auto &sk : skip) {
+        if (sk.first > cur) CU(cudaMemsetAsync(cur, 0, (size_t)(sk.first - cur), s));
+        cur = std::max(cur, sk.first + sk.second);
+    }
+    if (end > cur) CU(cudaMemsetAsync(cur, 0, (size_t)(end - cur), s));
     for (int i = 0; i < nf; ++i) {
         CU(cudaMemcpyAsync(c->lv[hi].buf[EVO_BUF_SOL][i], p->init_sol[i], fb, cudaMemcpyDeviceToDevice, s));
         // both jacobi slots carry the Dirichlet boundary values
