@@ -98,6 +98,8 @@ struct evo_problem {
     std::vector<std::pair<void *, size_t>> pool;  // recycled cycle work slabs
     int slab_world = 1, slab_rank = 0, slab_lc = 0;  // domain decomposition (slab_lc = 0: none)
     int own_g0[EVO_MAX_LEVELS], own_g1[EVO_MAX_LEVELS];   // owned global plane range per distributed level
+    struct CycleRes { cudaStream_t stream; cudaEvent_t ev0, ev1; SolveState *h_state; double *h_hist, *d_hist; int hist_cap; };
+    std::vector<CycleRes> res_pool;               // streams / events / pinned buffers of destroyed cycles, recycled
     int live_cycles = 0;                          // cycles still referring to this problem
     bool closed = false;                          // evo_problem_destroy called while cycles were alive
 };
@@ -145,6 +147,7 @@ struct evo_cycle {
     bool use_while_graph;
     bool pingpong = false;                               // the WHILE body holds two cycles (see build_solver_graph)
     bool odd_swap[EVO_MAX_LEVELS][EVO_MAX_FIELDS] = {};  // levels whose SOL ends in the [next] slot after one cycle
+    bool pristine = false;       // freshly reset: evo_cycle_solve need not reset again
     bool part_no_swap = false;   // partial execution of an out-of-place statement: leave SOL / [next] unexchanged
     int zc_lo = -1, zc_hi = -1;  // plane range override of the statement's destination level (domain decomposition)
     bool own_stream = true;
@@ -243,6 +246,12 @@ static void free_problem(evo_problem *p)
     cudaSetDevice(p->desc.device);
     for (int i = 0; i < EVO_MAX_FIELDS; ++i) { cudaFree(p->init_sol[i]); cudaFree(p->rhs0[i]); }
     for (auto &s : p->pool) cudaFree(s.first);
+    for (auto &cr : p->res_pool) {
+        if (cr.d_hist) cudaFree(cr.d_hist);
+        if (cr.h_state) cudaFreeHost(cr.h_state);
+        if (cr.h_hist) cudaFreeHost(cr.h_hist);
+        cudaEventDestroy(cr.ev0); cudaEventDestroy(cr.ev1); cudaStreamDestroy(cr.stream);
+    }
     delete p;
 }
 
@@ -441,6 +450,7 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
         // both jacobi slots carry the Dirichlet boundary values
         if (c->lv[hi].slot[i]) CU(cudaMemcpyAsync(c->lv[hi].slot[i], p->init_sol[i], fb, cudaMemcpyDeviceToDevice, s));
     }
+    c->pristine = true;
     return EVO_OK;
 }
 
@@ -1000,6 +1010,7 @@ static int dispatch_op_inner(evo_cycle *c, const evo_op &op, cudaStream_t s);
 // statement that writes one of them (same rule as oracle helm_bc_after_op)
 static int dispatch_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
 {
+    c->pristine = false;
     EV(dispatch_op_inner(c, op, s));
     if (c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ) return EVO_OK;
     int buf = -1;
@@ -1028,6 +1039,7 @@ static int dispatch_op_inner(evo_cycle *c, const evo_op &op, cudaStream_t s)
 
 static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store = false)
 {
+    c->pristine = false;
     const bool saved_dead = c->res_dead_on_entry;
     if (force_store) c->res_dead_on_entry = false;
     struct Restore { evo_cycle *c; bool v; ~Restore() { c->res_dead_on_entry = v; } } restore{c, saved_dead};
@@ -1179,10 +1191,17 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
     int rc = validate_ops(c);
     if (rc == EVO_OK) rc = allocate_cycle(c);
     if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&c->ev0));
-    CU(cudaEventCreate(&c->ev1));
-    CU(cudaMallocHost(&c->h_state, sizeof(SolveState)));
+    if (!p->res_pool.empty()) {
+        evo_problem::CycleRes cr = p->res_pool.back();
+        p->res_pool.pop_back();
+        c->stream = cr.stream; c->ev0 = cr.ev0; c->ev1 = cr.ev1; c->h_state = cr.h_state;
+        c->h_hist = cr.h_hist; c->d_hist = cr.d_hist; c->hist_cap = cr.hist_cap;
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&c->ev0));
+        CU(cudaEventCreate(&c->ev1));
+        CU(cudaMallocHost(&c->h_state, sizeof(SolveState)));
+    }
     rc = reset_cycle(c, c->stream);
     if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
     CU(cudaStreamSynchronize(c->stream));
@@ -1208,10 +1227,14 @@ extern "C" int evo_cycle_destroy(evo_cycle *c)
         cudaFree(c->p->pool.front().first);
         c->p->pool.erase(c->p->pool.begin());
     }
-    if (c->d_hist) cudaFree(c->d_hist);
-    if (c->h_state) cudaFreeHost(c->h_state);
-    if (c->h_hist) cudaFreeHost(c->h_hist);
-    if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->own_stream) cudaStreamDestroy(c->stream); }
+    if (c->stream && c->own_stream && c->h_state && !c->p->closed && c->p->res_pool.size() < 1024) {
+        c->p->res_pool.push_back({c->stream, c->ev0, c->ev1, c->h_state, c->h_hist, c->d_hist, c->hist_cap});
+    } else {
+        if (c->d_hist) cudaFree(c->d_hist);
+        if (c->h_state) cudaFreeHost(c->h_state);
+        if (c->h_hist) cudaFreeHost(c->h_hist);
+        if (c->stream) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->own_stream) cudaStreamDestroy(c->stream); }
+    }
     evo_problem *p = c->p;
     delete c;
     if (--p->live_cycles == 0 && p->closed) free_problem(p);
@@ -1260,6 +1283,7 @@ extern "C" int evo_cycle_get_field(evo_cycle *c, int level, int buf, int field, 
 extern "C" int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, const double *host, size_t n_doubles)
 {
     if (!c || !host) return fail(EVO_ERR_INVALID, "null argument");
+    c->pristine = false;
     void *dev;
     EV(field_ptr(c, level, buf, field, &dev));
     if (level == c->p->desc.max_level && buf == EVO_BUF_RHS && c->p->desc.kind != EVO_PROBLEM_HELMHOLTZ)
@@ -1678,7 +1702,8 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
 static int enqueue_solve(evo_cycle *c, const evo_solve_params *prm)
 {
     cudaStream_t s = c->stream;
-    if (!(prm->flags & EVO_SOLVE_KEEP_STATE)) EV(reset_cycle(c, s));
+    if (!(prm->flags & EVO_SOLVE_KEEP_STATE) && !c->pristine) EV(reset_cycle(c, s));   // a fresh cycle is already reset
+    c->pristine = false;
     CU(cudaEventRecord(c->ev0, s));
     if (prm->flags & EVO_SOLVE_NO_GRAPH) {
         // debugging path: direct launches, host-side loop with one synchronisation per iteration
