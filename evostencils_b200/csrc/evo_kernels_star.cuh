@@ -649,7 +649,33 @@ __global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star
     const double *uc = u + base, *fc = f + base;
     const double *uym = uc - g.pitch, *uyp = uc + g.pitch, *uzm = uc - g.plane, *uzp = uc + g.plane;
     double acc = 0.0;
-    for (int x = 1 + lane; x <= ni; x += 32) {
+    // four x-strides of loads in flight per lane before the first use (the kernel is latency bound otherwise);
+    // the sums and the canonical accumulation stay in ascending x order
+    int x = 1 + lane;
+    for (; x + 96 <= ni; x += 128) {
+        double vzm[4], vym[4], vxm[4], vc[4], vxp[4], vyp[4], vzp[4], vf[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + 32 * k;
+            vzm[k] = uzm[xx]; vym[k] = uym[xx]; vxm[k] = uc[xx - 1]; vc[k] = uc[xx]; vxp[k] = uc[xx + 1];
+            vyp[k] = uyp[xx]; vzp[k] = uzp[xx]; vf[k] = fc[xx];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double sum = 0.0;
+            sum = sum + c.zm * vzm[k];
+            sum = sum + c.ym * vym[k];
+            sum = sum + c.xm * vxm[k];
+            sum = sum + c.c * vc[k];
+            sum = sum + c.xp * vxp[k];
+            sum = sum + c.yp * vyp[k];
+            sum = sum + c.zp * vzp[k];
+            const double rv = vf[k] - sum;
+            if (STORE) r[base + x + 32 * k] = rv;
+            if (NORM) acc = acc + rv * rv;
+        }
+    }
+    for (; x <= ni; x += 32) {
         double sum = 0.0;
         sum = sum + c.zm * uzm[x];
         sum = sum + c.ym * uym[x];
@@ -682,7 +708,29 @@ __global__ void __launch_bounds__(256) k3_jacobi_rows(const Geom g, const Star7 
     const long long base = (long long)z * g.plane + (long long)y * g.pitch;
     const double *uc = u + base, *fc = f + base;
     const double *uym = uc - g.pitch, *uyp = uc + g.pitch, *uzm = uc - g.plane, *uzp = uc + g.plane;
-    for (int x = 1 + lane; x <= ni; x += 32) {
+    int x = 1 + lane;
+    for (; x + 96 <= ni; x += 128) {   // four x-strides of loads in flight per lane (see k3_residual_rows)
+        double vzm[4], vym[4], vxm[4], vc[4], vxp[4], vyp[4], vzp[4], vf[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + 32 * k;
+            vzm[k] = uzm[xx]; vym[k] = uym[xx]; vxm[k] = uc[xx - 1]; vc[k] = uc[xx]; vxp[k] = uc[xx + 1];
+            vyp[k] = uyp[xx]; vzp[k] = uzp[xx]; vf[k] = fc[xx];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double sum = 0.0;
+            sum = sum + c.zm * vzm[k];
+            sum = sum + c.ym * vym[k];
+            sum = sum + c.xm * vxm[k];
+            sum = sum + c.xp * vxp[k];
+            sum = sum + c.yp * vyp[k];
+            sum = sum + c.zp * vzp[k];
+            const double xs = (vf[k] - sum) * inv_c;
+            unew[base + x + 32 * k] = vc[k] + omega * (xs - vc[k]);
+        }
+    }
+    for (; x <= ni; x += 32) {
         double sum = 0.0;
         sum = sum + c.zm * uzm[x];
         sum = sum + c.ym * uym[x];
