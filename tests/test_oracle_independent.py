@@ -85,3 +85,41 @@ def test_fas_solution_satisfies_the_nonlinear_equations(oracle_mod):
     x = np.linspace(0, 1, n)
     exact = prob.exact_solution(x[None, 1:-1], x[1:-1, None]).reshape(-1)
     assert np.abs(u - exact).max() < 5e-3
+
+
+def test_helmholtz_solution_satisfies_independently_assembled_equations(oracle_mod):
+    """Outer operator -Lap_h - k^2 with the Robin closure u_b = u_inner / (1 - i k h) on the x boundaries and u = 0 on the
+    y boundaries (Helmholtz exa4:43-108), assembled here from the stencil table; the oracle's BiCGStab solution (stop
+    1e-7) must satisfy it and agree with a sparse direct solve."""
+    prob = problems.Helmholtz2D(3, 6, k=40.0)
+    level = prob.max_level
+    n, ni = prob.nodes(level), prob.nodes(level) - 2
+    h = prob.spacing(level)
+    table = prob.outer_operator(level)
+    rden = 1.0 / (1.0 - 1j * prob.wave_number * h)
+    idx = np.arange(ni * ni).reshape(ni, ni)                 # [y-1, x-1]
+    A = sp.lil_matrix((ni * ni, ni * ni), dtype=np.complex128)
+    for p in range(ol.STENCIL_POINTS):
+        cf = table[0, 0, p]
+        if cf == 0:
+            continue
+        dx, dy = ol.stencil_offset(p, 2)
+        for y in range(1, n - 1):
+            for x in range(1, n - 1):
+                xx, yy = x + dx, y + dy
+                if yy < 1 or yy > n - 2:
+                    continue                                  # Dirichlet 0
+                if xx < 1 or xx > n - 2:
+                    A[idx[y - 1, x - 1], idx[yy - 1, x - 1]] += cf * rden     # Robin: boundary value = rden * inner neighbour
+                else:
+                    A[idx[y - 1, x - 1], idx[yy - 1, xx - 1]] += cf
+    b = prob.rhs(0, level)[1:-1, 1:-1].reshape(-1).astype(np.complex128)
+    cyc = oracle_mod.OracleProblem(prob).build(cycles.default_solver_cycle(prob))
+    out = cyc.helmholtz_solve(prob.settings.tol, prob.settings.max_iters, 1)
+    u = cyc.get_field(level, ol.BUF_COR)[1:-1, 1:-1].reshape(-1)      # the outer solution is left in COR@finest
+    A = A.tocsc()
+    assert out.residuals[-1] < prob.settings.tol * out.residuals[0]
+    assert abs(np.linalg.norm(b) - out.residuals[0]) <= 1e-12 * out.residuals[0]
+    assert np.linalg.norm(b - A @ u) < 5e-7 * np.linalg.norm(b)
+    direct = spla.spsolve(A, b)
+    assert np.abs(u - direct).max() < 1e-4 * np.abs(direct).max()
