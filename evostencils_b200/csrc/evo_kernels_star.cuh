@@ -324,9 +324,12 @@ template <int OFF> __device__ __forceinline__ double lds_f64_off(uint32_t addr)
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
+#ifndef RB_LEAN_MINB
+#define RB_LEAN_MINB 6
+#endif
 constexpr int RB_LEAN_NP = 5;   // ring depth of the lean kernel: planes t-2 .. t+2 (6 = two planes of TMA prefetch: no gain measured)
 template <int TY, int NT>
-__global__ void __launch_bounds__(NT, (NT <= 256 && TY <= 8) ? 5 : 1) k3_rbgs_lean(const __grid_constant__ CUtensorMap umap, const double *__restrict__ f,
+__global__ void __launch_bounds__(NT, (NT <= 256 && TY <= 8) ? RB_LEAN_MINB : 1) k3_rbgs_lean(const __grid_constant__ CUtensorMap umap, const double *__restrict__ f,
                                                    double *__restrict__ uout, const Geom g, const Star7 c, const double inv_c,
                                                    const double omega, const int tz)
 {
