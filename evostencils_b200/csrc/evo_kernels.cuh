@@ -761,6 +761,100 @@ __global__ void __launch_bounds__(1024) k2_smooth_rowseq_win(const Geom g, const
 // dense 3x3 coefficient tables of the NF x NF blocks (table order p = (dy+1)*3 + (dx+1)); zero = no entry
 template <int NF> struct Dense9 { double w[NF][NF][9]; };
 
+// CG on a 2-D coarsest grid with at most 32 x 32 inner nodes: ONE node per thread (warp = row, lane = x), x / r / p /
+// A p of the node live in registers for the whole solve, only p is mirrored in shared memory for the neighbours.
+// Statement for statement the arithmetic of k_coarse_cg_smem (A p accumulated in table order, row sums by the xor
+// butterfly, rows and fields added by warp_vecsum in order) -> the same iterates bit for bit, at a third of the
+// latency per iteration (the coarse solve was half of a 2-D Poisson cycle).
+template <int NF>
+__global__ void __launch_bounds__(1024) k2_coarse_cg_reg(const Geom g, const __grid_constant__ Dense9<NF> dn, Fields<double> xg,
+                                                        Fields<double> bg, int max_it, double tol, int *iters_out)
+{
+    extern __shared__ double psm[];          // [NF][n][n] compact copy of p (boundary entries 0)
+    __shared__ double rowsum[2][NF * 32];
+    const int n = g.n, ni = n - 2, vol = n * n;
+    const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool act = row < ni && lane < ni;
+    const int c0 = (1 + row) * n + 1 + lane;  // compact index of this thread's node
+    for (int t = threadIdx.x; t < NF * vol; t += 1024) psm[t] = 0.0;
+    double xv[NF], rv[NF], pv[NF], av[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        xv[i] = 0.0; av[i] = 0.0;
+        rv[i] = act ? bg.p[i][node_index(g, 1 + lane, 1 + row, 0)] : 0.0;
+        pv[i] = rv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+        if (act) psm[i * vol + c0] = pv[i];
+    int flip = 0;
+    // row sums -> rowsum[flip][field * ni + row]; then (after ONE barrier) every warp forms the identical total
+    auto reduce = [&](const double (&term)[NF]) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            double acc = 0.0;
+            if (act) acc = acc + term[i];
+            acc = warp_butterfly(acc);
+            if (lane == 0 && row < ni) rowsum[flip][i * ni + row] = acc;
+        }
+        __syncthreads();
+        double total = 0.0;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) total = total + warp_vecsum(&rowsum[flip][i * ni], ni);
+        flip ^= 1;
+        return total;
+    };
+    double term[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) term[i] = rv[i] * rv[i];
+    double rr = reduce(term);     // also orders the p mirror before the first A p
+    const double r0 = sqrt(rr);
+    int it = 0;
+    if (r0 != 0.0) {
+        while (it < max_it) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                double a = 0.0;
+                if (act) {
+#pragma unroll
+                    for (int j = 0; j < NF; ++j)
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) {
+                            const double cf = dn.w[i][j][q];
+                            if (cf != 0.0) a = a + cf * psm[j * vol + c0 + (q / 3 - 1) * n + (q % 3 - 1)];
+                        }
+                }
+                av[i] = a;
+                term[i] = pv[i] * a;
+            }
+            const double pap = reduce(term);
+            const double alpha = rr / pap;
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                xv[i] = xv[i] + alpha * pv[i];
+                rv[i] = rv[i] - alpha * av[i];
+                term[i] = rv[i] * rv[i];
+            }
+            const double rr_new = reduce(term);
+            ++it;
+            if (!(sqrt(rr_new) > tol * r0)) break;
+            const double beta = rr_new / rr;
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                pv[i] = rv[i] + beta * pv[i];
+                if (act) psm[i * vol + c0] = pv[i];
+            }
+            rr = rr_new;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+        if (act) xg.p[i][node_index(g, 1 + lane, 1 + row, 0)] = xv[i];
+    if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
 // Pipelined version: the 2k colour passes of k consecutive sweeps run concurrently, pass p two rows behind pass
 // p-1 (row y of a pass reads rows y-1 (already updated by this pass), y, y+1 (updated by the previous pass one
 // step earlier): exactly the values the sequential sweeps would see).  Each pass is a group of warps of the one

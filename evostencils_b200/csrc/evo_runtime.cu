@@ -762,6 +762,27 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
         const size_t smem = 4 * NF * vol * sizeof(double);
         const int nrows = ni * (DIM == 3 ? ni : 1);
         static const bool disabled = getenv("EVO_CG_GLOBAL") != nullptr;
+        static const bool no_reg = getenv("EVO_CG_NOREG") != nullptr;
+        if constexpr (DIM == 2) {
+            // one node per thread, CG vectors in registers (coarsest grids up to 33 x 33)
+            Dense9<NF> dn;
+            bool dense_ok = !disabled && !no_reg && ni <= 32;
+            for (int a = 0; a < NF && dense_ok; ++a)
+                for (int j = 0; j < NF; ++j) {
+                    for (int q = 0; q < 9; ++q) dn.w[a][j][q] = 0.0;
+                    const Sten &sj = c->sten[l].s[a][j];
+                    for (int q = 0; q < sj.nnz; ++q) {
+                        if (sj.oz[q] != 0 || sj.im[q] != 0.0 || sj.re[q] == 0.0) dense_ok = false;
+                        dn.w[a][j][(sj.oy[q] + 1) * 3 + (sj.ox[q] + 1)] = sj.re[q];
+                    }
+                }
+            if (dense_ok) {
+                k2_coarse_cg_reg<NF><<<1, 1024, NF * vol * sizeof(double), s>>>(g, dn, x, b, op.count, op.tol, c->d_cg_iters);
+                c->launch_counter++;
+                CU(cudaGetLastError());
+                return EVO_OK;
+            }
+        }
         if (!disabled && smem <= 160 * 1024 && NF * nrows <= 512 && (DIM == 2 || ni <= 64)) {
             static bool attr = false;
             if (!attr) {
