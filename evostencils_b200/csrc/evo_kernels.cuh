@@ -921,6 +921,17 @@ __global__ void __launch_bounds__(ROWSEQ_NT, 2) k2_smooth_rowseq_pipe(const Geom
         for (int m = 0; m < NF; ++m) M0[a][m] = dn.w[a][m][4];
     DenseLU<double, NF> lu;
     dense_factor<double, NF>(M0, lu);
+    // which table entries exist: tested per term in the sweep without touching the constant bank again
+    unsigned nz[NF][NF];
+#pragma unroll
+    for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            nz[a][j] = 0u;
+#pragma unroll
+            for (int p = 0; p < 9; ++p)
+                if (dn.w[a][j][p] != 0.0) nz[a][j] |= 1u << p;
+        }
     fetch(0, 0); fetch(1, 1); fetch(2, 2);
     const int last = (n - 2) + 2 * (P - 1);
     // window slots (row % W), advanced by one per step: row y+2 (fetch), this pass's row yr = y - 2 grp, and the row
@@ -965,8 +976,7 @@ __global__ void __launch_bounds__(ROWSEQ_NT, 2) k2_smooth_rowseq_pipe(const Geom
 #pragma unroll
                         for (int p = 0; p < 9; ++p) {
                             if (p == 4) continue;
-                            const double cf = dn.w[a][j][p];
-                            if (cf != 0.0) sacc = sacc + cf * nbv[j][p];
+                            if ((nz[a][j] >> p) & 1u) sacc = sacc + dn.w[a][j][p] * nbv[j][p];
                         }
                     b[a] = fr[a * pitch + x] - sacc;
                 }
