@@ -259,6 +259,10 @@ class Lowering:
         return self._cor(level)
 
     def _register_operator(self, system_operator, level: int):
+        seen = self.__dict__.setdefault("_registered_operators", {})
+        if seen.get(id(system_operator)) == level:        # the same terminal again (kept alive by the tree)
+            return
+        seen[id(system_operator)] = level
         table = operator_table(system_operator, self.nf)
         if level in self.operators:
             if not np.array_equal(self.operators[level], table):

@@ -88,10 +88,24 @@ class CEvoSolveResult(C.Structure):
 
 def stencil_index(offset: Sequence[int]) -> int:
     """Table index p = (dz+1)*9 + (dy+1)*3 + (dx+1) of a stencil offset (2-D: dz = 0)."""
+    try:
+        return _STENCIL_INDEX[tuple(offset)]
+    except (KeyError, TypeError):
+        pass
     o = tuple(int(v) for v in offset) + (0,) * (3 - len(offset))
     if any(abs(v) > 1 for v in o):
         raise ValueError(f"stencil offset {offset} outside the 3^d neighbourhood")
     return (o[2] + 1) * 9 + (o[1] + 1) * 3 + (o[0] + 1)
+
+
+# every offset of the 3^d neighbourhoods (the lowering calls stencil_index ~400 times per individual)
+_STENCIL_INDEX = {}
+for _dz in (-1, 0, 1):
+    for _dy in (-1, 0, 1):
+        for _dx in (-1, 0, 1):
+            _STENCIL_INDEX[(_dx, _dy, _dz)] = (_dz + 1) * 9 + (_dy + 1) * 3 + (_dx + 1)
+            if _dz == 0:
+                _STENCIL_INDEX[(_dx, _dy)] = 9 + (_dy + 1) * 3 + (_dx + 1)
 
 
 def stencil_offset(p: int, dim: int) -> Tuple[int, ...]:
