@@ -46,6 +46,9 @@ def measured_peak():
 def make_workload(name: str, fuse: bool = True):
     """The problem and its `generate solver` cycle, lowered the way the drop-in ProgramGenerator lowers it
     (program_generator.py: fuse=True -> lowering.optimise merges residual + restriction where the residual is dead)."""
+    wcycle = name.endswith("_w")           # same problem, W-cycle (gamma = 2) instead of the V-cycle of the solver block
+    if wcycle:
+        name = name[:-2]
     if name == "poisson3d_513":
         prob = problems.Poisson3D(2, 9)
     elif name == "poisson3d_257":
@@ -58,7 +61,8 @@ def make_workload(name: str, fuse: bool = True):
         prob = problems.Poisson2D(5, 12)
     else:
         raise SystemExit(f"unknown workload {name}")
-    prog = cycles.default_solver_cycle(prob)
+    s_ = prob.settings
+    prog = cycles.w_cycle(prob, s_.num_pre, s_.num_post, s_.damping, s_.red_black) if wcycle else cycles.default_solver_cycle(prob)
     if fuse:
         from evostencils_b200 import lowering
         prog = lowering.optimise(prog)
@@ -204,7 +208,7 @@ METRIC = "evolved-cycle fitness evals/s (one eval = solve to 1e-12 with the cycl
 def workload_config(name, prob, world):
     return {"workload": name, "problem": prob.name, "finest_nodes": f"{prob.nodes(prob.max_level)}^{prob.dim}",
             "levels": f"{prob.max_level}..{prob.min_level}",
-            "cycle": f"V({prob.settings.num_pre},{prob.settings.num_post}) red-black GS omega={prob.settings.damping} + CG",
+            "cycle": f"{'W' if name.endswith('_w') else 'V'}({prob.settings.num_pre},{prob.settings.num_post}) red-black GS omega={prob.settings.damping} + CG",
             "tol": prob.settings.tol, "max_iters": prob.settings.max_iters,
             "parallelism": "1 GPU" if world == 1 else f"population-sharded x{world} (one evaluation per GPU per step)",
             "l2_policy": "inputs larger than L2 (finest fields 1.1 GB each)" if prob.dim == 3 and prob.max_level >= 8
