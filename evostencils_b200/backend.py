@@ -29,14 +29,27 @@ EXPORTED_SYMBOLS = (
     "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
     "evo_problem_set_slab", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
     "evo_cycle_residual_plane_sums", "evo_cycle_vecsum", "evo_cycle_vecsum_async", "evo_cycle_read_sum",
-    "evo_cycle_swap_slots", "evo_cycle_exec_part",
+    "evo_cycle_swap_slots", "evo_cycle_exec_part", "evo_set_option", "evo_get_option",
 )
 
 _lib = None
 
 
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_OOM = -1, -2, -3, -4, -5
+
+
 class BackendError(RuntimeError):
-    pass
+    """Failure of a C-ABI call; ``status`` is the library's status code (include/evostencils_b200.h)."""
+
+    def __init__(self, message: str, status: int = ERR_INVALID):
+        super().__init__(message)
+        self.status = status
+
+    @property
+    def infrastructure(self) -> bool:
+        """True for failures that say nothing about the individual (no device, CUDA error, out of memory, a
+        statement the library does not implement): callers must not turn these into a fitness value."""
+        return self.status in (ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_OOM)
 
 
 def load_library(path: Optional[str] = None):
@@ -84,6 +97,8 @@ def load_library(path: Optional[str] = None):
     lib.evo_cycle_read_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.evo_cycle_swap_slots.argtypes = [C.c_void_p, C.c_int]
     lib.evo_cycle_exec_part.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.c_int, C.c_int]
+    lib.evo_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.evo_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     if lib.evo_abi_version() != ol.ABI_VERSION:
         raise BackendError("ABI version mismatch between the Python host and libevostencils_b200.so")
     if path == LIB_PATH:
@@ -94,7 +109,20 @@ def load_library(path: Optional[str] = None):
 def _check(lib, rc: int, what: str):
     if rc != 0:
         msg = lib.evo_last_error()
-        raise BackendError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+        raise BackendError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}", status=rc)
+
+
+def set_option(name: str, value: int) -> None:
+    """Tuning switch of the CUDA library (``EVO_RB_VARIANT`` ...); applies to solver graphs captured afterwards."""
+    lib = load_library()
+    _check(lib, lib.evo_set_option(name.encode(), int(value)), f"evo_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    lib = load_library()
+    v = C.c_int(0)
+    _check(lib, lib.evo_get_option(name.encode(), C.byref(v)), f"evo_get_option({name})")
+    return int(v.value)
 
 
 def device_count() -> int:
@@ -230,8 +258,8 @@ class DeviceCycle:
     def swap_slots(self, level: int):
         _check(self._lib, self._lib.evo_cycle_swap_slots(self._h, level), "evo_cycle_swap_slots")
 
-    def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0) -> SolveOutcome:
-        prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)
+    def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0, timeout_ms: int = 0) -> SolveOutcome:
+        prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, int(timeout_ms))
         res = ol.CEvoSolveResult()
         hist = np.zeros(max_iters + 1, dtype=np.float64)
         _check(self._lib, self._lib.evo_cycle_solve(self._h, C.byref(prm), C.byref(res),
@@ -239,12 +267,12 @@ class DeviceCycle:
         return SolveOutcome(res, hist)
 
 
-def _helmholtz_solve(cycle: "DeviceCycle", tol: float, max_iters: int, samples: int = 1) -> SolveOutcome:
+def _helmholtz_solve(cycle: "DeviceCycle", tol: float, max_iters: int, samples: int = 1, timeout_ms: int = 0) -> SolveOutcome:
     prob = cycle.problem.problem
     outer = ol.Program(dim=2, n_fields=1, min_level=prob.max_level, max_level=prob.max_level,
                        operators={prob.max_level: prob.outer_operator(prob.max_level)})
     arr, _ = outer.c_operators()
-    prm = ol.CEvoSolveParams(tol, max_iters, samples, 0, 0)
+    prm = ol.CEvoSolveParams(tol, max_iters, samples, 0, int(timeout_ms))
     res = ol.CEvoSolveResult()
     hist = np.zeros(max_iters + 1, dtype=np.float64)
     _check(cycle._lib, cycle._lib.evo_helmholtz_solve(cycle._h, arr, C.byref(prm), C.byref(res),
@@ -304,10 +332,14 @@ class DeviceProblem:
         return {k: int(v) for k, v in zip(keys, info)}
 
     def batch_solve(self, cycles: Sequence[DeviceCycle], tol: float, max_iters: int, samples: int = 1,
-                    flags: int = 0) -> Tuple[List[SolveOutcome], float]:
+                    flags: int = 0, solo_timing: bool = False, timeout_ms: int = 0) -> Tuple[List[SolveOutcome], float]:
+        """All cycles solve concurrently (one stream each).  ``solo_timing``: ``time_ms`` of every converged member is
+        re-measured with the GPU to itself (a few iterations, extrapolated) -- comparable with a single ``solve``."""
+        if solo_timing:
+            flags |= ol.SOLVE_SOLO_TIMING
         n = len(cycles)
         handles = (C.c_void_p * n)(*[c._h for c in cycles])
-        prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)
+        prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, int(timeout_ms))
         results = (ol.CEvoSolveResult * n)()
         hist = np.zeros((n, max_iters + 1), dtype=np.float64)
         ms = C.c_double()

@@ -6,9 +6,61 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "../../include/evostencils_b200.h"
 
 namespace evo {
+
+// ---------------------------------------------------------------------------------------------
+// Tuning switches (kernel variants, experiments).  Each one is initialised from its environment variable on
+// first use and can be changed at run time through evo_set_option() -- a new value takes effect for cycles
+// whose solver graph is captured afterwards.  Defaults are the measured best.
+enum {
+    OPT_RB_VARIANT,      // EVO_RB_VARIANT      tile shapes / kernel of the 3-D RB-GS sweep
+    OPT_RB_FUSE2,        // EVO_RB_FUSE2        two consecutive RB-GS sweeps per launch (temporal blocking)
+    OPT_RR_VARIANT,      // EVO_RR_VARIANT      tiles of the fused residual + restriction
+    OPT_NO_PINGPONG,     // EVO_NO_PINGPONG     copy the [next] slot back every cycle
+    OPT_CG_GLOBAL,       // EVO_CG_GLOBAL       coarse CG with its vectors in global memory
+    OPT_CG_NOREG,        // EVO_CG_NOREG        no register-resident coarse CG
+    OPT_ROWSEQ_GLOBAL,   // EVO_ROWSEQ_GLOBAL   order-dependent coloured sweeps without the shared-memory window
+    OPT_ROWSEQ_NOPIPE,   // EVO_ROWSEQ_NOPIPE   ... without the pipelined passes
+    OPT_FAS_CGS,         // EVO_FAS_CGS         FAS coarse solver: 0 auto, 1 one CTA, 2 one launch per sweep
+    OPT_FAS_CGS_GLOBAL,  // EVO_FAS_CGS_GLOBAL  FAS coarse solver without shared memory
+    OPT_LEX_VARIANT,     // EVO_LEX_VARIANT     lexicographic sweeps: 0 cluster wavefront, 1 single CTA
+    OPT_STAR2D,          // EVO_STAR2D          0 = generic 2-D kernels only (no specialised 5-point path)
+    OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     0 = one launch per statement on the coarse levels
+    OPT_COUNT
+};
+struct OptionTable {
+    int value[OPT_COUNT];
+    bool init[OPT_COUNT];
+};
+inline const char *option_name(int id)
+{
+    static const char *names[OPT_COUNT] = {"EVO_RB_VARIANT", "EVO_RB_FUSE2", "EVO_RR_VARIANT", "EVO_NO_PINGPONG", "EVO_CG_GLOBAL",
+                                           "EVO_CG_NOREG", "EVO_ROWSEQ_GLOBAL", "EVO_ROWSEQ_NOPIPE", "EVO_FAS_CGS",
+                                           "EVO_FAS_CGS_GLOBAL", "EVO_LEX_VARIANT", "EVO_STAR2D", "EVO_COARSE_FUSE"};
+    return names[id];
+}
+inline OptionTable &option_table()
+{
+    static OptionTable t = {};
+    return t;
+}
+inline int option_default(int id) { return (id == OPT_STAR2D || id == OPT_COARSE_FUSE) ? 1 : 0; }
+inline int option(int id)
+{
+    OptionTable &t = option_table();
+    if (!t.init[id]) {
+        const char *e = getenv(option_name(id));
+        // a variable that is set but empty / not a number counts as 1 (the historical "is it set" switches)
+        t.value[id] = e ? ((*e >= '0' && *e <= '9') || *e == '-' ? atoi(e) : 1) : option_default(id);
+        t.init[id] = true;
+    }
+    return t.value[id];
+}
 
 // ---------------------------------------------------------------------------------------------
 // complex fp64 as one 16-byte word (double2): one Helmholtz unknown per LDG.128/STG.128

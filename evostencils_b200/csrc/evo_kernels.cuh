@@ -97,8 +97,19 @@ struct SolveState {
     int it;           // iterations done
     int done;         // 1 = converged / cap / non-finite
     int bad;          // non-finite residual seen
+    int cap;          // > 0: stop after this many iterations (solo re-timing of a batch member); 0 = no extra cap
+    unsigned long long t_start;     // %globaltimer at the initial residual
+    unsigned long long timeout_ns;  // > 0: watchdog, checked after every iteration
+    int timed_out;
     int pad;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // |r|^2 row sums of every field: one warp per row; rows[(field * nzi + (z - z0)) * ni + (y - 1)]
 template <typename T, int DIM, int NF>
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(128) k_row_sumsq(const Geom g, Fields<T> r, do
 
 // canonical reduction, second and third level: row sums -> plane sums (3-D: one warp per plane, many
 // blocks) -> field sums -> total (one warp)
-__global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int count /* fields * planes */, int ni, double *planes)
+static __global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int count /* fields * planes */, int ni, double *planes)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long id = (long long)blockIdx.x * 8 + warp;   // (field, plane)
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(256) k_reduce_planes(const double *rows, int c
 }
 
 // vals: per field `m` partial sums (plane sums in 3-D, row sums in 2-D)
-__global__ void __launch_bounds__(32) k_reduce_final(const double *vals, int nf, int m, SolveState *st)
+static __global__ void __launch_bounds__(32) k_reduce_final(const double *vals, int nf, int m, SolveState *st)
 {
     double total = 0.0;
     for (int i = 0; i < nf; ++i) total = total + warp_vecsum(vals + (long long)i * m, m);
@@ -137,12 +148,13 @@ __global__ void __launch_bounds__(32) k_reduce_final(const double *vals, int nf,
 
 // bookkeeping of the outer loop: `until res < tol*res0 or it >= maxIts`
 // (example_problems/Poisson/2D_FD_Poisson_fromL2.exa3:3-4); mode 0 = initial residual, 1 = after a cycle
-__global__ void k_outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
+static __global__ void k_outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double res = sqrt(st->sum);
     if (mode == 0) {
-        st->res0 = res; st->res_prev = res; st->res = res; st->it = 0; st->bad = 0;
+        st->res0 = res; st->res_prev = res; st->res = res; st->it = 0; st->bad = 0; st->timed_out = 0;
+        st->t_start = global_timer_ns();
         hist[0] = res;
         st->done = (max_iters <= 0) ? 1 : 0;
         if (!isfinite(res)) { st->bad = 1; st->done = 1; }
@@ -154,7 +166,8 @@ __global__ void k_outer_update(SolveState *st, double *hist, double tol, int max
     st->res_prev = st->res;
     st->res = res;
     if (!isfinite(res)) { st->bad = 1; st->done = 1; }
-    else if (res < tol * st->res0 || st->it >= max_iters) st->done = 1;
+    else if (res < tol * st->res0 || st->it >= max_iters || (st->cap > 0 && st->it >= st->cap)) st->done = 1;
+    else if (st->timeout_ns && global_timer_ns() - st->t_start > st->timeout_ns) { st->timed_out = 1; st->done = 1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -357,6 +370,68 @@ __global__ void __launch_bounds__(1024) k_smooth_rowseq(const Geom g, const __gr
                 __syncthreads();
             }
     }
+}
+
+// Lexicographic in-place sweep (`solve locally` without `with jacobi` and without colouring: what the reference
+// emits in model-based mode, exastencils.py:64-70, :781-822 with _use_jacobi_prefix = False).  The reference loop
+// is sequential, i0 fastest; anchors P < Q conflict when one writes what the other reads or writes.  With the skew
+// t = x + a*y + b*z (a, b from lex_skew(): every conflicting pair has t(P) < t(Q)) all anchors of one hyperplane t
+// are independent, and sweeping the hyperplanes in ascending t reproduces the sequential result exactly (block
+// smoothers with overlapping writes included).  One thread-block cluster runs the whole sweep: CTAs share a
+// hyperplane, a cluster barrier separates hyperplanes.  Latency bound by construction (as the statement is).
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }   // b > 0
+__device__ __forceinline__ int ceil_div(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }  // b > 0
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+template <typename T, int DIM, int NF, int NU>
+__global__ void __launch_bounds__(1024) k_smooth_lex(const Geom g, const __grid_constant__ OpSten st,
+                                                     const __grid_constant__ SmoothParams sp, Fields<T> u, Fields<T> rhs,
+                                                     const int a, const int b, const int sweeps)
+{
+    const int ni = g.n - 2;
+    const int nthreads = (int)(cluster_nctarank() * blockDim.x), gtid = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+    const int nwarps = nthreads >> 5, gw = gtid >> 5, lane = gtid & 31;
+    const int tmin = 1 + a + (DIM == 3 ? b : 0), tmax = ni * (1 + a + (DIM == 3 ? b : 0));
+    for (int sweep = 0; sweep < sweeps; ++sweep)
+        for (int t = tmin; t <= tmax; ++t) {
+            if (DIM == 2) {
+                // x = t - a*y in [1, ni]
+                int ylo = 1, yhi = ni;
+                if (a > 0) { ylo = max(1, ceil_div(t - ni, a)); yhi = min(ni, floor_div(t - 1, a)); }
+                else if (t > ni) { ylo = 1; yhi = 0; }
+                for (int y = ylo + gtid; y <= yhi; y += nthreads) local_solve<T, DIM, NF, NU>(g, st, sp, u, u, rhs, t - a * y, y, 0);
+            } else {
+                // x + a*y = t - b*z in [1 + a, ni*(1 + a)]
+                int zlo = 1, zhi = ni;
+                if (b > 0) { zlo = max(1, ceil_div(t - ni * (1 + a), b)); zhi = min(ni, floor_div(t - 1 - a, b)); }
+                else if (t > ni * (1 + a)) { zlo = 1; zhi = 0; }
+                for (int z = zlo + gw; z <= zhi; z += nwarps) {
+                    const int rem = t - b * z;
+                    int ylo = 1, yhi = ni;
+                    if (a > 0) { ylo = max(1, ceil_div(rem - ni, a)); yhi = min(ni, floor_div(rem - 1, a)); }
+                    else if (rem < 1 || rem > ni) { ylo = 1; yhi = 0; }
+                    for (int y = ylo + lane; y <= yhi; y += 32) local_solve<T, DIM, NF, NU>(g, st, sp, u, u, rhs, rem - a * y, y, z);
+                }
+            }
+            cluster_barrier();
+        }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,7 +61,7 @@ __device__ __forceinline__ double fas_point(const Geom &g, const Lin2 &L, double
 }
 
 // color < 0: Jacobi sweep src -> dst; color 0/1: one colour of the in-place red-black sweep
-__global__ void __launch_bounds__(BX) k2_fas_smooth(const Geom g, const __grid_constant__ Lin2 L, double gamma,
+static __global__ void __launch_bounds__(BX) k2_fas_smooth(const Geom g, const __grid_constant__ Lin2 L, double gamma,
                                                     const double *__restrict__ src, double *dst, const double *__restrict__ f,
                                                     int newton, int steps, double w, int color)
 {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(BX) k2_fas_smooth(const Geom g, const __grid_c
     dst[idx] = fas_point(g, L, gamma, src, f[idx], idx, newton != 0, steps, w);
 }
 
-__global__ void __launch_bounds__(BX) k2_fas_residual(const Geom g, const __grid_constant__ Lin2 L, double gamma,
+static __global__ void __launch_bounds__(BX) k2_fas_residual(const Geom g, const __grid_constant__ Lin2 L, double gamma,
                                                       const double *__restrict__ u, const double *__restrict__ f,
                                                       double *__restrict__ r)
 {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BX) k2_fas_residual(const Geom g, const __grid
 }
 
 // RHS_c += (A + N)(APX_c)   (second half of  RHS@(l-1) = R * Residual@l + (A + N)(Approximation@(l-1)))
-__global__ void __launch_bounds__(BX) k2_fas_add_operator(const Geom g, const __grid_constant__ Lin2 L, double gamma,
+static __global__ void __launch_bounds__(BX) k2_fas_add_operator(const Geom g, const __grid_constant__ Lin2 L, double gamma,
                                                           const double *__restrict__ apx, double *__restrict__ rhs)
 {
     const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(BX) k2_fas_add_operator(const Geom g, const __
 }
 
 // SOL -= APX on the whole padded array (both carry identical boundary values)
-__global__ void k_sub_inplace(double *__restrict__ a, const double *__restrict__ b, long long n)
+static __global__ void k_sub_inplace(double *__restrict__ a, const double *__restrict__ b, long long n)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         a[i] = a[i] - b[i];
@@ -102,7 +102,7 @@ __global__ void k_sub_inplace(double *__restrict__ a, const double *__restrict__
 
 // CGS@coarsest: `sweeps` damped Newton-Jacobi sweeps in ONE CTA (the coarsest grid is latency bound;
 // 200 separate launches would cost ~1 ms); ping-pong between the two SOL slots, result ends in `a`
-__global__ void __launch_bounds__(1024) k2_fas_coarse(const Geom g, const __grid_constant__ Lin2 L, double gamma,
+static __global__ void __launch_bounds__(1024) k2_fas_coarse(const Geom g, const __grid_constant__ Lin2 L, double gamma,
                                                       double *a, double *b, const double *__restrict__ f, int sweeps, double w)
 {
     const int ni = g.n - 2;

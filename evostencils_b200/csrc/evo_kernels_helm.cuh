@@ -13,7 +13,8 @@ struct HelmState {
     cplx alpha, beta, rho, rho_new, omega;
     cplx dot[4];
     double init, cur;
-    int it, done, bad, pad;
+    int it, done, bad, timed_out;
+    unsigned long long t_start, timeout_ns;   // watchdog (see SolveState)
 };
 
 // u_b = u_neighbour * rden on x = 0 and x = n-1 (rows 1..n-2), 0 on the rows y = 0 and y = n-1 (corners end 0)
@@ -28,13 +29,13 @@ __device__ __forceinline__ void bc_node_rows(const Geom &g, cplx *u, cplx rden, 
         u[(long long)t * g.pitch + n - 1] = u[(long long)t * g.pitch + n - 2] * rden;
     }
 }
-__global__ void k2_helm_bc(const Geom g, cplx *u, cplx rden)
+static __global__ void k2_helm_bc(const Geom g, cplx *u, cplx rden)
 {
     bc_node_rows(g, u, rden, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // canonical unconjugated complex dot over inner nodes: rows[(y-1)] per warp, then one warp
-__global__ void __launch_bounds__(128) k2_cdot_rows(const Geom g, const cplx *a, const cplx *b, cplx *rows)
+static __global__ void __launch_bounds__(128) k2_cdot_rows(const Geom g, const cplx *a, const cplx *b, cplx *rows)
 {
     const int ni = g.n - 2;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(128) k2_cdot_rows(const Geom g, const cplx *a,
     cplx s = warp_row_dot<cplx, cplx>(a, b, (long long)(row + 1) * g.pitch + 1, ni);
     if ((threadIdx.x & 31) == 0) rows[row] = s;
 }
-__global__ void __launch_bounds__(32) k2_cdot_final(const cplx *rows, int ni, HelmState *st, int slot)
+static __global__ void __launch_bounds__(32) k2_cdot_final(const cplx *rows, int ni, HelmState *st, int slot)
 {
     cplx s = warp_vecsum(rows, ni);
     if (threadIdx.x == 0) st->dot[slot] = s;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(32) k2_cdot_final(const cplx *rows, int ni, He
 __device__ __forceinline__ double abs_sqrt(cplx z) { return sqrt(sqrt(z.re * z.re + z.im * z.im)); }  // |sqrt(z)|
 
 // scalar recurrences of the outer iteration; stage: 0 = init, 1 = beta, 2 = alpha, 3 = omega, 4 = convergence
-__global__ void k_helm_scalar(HelmState *st, double *hist, double tol, int max_iters, int stage)
+static __global__ void k_helm_scalar(HelmState *st, double *hist, double tol, int max_iters, int stage)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (stage == 0) {
@@ -59,7 +60,8 @@ __global__ void k_helm_scalar(HelmState *st, double *hist, double tol, int max_i
         st->cur = st->init;
         hist[0] = st->init;
         st->alpha = cplx(1.0); st->beta = cplx(1.0); st->rho_new = cplx(1.0); st->omega = cplx(1.0);
-        st->it = 0; st->bad = 0;
+        st->it = 0; st->bad = 0; st->timed_out = 0;
+        st->t_start = global_timer_ns();
         st->done = (st->init == 0.0 || max_iters <= 0) ? 1 : 0;
         if (!isfinite(st->init)) { st->bad = 1; st->done = 1; }
     } else if (stage == 1) {
@@ -77,13 +79,14 @@ __global__ void k_helm_scalar(HelmState *st, double *hist, double tol, int max_i
         hist[st->it] = st->cur;
         if (!isfinite(st->cur)) { st->bad = 1; st->done = 1; }
         else if (st->cur < tol * st->init || st->it >= max_iters) st->done = 1;
+        else if (st->timeout_ns && global_timer_ns() - st->t_start > st->timeout_ns) { st->timed_out = 1; st->done = 1; }
     }
 }
 
 // mode 0: p = r + beta (p - omega ap)        mode 1: h = x + alpha u ; s = r - alpha ap
 // mode 2: x = h + omega u                    mode 3: r = s - omega t
 // mode 4: dst = src (inner nodes)
-__global__ void __launch_bounds__(BX) k2_helm_vec(const Geom g, int mode, const HelmState *st, cplx *a, cplx *b,
+static __global__ void __launch_bounds__(BX) k2_helm_vec(const Geom g, int mode, const HelmState *st, cplx *a, cplx *b,
                                                   const cplx *c, const cplx *d, const cplx *e, const cplx *f)
 {
     const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(BX) k2_helm_vec(const Geom g, int mode, const 
 }
 
 // out = A * u on inner nodes (A = un-shifted operator of the finest level)
-__global__ void __launch_bounds__(BX) k2_apply_op(const Geom g, const __grid_constant__ OpSten st, const cplx *u, cplx *out,
+static __global__ void __launch_bounds__(BX) k2_apply_op(const Geom g, const __grid_constant__ OpSten st, const cplx *u, cplx *out,
                                                   const cplx *minus_from /* nullable: out = minus_from - A u */)
 {
     const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y;
@@ -109,14 +112,14 @@ __global__ void __launch_bounds__(BX) k2_apply_op(const Geom g, const __grid_con
     out[i] = minus_from ? minus_from[i] - acc : acc;
 }
 
-__global__ void k_set_while_condition_helm(cudaGraphConditionalHandle handle, const HelmState *st)
+static __global__ void k_set_while_condition_helm(cudaGraphConditionalHandle handle, const HelmState *st)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) cudaGraphSetConditional(handle, st->done ? 0u : 1u);
 }
 
 // gen_mgCycle@coarsest: BiCGStab on M, zero initial guess, one CTA (exa3:396-433).  Vectors in global memory
 // (the coarsest Helmholtz grid is 9 x 9); boundary function on x, r, p, s like the oracle.
-__global__ void __launch_bounds__(1024) k2_coarse_bicgstab(const Geom g, const __grid_constant__ OpSten st, cplx rden, cplx *x,
+static __global__ void __launch_bounds__(1024) k2_coarse_bicgstab(const Geom g, const __grid_constant__ OpSten st, cplx rden, cplx *x,
                                                            const cplx *b, cplx *r, cplx *rh, cplx *p, cplx *nu, cplx *s, cplx *t,
                                                            cplx *hh, cplx *rows, int max_it, double tol, int robin)
 {

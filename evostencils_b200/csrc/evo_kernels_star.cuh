@@ -582,6 +582,11 @@ static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, cons
     return cudaGetLastError() == cudaSuccess;
 }
 
+// register-carried pair-column kernel (evo_kernels_rbcol.cuh)
+template <int TY, bool RC, int MINB>
+static bool launch_rbgs_col(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout, double omega,
+                            cudaStream_t s);
+
 // k pointwise RB-GS sweeps, out of place (u -> uout); returns false if not applicable
 template <typename T, int DIM, int NF>
 static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Fields<T> u, Fields<T> f, Fields<T> uout,
@@ -590,8 +595,7 @@ static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Field
     if constexpr (std::is_same<T, double>::value && DIM == 3 && NF == 1) {
         Star7 c;
         if (g.n < 33 || !match_star7(st.s[0][0], &c)) return false;
-        static int variant = -1;   // EVO_RB_VARIANT: tile-shape experiments (0 = default)
-        if (variant < 0) { const char *e = getenv("EVO_RB_VARIANT"); variant = e ? atoi(e) : 0; }
+        const int variant = option(OPT_RB_VARIANT);   // tile-shape / kernel experiments (0 = default)
         const double *up = u.p[0], *fp = f.p[0];
         double *op = uout.p[0];
         if (sweeps == 1) {
@@ -607,6 +611,12 @@ static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Field
             if (variant == 12) return launch_rbgs_lean<32, 256>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 13) return launch_rbgs_lean<16, 512>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 14) return launch_rbgs_lean<8, 128>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 30) return launch_rbgs_col<8, false, 3>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 31) return launch_rbgs_col<16, false, 1>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 32) return launch_rbgs_col<8, true, 2>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 33) return launch_rbgs_col<16, true, 1>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 34) return launch_rbgs_col<8, false, 2>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 35) return launch_rbgs_col<8, true, 3>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 20) return launch_rbgs_stream<2, 8, 256>(sm_count, g, c, up, fp, op, omega, s);   // generic multi-stage kernel: 65-68 %
             return launch_rbgs_lean<8, 256>(sm_count, g, c, up, fp, op, omega, s);   // best measured: 73 % of HBM peak
         }
@@ -700,7 +710,7 @@ __global__ void __launch_bounds__(256) k3_residual_rows(const Geom g, const Star
 // 3-D pointwise weighted Jacobi sweep (`solve locally ... with jacobi`), same row mapping: reads the
 // current slot, writes the next slot; per node s = sum of the off-diagonal terms in table order,
 // x = (f - s) * (1/a), u_new = u + w (x - u)
-__global__ void __launch_bounds__(256) k3_jacobi_rows(const Geom g, const Star7 c, const double inv_c, const double omega,
+static __global__ void __launch_bounds__(256) k3_jacobi_rows(const Geom g, const Star7 c, const double inv_c, const double omega,
                                                       const double *__restrict__ u, const double *__restrict__ f,
                                                       double *__restrict__ unew)
 {
@@ -775,7 +785,7 @@ __device__ __forceinline__ double prolong_node(const DenseW &P, const double (&e
     return acc;
 }
 
-__global__ void __launch_bounds__(128) k3_prolong_add(const Geom gf, const Geom gc, const DenseW P,
+static __global__ void __launch_bounds__(128) k3_prolong_add(const Geom gf, const Geom gc, const DenseW P,
                                                       const double *__restrict__ ec, double *__restrict__ u,
                                                       const double weight, const int zc0)
 {
@@ -1092,11 +1102,7 @@ static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, 
         if (gf.n < 33 || R.nnz != 27 || !match_star7(st.s[0][0], &c) || get_encode_tiled() == nullptr) return false;
         DenseW W;
         for (int q = 0; q < 27; ++q) W.w[(R.oz[q] + 1) * 9 + (R.oy[q] + 1) * 3 + (R.ox[q] + 1)] = R.w[q];
-        static int variant = -1;
-        if (variant < 0) {
-            const char *e = getenv("EVO_RR_VARIANT");
-            variant = e ? atoi(e) : 0;
-        }
+        const int variant = option(OPT_RR_VARIANT);
         switch (variant) {
         case 1: return launch_residual_restrict<2, 64>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);
         case 2: return launch_residual_restrict<4, 64>(sm_count, gf, gc, c, W, u.p[0], f.p[0], dst.p[0], s);

@@ -6,21 +6,7 @@
 //                     WHILE conditional node (the generated solver's outer loop runs on the device)
 //   evo_cycle_solve : one graph launch per sample, CUDA-event timed, residual history read back
 // No CPU fallback exists: without a CUDA device evo_problem_create fails with EVO_ERR_NO_DEVICE.
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "evo_kernels.cuh"
-#include "evo_kernels_star.cuh"
-#include "evo_kernels_fas.cuh"
-#include "evo_kernels_helm.cuh"
-
-using namespace evo;
+#include "evo_runtime_internal.cuh"
 
 // Many individuals are evaluated concurrently, one stream each: the default of 8 hardware work queues
 // would serialise unrelated streams, so ask for the maximum before the CUDA context is created.
@@ -32,7 +18,7 @@ struct EnvInit {
 
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...)
+int fail(int code, const char *fmt, ...)
 {
     char buf[1024];
     va_list ap;
@@ -42,18 +28,9 @@ static int fail(int code, const char *fmt, ...)
     g_err = buf;
     return code;
 }
-#define CU(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess)                                                                         \
-            return fail(e_ == cudaErrorMemoryAllocation ? EVO_ERR_OOM : EVO_ERR_CUDA, "%s: %s (%s:%d)", #call, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
-    } while (0)
-#define EV(call)                     \
-    do {                             \
-        int rc_ = (call);            \
-        if (rc_ != EVO_OK) return rc_; \
-    } while (0)
+
+// every live problem, so that an allocation failure can reclaim the recycled work slabs of all of them
+static std::vector<evo_problem *> g_problems;
 
 static Geom make_geom(int level, int dim)
 {
@@ -87,92 +64,30 @@ static TransferW make_transfer(const double *w, int dim)
 }
 
 // ------------------------------------------------------------------------------------------------
-struct evo_problem {
-    evo_problem_desc desc;
-    int words;
-    int sm_count;
-    Geom geom[EVO_MAX_LEVELS];
-    TransferW R, P;
-    void *init_sol[EVO_MAX_FIELDS];  // pristine finest-level SOL (incl. boundary values), padded layout
-    void *rhs0[EVO_MAX_FIELDS];      // finest-level RHS, read-only, shared by all cycles
-    std::vector<std::pair<void *, size_t>> pool;  // recycled cycle work slabs
-    int slab_world = 1, slab_rank = 0, slab_lc = 0;  // domain decomposition (slab_lc = 0: none)
-    int own_g0[EVO_MAX_LEVELS], own_g1[EVO_MAX_LEVELS];   // owned global plane range per distributed level
-    struct CycleRes { cudaStream_t stream; cudaEvent_t ev0, ev1; SolveState *h_state; double *h_hist, *d_hist; int hist_cap; };
-    std::vector<CycleRes> res_pool;               // streams / events / pinned buffers of destroyed cycles, recycled
-    int live_cycles = 0;                          // cycles still referring to this problem
-    bool closed = false;                          // evo_problem_destroy called while cycles were alive
-};
-
-struct LevelMem {
-    void *buf[EVO_BUF_COUNT][EVO_MAX_FIELDS];
-    void *slot[EVO_MAX_FIELDS];  // [next] slot of SOL for `with jacobi` statements
-    bool swapped[EVO_MAX_FIELDS];
-};
-
-struct evo_cycle {
-    evo_problem *p;
-    std::vector<evo_op> ops;
-    OpSten sten[EVO_MAX_LEVELS];
-    bool has_sten[EVO_MAX_LEVELS];
-    LevelMem lv[EVO_MAX_LEVELS];
-    void *slab;
-    size_t slab_bytes;
-    void *krylov[8][EVO_MAX_FIELDS];  // coarsest-level Krylov vectors
-    void *scratch[EVO_MAX_FIELDS];    // finest-level scratch field (Richardson)
-    void *helm[9];                    // Helmholtz outer solver: x, r, p, ap, s, t, h, rhat, row sums
-    helm::HelmState *d_helm;
-    OpSten helm_A;                    // un-shifted operator of the finest level
-    cudaGraph_t helm_graph;
-    cudaGraphExec_t helm_exec;
-    double helm_tol;
-    int helm_max_iters;
-    SolveState *d_state;
-    double *d_hist;
-    int hist_cap;
-    double *d_partials;
-    int n_partials;
-    int *d_cg_iters;
-    SolveState *h_state;  // pinned
-    double *h_hist;       // pinned
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    // captured solver graph (valid for one (tol, max_iters))
-    cudaGraph_t graph;
-    cudaGraphExec_t exec;
-    double graph_tol;
-    int graph_max_iters;
-    int64_t kernels_per_cycle, kernels_prologue;
-    int64_t launch_counter;  // counts kernel launches while enqueueing
-    bool use_while_graph;
-    bool pingpong = false;                               // the WHILE body holds two cycles (see build_solver_graph)
-    bool odd_swap[EVO_MAX_LEVELS][EVO_MAX_FIELDS] = {};  // levels whose SOL ends in the [next] slot after one cycle
-    bool pristine = false;       // freshly reset: evo_cycle_solve need not reset again
-    bool part_no_swap = false;   // partial execution of an out-of-place statement: leave SOL / [next] unexchanged
-    int zc_lo = -1, zc_hi = -1;  // plane range override of the statement's destination level (domain decomposition)
-    bool own_stream = true;
-    bool res_dead_on_entry;  // the cycle overwrites RES@finest before reading it: the solver's own residual
-                             // (convergence test) need not be stored
-};
-
-template <typename T> static Fields<T> fields_of(void *const *p, int nf)
-{
-    Fields<T> f;
-    for (int i = 0; i < EVO_MAX_FIELDS; ++i) f.p[i] = i < nf ? (T *)p[i] : nullptr;
-    return f;
-}
-
-static dim3 row_grid(const Geom &g, int per_thread = 1)
-{
-    int inner = g.n - 2;
-    int threads = (inner + per_thread - 1) / per_thread;
-    return dim3((threads + BX - 1) / BX, inner, g.dim == 3 ? g.zhi - g.zlo + 1 : 1);
-}
-
-// ------------------------------------------------------------------------------------------------
 // library
 extern "C" int evo_abi_version(void) { return EVO_ABI_VERSION; }
 extern "C" const char *evo_last_error(void) { return g_err.c_str(); }
+
+// tuning switches: `name` is the environment-variable name (EVO_RB_VARIANT, EVO_RB_FUSE2, ...)
+extern "C" int evo_set_option(const char *name, int value)
+{
+    if (!name) return fail(EVO_ERR_INVALID, "null argument");
+    for (int id = 0; id < OPT_COUNT; ++id)
+        if (strcmp(name, option_name(id)) == 0) {
+            option_table().value[id] = value;
+            option_table().init[id] = true;
+            return EVO_OK;
+        }
+    return fail(EVO_ERR_INVALID, "unknown option %s", name);
+}
+
+extern "C" int evo_get_option(const char *name, int *value)
+{
+    if (!name || !value) return fail(EVO_ERR_INVALID, "null argument");
+    for (int id = 0; id < OPT_COUNT; ++id)
+        if (strcmp(name, option_name(id)) == 0) { *value = option(id); return EVO_OK; }
+    return fail(EVO_ERR_INVALID, "unknown option %s", name);
+}
 
 extern "C" int evo_device_count(void)
 {
@@ -227,6 +142,10 @@ extern "C" int evo_problem_create(const evo_problem_desc *d, evo_problem **out)
         CU(cudaMemset(p->init_sol[i], 0, bytes));
         CU(cudaMemset(p->rhs0[i], 0, bytes));
     }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { total_b = (size_t)64 << 30; cudaGetLastError(); }
+    p->device_bytes = total_b;
+    g_problems.push_back(p);
     *out = p;
     return EVO_OK;
 }
@@ -243,6 +162,7 @@ extern "C" int evo_problem_destroy(evo_problem *p)
 
 static void free_problem(evo_problem *p)
 {
+    g_problems.erase(std::remove(g_problems.begin(), g_problems.end(), p), g_problems.end());
     cudaSetDevice(p->desc.device);
     for (int i = 0; i < EVO_MAX_FIELDS; ++i) { cudaFree(p->init_sol[i]); cudaFree(p->rhs0[i]); }
     for (auto &s : p->pool) cudaFree(s.first);
@@ -254,8 +174,6 @@ static void free_problem(evo_problem *p)
     }
     delete p;
 }
-
-static bool slab_level(const evo_problem *p, int level) { return p->slab_lc > 0 && level >= p->slab_lc; }
 
 extern "C" int evo_problem_set_slab(evo_problem *p, int rank, int world, int lc)
 {
@@ -368,6 +286,15 @@ static bool uses_buffer(const evo_cycle *c, int level, int buf)
     return false;
 }
 
+static void release_pools(int device)
+{
+    for (evo_problem *q : g_problems) {
+        if (q->desc.device != device) continue;
+        for (auto &sl : q->pool) cudaFree(sl.first);
+        q->pool.clear();
+    }
+}
+
 static int allocate_cycle(evo_cycle *c)
 {
     evo_problem *p = c->p;
@@ -412,14 +339,35 @@ static int allocate_cycle(evo_cycle *c)
         c->d_partials = (double *)take(sizeof(double) * ((size_t)c->n_partials + (size_t)nf * gf.n));
         if (pass == 0) {
             c->slab_bytes = off;
+            c->slab_cap = off;
             c->slab = nullptr;
+            // best fit among the recycled slabs: the smallest one that is large enough and wastes at most 25 %
+            size_t best = (size_t)-1;
             for (size_t k = 0; k < p->pool.size(); ++k)
-                if (p->pool[k].second == off) {
-                    c->slab = p->pool[k].first;
-                    p->pool.erase(p->pool.begin() + k);
-                    break;
+                if (p->pool[k].second >= off && p->pool[k].second <= off + off / 4 &&
+                    (best == (size_t)-1 || p->pool[k].second < p->pool[best].second))
+                    best = k;
+            if (best != (size_t)-1) {
+                c->slab = p->pool[best].first;
+                c->slab_cap = p->pool[best].second;
+                p->pool.erase(p->pool.begin() + best);
+            }
+            if (!c->slab) {
+                cudaError_t e = cudaMalloc(&c->slab, off);
+                if (e == cudaErrorMemoryAllocation) {
+                    // idle slabs of other sizes may hold the memory: give every pool on this device back and retry
+                    cudaGetLastError();
+                    c->slab = nullptr;
+                    release_pools(p->desc.device);
+                    e = cudaMalloc(&c->slab, off);
                 }
-            if (!c->slab) CU(cudaMalloc(&c->slab, off));
+                if (e != cudaSuccess) {
+                    c->slab = nullptr;
+                    cudaGetLastError();
+                    return fail(e == cudaErrorMemoryAllocation ? EVO_ERR_OOM : EVO_ERR_CUDA, "cudaMalloc of a %zu-byte work slab: %s", off,
+                                cudaGetErrorString(e));
+                }
+            }
         }
     }
     return EVO_OK;
@@ -454,398 +402,17 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
     return EVO_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// cycle: op dispatch (every function only enqueues work on `s`; safe under stream capture)
-template <typename T, int DIM, int NF> struct Launch {
-    // d_partials holds the canonical row sums [NF][nzi][ni]; reduce them to SolveState::sum
-    static int reduce_rows(evo_cycle *c, int ni, cudaStream_t s)
-    {
-        if (DIM == 3) {
-            double *planes = c->d_partials + (size_t)NF * ni * ni;
-            k_reduce_planes<<<(unsigned)((NF * ni + 7) / 8), 256, 0, s>>>(c->d_partials, NF * ni, ni, planes);
-            k_reduce_final<<<1, 32, 0, s>>>(planes, NF, ni, c->d_state);
-            c->launch_counter += 2;
-        } else {
-            k_reduce_final<<<1, 32, 0, s>>>(c->d_partials, NF, ni, c->d_state);
-            c->launch_counter += 1;
-        }
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    static int residual(evo_cycle *c, int l, bool norm, cudaStream_t s)
-    {
-        Geom g = c->p->geom[l];
-        if (c->zc_lo >= 0 && !norm) { g.zlo = c->zc_lo; g.zhi = c->zc_hi; }   // domain decomposition: include ghost planes
-        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
-             r = fields_of<T>(c->lv[l].buf[EVO_BUF_RES], NF);
-        const int ni = g.n - 2;
-        if (norm && star::try_residual_norm<T, DIM, NF>(g, c->sten[l], u, f, r, c->d_partials, !c->res_dead_on_entry, s)) {
-            // residual and canonical row sums in one pass; the field itself is only stored if a later
-            // statement may read it
-            c->launch_counter += 1;
-            EV(reduce_rows(c, ni, s));
-            return EVO_OK;
-        }
-        if (!star::try_residual<T, DIM, NF>(c->p->sm_count, g, c->sten[l], u, f, r, s)) {
-            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: residual needs the 7-point fast path");
-            k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
-        }
-        c->launch_counter++;
-        if (norm) {
-            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: use evo_cycle_residual_plane_sums");
-            const long long nrows = (long long)ni * (DIM == 3 ? ni : 1);
-            k_row_sumsq<T, DIM, NF><<<(unsigned)((nrows + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
-            c->launch_counter += 1;
-            EV(reduce_rows(c, ni, s));
-        }
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    template <int NU> static int smooth_nu(evo_cycle *c, const evo_op &op, cudaStream_t s)
-    {
-        const int l = op.level;
-        const Geom &g = c->p->geom[l];
-        SmoothParams sp;
-        memset(&sp, 0, sizeof(sp));
-        sp.nu = NU;
-        sp.omega = op.omega;
-        sp.write_all = 0;
-        bool has_own[EVO_MAX_FIELDS] = {false, false}, written[EVO_MAX_FIELDS] = {false, false};
-        for (int a = 0; a < NU; ++a) {
-            sp.field[a] = op.unk_field[a];
-            if (sp.field[a] < 0 || sp.field[a] >= NF) return fail(EVO_ERR_INVALID, "unknown refers to field %d", sp.field[a]);
-            for (int d = 0; d < 3; ++d) sp.off[a][d] = d < DIM ? op.unk_off[a][d] : 0;
-            written[sp.field[a]] = true;
-            if (sp.off[a][0] == 0 && sp.off[a][1] == 0 && sp.off[a][2] == 0) has_own[sp.field[a]] = true;
-        }
-        for (int i = 0; i < NF; ++i)
-            if (written[i] && !has_own[i])
-                return fail(EVO_ERR_UNSUPPORTED, "local system without an unknown at the anchor node for field %d", i);
-        auto rhs = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
-        int reps = op.count > 1 ? op.count : 1;
-        Geom gsub = g;   // domain decomposition: a sub-range of the owned planes (boundary planes first, interior later)
-        if (c->zc_lo >= 0 && slab_level(c->p, l)) { gsub.zlo = c->zc_lo; gsub.zhi = c->zc_hi; }
-        if (NU == 1 && op.mode == EVO_SMOOTH_REDBLACK && c->lv[l].slot[0] && star::rbgs_stream_applicable<T, DIM, NF>(g, c->sten[l])) {
-            // fused streaming kernel: up to 2 sweeps per pass, out of place into the [next] slot
-            while (reps > 0) {
-                // one launch per sweep: the 2-sweep variant (S = 4) is currently slower than two S = 2 launches
-                static const bool fuse2 = getenv("EVO_RB_FUSE2") != nullptr;
-                const int k = (fuse2 && reps >= 2) ? 2 : 1;
-                auto src = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), dst = fields_of<T>(c->lv[l].slot, NF);
-                if (!star::try_rbgs_stream<T, DIM, NF>(c->p->sm_count, gsub, c->sten[l], src, rhs, dst, op.omega, k, s)) break;
-                c->launch_counter++;
-                if (c->part_no_swap) { reps -= k; continue; }
-                bool cor_alias = c->lv[l].buf[EVO_BUF_COR][0] == c->lv[l].buf[EVO_BUF_SOL][0];
-                std::swap(c->lv[l].buf[EVO_BUF_SOL][0], c->lv[l].slot[0]);
-                if (cor_alias) c->lv[l].buf[EVO_BUF_COR][0] = c->lv[l].buf[EVO_BUF_SOL][0];
-                c->lv[l].swapped[0] = !c->lv[l].swapped[0];
-                reps -= k;
-            }
-            if (reps == 0) { CU(cudaGetLastError()); return EVO_OK; }
-        }
-        if (slab_level(c->p, l) && !(NU == 1 && op.mode == EVO_SMOOTH_JACOBI))
-            return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: only pointwise RB-GS / Jacobi on 7-point stencils");
-        for (int rep = 0; rep < reps; ++rep) {
-            if (op.mode == EVO_SMOOTH_JACOBI) {
-                // read the current slot, write the next slot, then `advance` (swap) the written fields
-                void *cur[EVO_MAX_FIELDS], *nxt[EVO_MAX_FIELDS];
-                for (int i = 0; i < NF; ++i) {
-                    cur[i] = c->lv[l].buf[EVO_BUF_SOL][i];
-                    nxt[i] = written[i] ? c->lv[l].slot[i] : cur[i];
-                    if (written[i] && !nxt[i]) return fail(EVO_ERR_INVALID, "missing jacobi slot");
-                }
-                sp.color = -1;
-                auto src = fields_of<T>(cur, NF), dst = fields_of<T>(nxt, NF);
-                if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, gsub, c->sten[l], sp, src, dst, rhs, s))) {
-                    if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: Jacobi needs the 7-point fast path");
-                    k_smooth<T, DIM, NF, NU><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], sp, src, dst, rhs);
-                }
-                c->launch_counter++;
-                for (int i = 0; i < NF; ++i)
-                    if (written[i] && !c->part_no_swap) {
-                        bool cor_alias = c->lv[l].buf[EVO_BUF_COR][i] == c->lv[l].buf[EVO_BUF_SOL][i];
-                        std::swap(c->lv[l].buf[EVO_BUF_SOL][i], c->lv[l].slot[i]);
-                        c->lv[l].swapped[i] = !c->lv[l].swapped[i];
-                        if (cor_alias) c->lv[l].buf[EVO_BUF_COR][i] = c->lv[l].buf[EVO_BUF_SOL][i];
-                    }
-            } else if (op.mode == EVO_SMOOTH_REDBLACK) {
-                auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF);
-                if (color_order_dependent(c->sten[l], sp, NF)) {
-                    if constexpr (NU == NF) {
-                        bool done = false;
-                        if constexpr (DIM == 2 && std::is_same<T, double>::value) {
-                            // unknown a must be field a at the anchor (collective pointwise smoother)
-                            bool canonical = true;
-                            for (int a = 0; a < NU; ++a)
-                                if (sp.field[a] != a || sp.off[a][0] || sp.off[a][1] || sp.off[a][2]) canonical = false;
-                            const size_t smem = (size_t)5 * 2 * NF * g.pitch * sizeof(double);
-                            static const bool disabled = getenv("EVO_ROWSEQ_GLOBAL") != nullptr;
-                            static const bool no_pipe = getenv("EVO_ROWSEQ_NOPIPE") != nullptr;
-                            // pipelined passes: as many of the remaining sweeps as the window fits (<= 4)
-                            int k = std::min(reps - rep, 4);
-                            while (k > 0 && (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double) > 200 * 1024) --k;
-                            Dense9<NF> dn;
-                            bool dense_ok = true;
-                            for (int a = 0; a < NF; ++a)
-                                for (int j = 0; j < NF; ++j) {
-                                    for (int q = 0; q < 9; ++q) dn.w[a][j][q] = 0.0;
-                                    const Sten &sj = c->sten[l].s[a][j];
-                                    for (int q = 0; q < sj.nnz; ++q) {
-                                        if (sj.oz[q] != 0 || sj.im[q] != 0.0 || sj.re[q] == 0.0) dense_ok = false;
-                                        dn.w[a][j][(sj.oy[q] + 1) * 3 + (sj.ox[q] + 1)] = sj.re[q];
-                                    }
-                                }
-                            if (canonical && !disabled && !no_pipe && k > 0 && dense_ok) {
-                                static bool attr_p = false;
-                                if (!attr_p) {
-                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                                    attr_p = true;
-                                }
-                                const size_t sm2 = (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double);
-                                k2_smooth_rowseq_pipe<NF><<<1, ROWSEQ_NT, sm2, s>>>(g, c->sten[l], dn, sp.omega, u, rhs, k);
-                                done = true;
-                                rep += k - 1;
-                            } else if (canonical && !disabled && smem <= 200 * 1024) {
-                                static bool attr = false;
-                                if (!attr) {
-                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_win<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                                    attr = true;
-                                }
-                                k2_smooth_rowseq_win<NF><<<1, 1024, smem, s>>>(g, c->sten[l], sp.omega, u, rhs);
-                                done = true;
-                            }
-                        }
-                        if (!done) k_smooth_rowseq<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs);
-                        c->launch_counter++;
-                    } else {
-                        return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
-                    }
-                } else {
-                    for (int color = 0; color < 2; ++color) {
-                        sp.color = color;
-                        if (!(NU == 1 && star::try_smooth_point<T, DIM, NF>(c->p->sm_count, g, c->sten[l], sp, u, u, rhs, s)))
-                            k_smooth<T, DIM, NF, NU><<<row_grid(g, 2), BX, 0, s>>>(g, c->sten[l], sp, u, u, rhs);
-                        c->launch_counter++;
-                    }
-                }
-            } else {
-                return fail(EVO_ERR_UNSUPPORTED, "lexicographic in-place smoothing (model-based mode) is not implemented");
-            }
-        }
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    static bool color_order_dependent(const OpSten &st, const SmoothParams &sp, int nf)
-    {
-        for (int a = 0; a < sp.nu; ++a)
-            for (int j = 0; j < nf; ++j) {
-                const Sten &sj = st.s[sp.field[a]][j];
-                for (int q = 0; q < sj.nnz; ++q) {
-                    int ox = sp.off[a][0] + sj.ox[q], oy = sp.off[a][1] + sj.oy[q], oz = sp.off[a][2] + sj.oz[q];
-                    bool is_unknown = false;
-                    for (int m = 0; m < sp.nu; ++m)
-                        if (sp.field[m] == j && sp.off[m][0] == ox && sp.off[m][1] == oy && sp.off[m][2] == oz) is_unknown = true;
-                    if (is_unknown) continue;
-                    for (int m = 0; m < sp.nu; ++m) {
-                        if (sp.field[m] != j) continue;
-                        int sx = ox - sp.off[m][0], sy = oy - sp.off[m][1], sz = oz - sp.off[m][2];
-                        if (((sx + sy + sz) & 1) == 0) return true;
-                    }
-                }
-            }
-        return false;
-    }
-
-    static int smooth(evo_cycle *c, const evo_op &op, cudaStream_t s)
-    {
-        switch (op.n_unknowns) {
-        case 1: return smooth_nu<1>(c, op, s);
-        case 2: return smooth_nu<2>(c, op, s);
-        case 3: return smooth_nu<3>(c, op, s);
-        case 4: return smooth_nu<4>(c, op, s);
-        case 5: return smooth_nu<5>(c, op, s);
-        case 6: return smooth_nu<6>(c, op, s);
-        case 7: return smooth_nu<7>(c, op, s);
-        case 8: return smooth_nu<8>(c, op, s);
-        default: return fail(EVO_ERR_INVALID, "local system size %d", op.n_unknowns);
-        }
-    }
-
-    static int restrict_(evo_cycle *c, const evo_op &op, cudaStream_t s)
-    {
-        const int l = op.level;
-        const Geom &gf = c->p->geom[l];
-        Geom gc = c->p->geom[l - 1];
-        if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
-        auto src = fields_of<T>(c->lv[l].buf[op.src], NF), dst = fields_of<T>(c->lv[l - 1].buf[op.dst], NF);
-        k_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->p->R, src, dst);
-        c->launch_counter++;
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    static int residual_restrict(evo_cycle *c, const evo_op &op, cudaStream_t s)
-    {
-        const int l = op.level;
-        const Geom &gf = c->p->geom[l];
-        Geom gc = c->p->geom[l - 1];
-        if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
-        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
-             dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
-        if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
-            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
-            k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
-        }
-        c->launch_counter++;
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    static int prolong(evo_cycle *c, const evo_op &op, bool add, cudaStream_t s)
-    {
-        const int l = op.level;
-        Geom gf = c->p->geom[l];
-        const Geom &gc = c->p->geom[l - 1];
-        if (c->zc_lo >= 0) { gf.zlo = c->zc_lo; gf.zhi = c->zc_hi; }   // domain decomposition: include ghost planes
-        auto src = fields_of<T>(c->lv[l - 1].buf[op.src], NF);
-        auto dst = fields_of<T>(c->lv[l].buf[add ? EVO_BUF_SOL : op.dst], NF);
-        if (add) {
-            if (!star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s)) {
-                if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: prolongation needs the fast path");
-                k_prolong<T, DIM, NF, true><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, op.omega);
-            }
-        } else {
-            if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: PROLONG_SET not supported");
-            k_prolong<T, DIM, NF, false><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, 1.0);
-        }
-        c->launch_counter++;
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-    static int richardson(evo_cycle *c, const evo_op &op, cudaStream_t s)
-    {
-        if (slab_level(c->p, op.level)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: Richardson steps not supported");
-        // field by field: tmp = RHS_i - (A SOL)_i from the current values, then SOL_i += w * tmp
-        const int l = op.level;
-        const Geom &g = c->p->geom[l];
-        auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF);
-        for (int i = 0; i < NF; ++i) {
-            T *tmp = (T *)c->lv[l].slot[i];
-            if (!tmp) return fail(EVO_ERR_INVALID, "missing scratch slot");
-            Fields<T> r = u;  // residual of field i goes to tmp; other entries unused (NF passes write all -> use scratch trick)
-            for (int j = 0; j < NF; ++j) r.p[j] = (T *)c->lv[l].slot[j];
-            k_residual<T, DIM, NF><<<row_grid(g), BX, 0, s>>>(g, c->sten[l], u, f, r);
-            k_axpy_inner<T, DIM><<<row_grid(g), BX, 0, s>>>(g, (T *)c->lv[l].buf[EVO_BUF_SOL][i], tmp, op.omega);
-            c->launch_counter += 2;
-        }
-        // the slot was used as scratch: restore its boundary invariant (inner values are don't-care)
-        CU(cudaGetLastError());
-        return EVO_OK;
-    }
-
-};
-
-template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, cudaStream_t s)
-{
-    const int l = op.level;
-    const Geom &g = c->p->geom[l];
-    if (l != c->p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
-    auto x = fields_of<double>(c->lv[l].buf[EVO_BUF_SOL], NF), b = fields_of<double>(c->lv[l].buf[EVO_BUF_RHS], NF);
-    {
-        // shared-memory resident variant when the four CG vectors fit
-        const int ni = g.n - 2;
-        const size_t vol = (size_t)g.n * g.n * (DIM == 3 ? g.n : 1);
-        const size_t smem = 4 * NF * vol * sizeof(double);
-        const int nrows = ni * (DIM == 3 ? ni : 1);
-        static const bool disabled = getenv("EVO_CG_GLOBAL") != nullptr;
-        static const bool no_reg = getenv("EVO_CG_NOREG") != nullptr;
-        if constexpr (DIM == 2) {
-            // one node per thread, CG vectors in registers (coarsest grids up to 33 x 33)
-            Dense9<NF> dn;
-            bool dense_ok = !disabled && !no_reg && ni <= 32;
-            for (int a = 0; a < NF && dense_ok; ++a)
-                for (int j = 0; j < NF; ++j) {
-                    for (int q = 0; q < 9; ++q) dn.w[a][j][q] = 0.0;
-                    const Sten &sj = c->sten[l].s[a][j];
-                    for (int q = 0; q < sj.nnz; ++q) {
-                        if (sj.oz[q] != 0 || sj.im[q] != 0.0 || sj.re[q] == 0.0) dense_ok = false;
-                        dn.w[a][j][(sj.oy[q] + 1) * 3 + (sj.ox[q] + 1)] = sj.re[q];
-                    }
-                }
-            if (dense_ok) {
-                k2_coarse_cg_reg<NF><<<1, 1024, NF * vol * sizeof(double), s>>>(g, dn, x, b, op.count, op.tol, c->d_cg_iters);
-                c->launch_counter++;
-                CU(cudaGetLastError());
-                return EVO_OK;
-            }
-        }
-        if (!disabled && smem <= 160 * 1024 && NF * nrows <= 512 && (DIM == 2 || ni <= 64)) {
-            static bool attr = false;
-            if (!attr) {
-                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr = true;
-            }
-            k_coarse_cg_smem<DIM, NF><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
-            c->launch_counter++;
-            CU(cudaGetLastError());
-            return EVO_OK;
-        }
-    }
-    auto r = fields_of<double>(c->krylov[0], NF), p = fields_of<double>(c->krylov[1], NF), ap = fields_of<double>(c->krylov[2], NF);
-    k_coarse_cg<DIM, NF><<<1, 1024, 0, s>>>(g, c->sten[l], x, b, r, p, ap, (double *)c->krylov[3][0], op.count, op.tol,
-                                            c->d_cg_iters);
-    c->launch_counter++;
-    CU(cudaGetLastError());
-    return EVO_OK;
-}
-
-static cplx helm_rden(const evo_problem *p, int level);
-
-template <typename T, int DIM, int NF> static int enqueue_op(evo_cycle *c, const evo_op &op, cudaStream_t s)
-{
-    using L = Launch<T, DIM, NF>;
-    evo_problem *p = c->p;
-    const int l = op.level;
-    const size_t esz = sizeof(double) * p->words;
-    switch (op.code) {
-    case EVO_OP_ZERO:
-        for (int i = 0; i < NF; ++i) CU(cudaMemsetAsync(c->lv[l].buf[op.dst][i], 0, (size_t)p->geom[l].total * esz, s));
-        return EVO_OK;
-    case EVO_OP_COPY:
-        for (int i = 0; i < NF; ++i)
-            if (c->lv[l].buf[op.dst][i] != c->lv[l].buf[op.src][i])
-                CU(cudaMemcpyAsync(c->lv[l].buf[op.dst][i], c->lv[l].buf[op.src][i], (size_t)p->geom[l].total * esz,
-                                   cudaMemcpyDeviceToDevice, s));
-        return EVO_OK;
-    case EVO_OP_RESIDUAL: return L::residual(c, l, false, s);
-    case EVO_OP_RICHARDSON: return L::richardson(c, op, s);
-    case EVO_OP_SMOOTH: return L::smooth(c, op, s);
-    case EVO_OP_RESTRICT: return L::restrict_(c, op, s);
-    case EVO_OP_RESIDUAL_RESTRICT: return L::residual_restrict(c, op, s);
-    case EVO_OP_PROLONG_ADD: return L::prolong(c, op, true, s);
-    case EVO_OP_PROLONG_SET: return L::prolong(c, op, false, s);
-    case EVO_OP_COARSE_SOLVE:
-        if constexpr (std::is_same<T, double>::value) {
-            return coarse_cg<DIM, NF>(c, op, s);
-        } else {
-            if (l != p->desc.min_level) return fail(EVO_ERR_UNSUPPORTED, "coarse-grid solver below its level");
-            const Geom &g = p->geom[l];
-            helm::k2_coarse_bicgstab<<<1, 1024, 0, s>>>(
-                g, c->sten[l], helm_rden(p, l), (cplx *)c->lv[l].buf[EVO_BUF_SOL][0], (const cplx *)c->lv[l].buf[EVO_BUF_RHS][0],
-                (cplx *)c->lv[l].buf[EVO_BUF_RES][0], (cplx *)c->krylov[0][0], (cplx *)c->krylov[1][0], (cplx *)c->krylov[2][0],
-                (cplx *)c->krylov[3][0], (cplx *)c->krylov[4][0], (cplx *)c->krylov[5][0], (cplx *)c->krylov[6][0], op.count, op.tol,
-                p->desc.kind == EVO_PROBLEM_HELMHOLTZ ? 1 : 0);
-            c->launch_counter++;
-            CU(cudaGetLastError());
-            return EVO_OK;
-        }
-    default: return fail(EVO_ERR_UNSUPPORTED, "op code %d not implemented", op.code);
-    }
-}
+// the statement dispatch lives in evo_dispatch_inst.cu (one translation unit per combination)
+#define EVO_EXTERN_INST(...)                                                                  \
+    extern template int enqueue_op<__VA_ARGS__>(evo_cycle *, const evo_op &, cudaStream_t);    \
+    extern template int op_residual<__VA_ARGS__>(evo_cycle *, int, bool, cudaStream_t);        \
+    extern template int op_restrict<__VA_ARGS__>(evo_cycle *, const evo_op &, cudaStream_t);   \
+    extern template int op_reduce_rows<__VA_ARGS__>(evo_cycle *, int, cudaStream_t);
+EVO_EXTERN_INST(double, 2, 1)
+EVO_EXTERN_INST(double, 2, 2)
+EVO_EXTERN_INST(double, 3, 1)
+EVO_EXTERN_INST(double, 3, 2)
+EVO_EXTERN_INST(cplx, 2, 1)
 
 // ---- FAS problems (real scalar 2-D) -----------------------------------------------------------------
 static int fas_residual(evo_cycle *c, int l, cudaStream_t s)
@@ -902,7 +469,7 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
     case EVO_OP_FAS_RESTRICT_SOL: {
         evo_op r = op;
         r.code = EVO_OP_RESTRICT; r.dst = EVO_BUF_APX; r.src = EVO_BUF_SOL;
-        EV((Launch<double, 2, 1>::restrict_(c, r, s)));
+        EV((op_restrict<double, 2, 1>(c, r, s)));
         const size_t bytes = (size_t)c->p->geom[l - 1].total * sizeof(double);
         CU(cudaMemcpyAsync(c->lv[l - 1].buf[EVO_BUF_SOL][0], c->lv[l - 1].buf[EVO_BUF_APX][0], bytes, cudaMemcpyDeviceToDevice, s));
         return EVO_OK;
@@ -910,7 +477,7 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
     case EVO_OP_FAS_COARSE_RHS: {
         evo_op r = op;
         r.code = EVO_OP_RESTRICT; r.dst = EVO_BUF_RHS; r.src = EVO_BUF_RES;
-        EV((Launch<double, 2, 1>::restrict_(c, r, s)));
+        EV((op_restrict<double, 2, 1>(c, r, s)));
         fas::Lin2 L;
         if (!c->has_sten[l - 1] || !fas::make_lin2(c->sten[l - 1].s[0][0], &L)) return fail(EVO_ERR_INVALID, "FAS: no operator on level %d", l - 1);
         const Geom &gc = c->p->geom[l - 1];
@@ -933,7 +500,7 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
         if (!fas::make_lin2(c->sten[l].s[0][0], &L)) return fail(EVO_ERR_UNSUPPORTED, "FAS: unsupported linear stencil");
         if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing slot for the FAS coarse solver");
         const Geom &g = c->p->geom[l];
-        static const int cgs_mode = getenv("EVO_FAS_CGS") ? atoi(getenv("EVO_FAS_CGS")) : 0;   // 0 auto, 1 one CTA (smem), 2 launches
+        const int cgs_mode = option(OPT_FAS_CGS);   // 0 auto, 1 one CTA (smem), 2 launches
         if (cgs_mode == 0 && g.n <= 65) {   // 129^2: 200 graph-launched sweeps over all SMs are faster (measured)
             // rows split over a cluster of 8 CTAs (distributed shared memory halos, one cluster barrier per sweep)
             const int cs = 8, ni = g.n - 2, rp = (ni + cs - 1) / cs;
@@ -980,7 +547,7 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
             CU(cudaGetLastError());
             return EVO_OK;
         }
-        static const bool global_cgs = getenv("EVO_FAS_CGS_GLOBAL") != nullptr;
+        const bool global_cgs = option(OPT_FAS_CGS_GLOBAL) != 0;
         if (!global_cgs && g.n <= 65) {
             // both slots in shared memory, up to 4 nodes per thread in flight
             const size_t smem = (size_t)2 * (g.n + 1) * g.n * sizeof(double);
@@ -1006,7 +573,7 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
 }
 
 // 1 / (1 - i k h) by Smith's algorithm, the same operation sequence as the oracle's cdiv_smith(1.0, den)
-static cplx helm_rden(const evo_problem *p, int level)
+cplx helm_rden(const evo_problem *p, int level)
 {
     const double h = 1.0 / (double)(1 << level);
     // I * k = (0*kr - 1*ki) + (0*ki + 1*kr) i ; times h ; den = 1.0 - that
@@ -1073,13 +640,13 @@ static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store
         auto r = fields_of<double>(c->lv[l].buf[EVO_BUF_RES], 1);
         k_row_sumsq<double, 2, 1><<<(unsigned)((ni + 3) / 4), 128, 0, s>>>(g, r, c->d_partials);
         c->launch_counter++;
-        return Launch<double, 2, 1>::reduce_rows(c, ni, s);
+        return op_reduce_rows<double, 2, 1>(c, ni, s);
     }
-    if (d.scalar_words == 2) EV((Launch<cplx, 2, 1>::residual(c, l, true, s)));
-    else if (d.dim == 2 && d.n_fields == 1) EV((Launch<double, 2, 1>::residual(c, l, true, s)));
-    else if (d.dim == 2) EV((Launch<double, 2, 2>::residual(c, l, true, s)));
-    else if (d.n_fields == 1) EV((Launch<double, 3, 1>::residual(c, l, true, s)));
-    else EV((Launch<double, 3, 2>::residual(c, l, true, s)));
+    if (d.scalar_words == 2) EV((op_residual<cplx, 2, 1>(c, l, true, s)));
+    else if (d.dim == 2 && d.n_fields == 1) EV((op_residual<double, 2, 1>(c, l, true, s)));
+    else if (d.dim == 2) EV((op_residual<double, 2, 2>(c, l, true, s)));
+    else if (d.n_fields == 1) EV((op_residual<double, 3, 1>(c, l, true, s)));
+    else EV((op_residual<double, 3, 2>(c, l, true, s)));
     return EVO_OK;
 }
 
@@ -1239,11 +806,11 @@ extern "C" int evo_cycle_destroy(evo_cycle *c)
     if (c->graph) cudaGraphDestroy(c->graph);
     if (c->helm_exec) cudaGraphExecDestroy(c->helm_exec);
     if (c->helm_graph) cudaGraphDestroy(c->helm_graph);
-    if (c->slab) c->p->pool.push_back({c->slab, c->slab_bytes});
-    // keep the pool bounded: free slabs beyond a generous budget
+    if (c->slab) c->p->pool.push_back({c->slab, c->slab_cap});
+    // keep the pool bounded: at most 512 slabs and a quarter of the device memory stay parked here
     size_t pooled = 0;
     for (auto &s : c->p->pool) pooled += s.second;
-    while (!c->p->pool.empty() && (c->p->pool.size() > 512 || pooled > ((size_t)64 << 30))) {
+    while (!c->p->pool.empty() && (c->p->pool.size() > 512 || pooled > c->p->device_bytes / 4)) {
         pooled -= c->p->pool.front().second;
         cudaFree(c->p->pool.front().first);
         c->p->pool.erase(c->p->pool.begin());
@@ -1547,6 +1114,26 @@ static int ensure_hist(evo_cycle *c, int max_iters)
     return EVO_OK;
 }
 
+// Error paths of the graph builders: a failing call must not leave the stream in capture mode or leak the graph.
+struct CaptureGuard {       // ends an open capture (the graph of a capture-to-graph belongs to its parent)
+    cudaStream_t s;
+    bool open = false, owns_graph = false;
+    explicit CaptureGuard(cudaStream_t st) : s(st) {}
+    ~CaptureGuard()
+    {
+        if (!open) return;
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(s, &g);
+        if (g && owns_graph) cudaGraphDestroy(g);
+        cudaGetLastError();
+    }
+};
+struct GraphGuard {         // destroys a graph under construction unless release()d
+    cudaGraph_t g = nullptr;
+    ~GraphGuard() { if (g) cudaGraphDestroy(g); }
+    cudaGraph_t release() { cudaGraph_t r = g; g = nullptr; return r; }
+};
+
 // graph = [res0 + norm + update(0)] -> WHILE(!done) { cycle ops; residual + norm; update(1); set condition }
 static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
 {
@@ -1556,7 +1143,10 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     cudaStream_t s = c->stream;
     // prologue captured into the main graph
     c->launch_counter = 0;
+    CaptureGuard cap(s);
+    GraphGuard gg;
     CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cap.open = true; cap.owns_graph = true;
     int rc = dispatch_residual_norm(c, s);
     if (rc == EVO_OK) {
         k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 0);
@@ -1564,7 +1154,9 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     }
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(s, &g);
-    if (rc != EVO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    cap.open = false;
+    gg.g = g;
+    if (rc != EVO_OK) return rc;
     if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "prologue capture: %s", cudaGetErrorString(e));
     c->kernels_prologue = c->launch_counter;
     // find the leaf of the prologue to hang the while node on
@@ -1604,6 +1196,7 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     cudaGraph_t body = cp.conditional.phGraph_out[0];
     c->launch_counter = 0;
     CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    cap.open = true; cap.owns_graph = false;
     // Out-of-place statements (jacobi slots, the streaming RB-GS kernel) swap SOL and its [next] slot.  A cycle
     // with an odd number of swaps on a level ends in the other buffer: instead of copying it back every cycle
     // (2 x 8 B/DOF of pure overhead) the loop body holds TWO cycles -- the second one, inside an IF node, runs
@@ -1615,7 +1208,7 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
             c->odd_swap[l][i] = c->lv[l].swapped[i];
             odd = odd || c->lv[l].swapped[i];
         }
-    static const bool no_pingpong = getenv("EVO_NO_PINGPONG") != nullptr;
+    const bool no_pingpong = option(OPT_NO_PINGPONG) != 0;
     c->pingpong = odd && !no_pingpong && rc == EVO_OK;
     if (rc == EVO_OK && !c->pingpong) {
         // restore the canonical assignment by copying (no-op when nothing is swapped)
@@ -1633,8 +1226,9 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     }
     c->kernels_per_cycle = c->launch_counter;
     e = cudaStreamEndCapture(s, nullptr);
-    if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "body capture: %s", cudaGetErrorString(e)); }
+    cap.open = false;
+    if (rc != EVO_OK) return rc;
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "body capture: %s", cudaGetErrorString(e));
     if (c->pingpong) {
         std::vector<cudaGraphNode_t> bl;
         EV(graph_leaves(body, bl));
@@ -1659,6 +1253,7 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
         CU(cudaGraphAddNode(&inode, body, &setc, 1, &ip));
         cudaGraph_t second = ip.conditional.phGraph_out[0];
         CU(cudaStreamBeginCaptureToGraph(s, second, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        cap.open = true; cap.owns_graph = false;
         rc = enqueue_cycle_ops(c, s);
         bool still = false;
         for (int l = c->p->desc.min_level; l <= c->p->desc.max_level; ++l)
@@ -1670,8 +1265,9 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
             k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
         }
         e = cudaStreamEndCapture(s, nullptr);
-        if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
-        if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "second body capture: %s", cudaGetErrorString(e)); }
+        cap.open = false;
+        if (rc != EVO_OK) return rc;
+        if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "second body capture: %s", cudaGetErrorString(e));
         // epilogue: after an odd number of cycles copy the solution back into the canonical buffers (once per solve)
         cudaGraphConditionalHandle h_odd;
         CU(cudaGraphConditionalHandleCreate(&h_odd, g, 0, cudaGraphCondAssignDefault));
@@ -1695,6 +1291,7 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
         CU(cudaGraphAddNode(&onode, g, &seto, 1, &op));
         cudaGraph_t fix = op.conditional.phGraph_out[0];
         CU(cudaStreamBeginCaptureToGraph(s, fix, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        cap.open = true; cap.owns_graph = false;
         const size_t esz = sizeof(double) * c->p->words;
         cudaError_t ce = cudaSuccess;
         {
@@ -1706,18 +1303,23 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
                                              cudaMemcpyDeviceToDevice, s);
         }
         e = cudaStreamEndCapture(s, nullptr);
-        if (ce != cudaSuccess || e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "epilogue capture failed"); }
+        cap.open = false;
+        if (ce != cudaSuccess || e != cudaSuccess) return fail(EVO_ERR_CUDA, "epilogue capture failed");
     }
     c->kernels_per_cycle = c->launch_counter;
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, g, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
-    c->graph = g;
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    c->graph = gg.release();
     c->exec = exec;
     c->graph_tol = tol;
     c->graph_max_iters = max_iters;
     return EVO_OK;
 }
+
+static __global__ void k_set_cap(SolveState *st, int cap) { st->cap = cap; }
+static __global__ void k_set_timeout(SolveState *st, unsigned long long ns) { st->timeout_ns = ns; }
+static __global__ void k_set_timeout_helm(helm::HelmState *st, unsigned long long ns) { st->timeout_ns = ns; }
 
 // enqueue one complete solve on the cycle's stream (no host synchronisation)
 static int enqueue_solve(evo_cycle *c, const evo_solve_params *prm)
@@ -1725,6 +1327,7 @@ static int enqueue_solve(evo_cycle *c, const evo_solve_params *prm)
     cudaStream_t s = c->stream;
     if (!(prm->flags & EVO_SOLVE_KEEP_STATE) && !c->pristine) EV(reset_cycle(c, s));   // a fresh cycle is already reset
     c->pristine = false;
+    if (prm->timeout_ms > 0) k_set_timeout<<<1, 1, 0, s>>>(c->d_state, (unsigned long long)prm->timeout_ms * 1000000ull);
     CU(cudaEventRecord(c->ev0, s));
     if (prm->flags & EVO_SOLVE_NO_GRAPH) {
         // debugging path: direct launches, host-side loop with one synchronisation per iteration
@@ -1756,7 +1359,7 @@ static int collect_solve(evo_cycle *c, const evo_solve_params *prm, evo_solve_re
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     const SolveState &st = *c->h_state;
-    res->status = st.bad ? 1 : 0;
+    res->status = st.bad ? 1 : (st.timed_out ? 2 : 0);
     res->iterations = st.it;
     res->initial_residual = st.res0;
     res->final_residual = st.res;
@@ -1879,16 +1482,24 @@ static int helm_prologue(evo_cycle *c, double tol, int max_iters, cudaStream_t s
 
 static int build_helm_graph(evo_cycle *c, double tol, int max_iters)
 {
-    if (c->helm_exec && c->helm_tol == tol && c->helm_max_iters == max_iters) return EVO_OK;
+    // the un-shifted operator is a by-value kernel argument of the captured graph: a different A needs a new graph
+    if (c->helm_exec && c->helm_tol == tol && c->helm_max_iters == max_iters &&
+        memcmp(&c->helm_A_graph, &c->helm_A, sizeof(OpSten)) == 0)
+        return EVO_OK;
     if (c->helm_exec) { cudaGraphExecDestroy(c->helm_exec); c->helm_exec = nullptr; }
     if (c->helm_graph) { cudaGraphDestroy(c->helm_graph); c->helm_graph = nullptr; }
     cudaStream_t s = c->stream;
     c->launch_counter = 0;
+    CaptureGuard cap(s);
+    GraphGuard gg;
     CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cap.open = true; cap.owns_graph = true;
     int rc = helm_prologue(c, tol, max_iters, s);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(s, &g);
-    if (rc != EVO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    cap.open = false;
+    gg.g = g;
+    if (rc != EVO_OK) return rc;
     if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "helmholtz prologue capture: %s", cudaGetErrorString(e));
     c->kernels_prologue = c->launch_counter;
     size_t n_nodes = 0;
@@ -1922,19 +1533,22 @@ static int build_helm_graph(evo_cycle *c, double tol, int max_iters)
     cudaGraph_t body = cp.conditional.phGraph_out[0];
     c->launch_counter = 0;
     CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    cap.open = true; cap.owns_graph = false;
     rc = helm_iteration(c, tol, max_iters, s);
     if (rc == EVO_OK) {
         helm::k_set_while_condition_helm<<<1, 32, 0, s>>>(handle, c->d_helm);
         c->launch_counter++;
     }
     e = cudaStreamEndCapture(s, nullptr);
-    if (rc != EVO_OK) { cudaGraphDestroy(g); return rc; }
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "helmholtz body capture: %s", cudaGetErrorString(e)); }
+    cap.open = false;
+    if (rc != EVO_OK) return rc;
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "helmholtz body capture: %s", cudaGetErrorString(e));
     c->kernels_per_cycle = c->launch_counter;
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, g, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
-    c->helm_graph = g; c->helm_exec = exec; c->helm_tol = tol; c->helm_max_iters = max_iters;
+    if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    c->helm_graph = gg.release(); c->helm_exec = exec; c->helm_tol = tol; c->helm_max_iters = max_iters;
+    memcpy(&c->helm_A_graph, &c->helm_A, sizeof(OpSten));
     return EVO_OK;
 }
 
@@ -1958,7 +1572,6 @@ extern "C" int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, co
         }
     }
     EV(ensure_hist(c, prm->max_iters));
-    // the operator is baked into the graph: rebuild when it changes is the caller's business (one A per cycle)
     EV(build_helm_graph(c, prm->tol, prm->max_iters));
     const int samples = prm->samples > 0 ? prm->samples : 1;
     std::vector<float> times;
@@ -1967,6 +1580,7 @@ extern "C" int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, co
     for (int sidx = 0; sidx < samples; ++sidx) {
         cudaStream_t s = c->stream;
         EV(reset_cycle(c, s));
+        if (prm->timeout_ms > 0) k_set_timeout_helm<<<1, 1, 0, s>>>(c->d_helm, (unsigned long long)prm->timeout_ms * 1000000ull);
         CU(cudaEventRecord(c->ev0, s));
         CU(cudaGraphLaunch(c->helm_exec, s));
         CU(cudaEventRecord(c->ev1, s));
@@ -1977,7 +1591,7 @@ extern "C" int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, co
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         times.push_back(ms);
     }
-    res->status = hs.bad ? 1 : 0;
+    res->status = hs.bad ? 1 : (hs.timed_out ? 2 : 0);
     res->iterations = hs.it;
     res->initial_residual = hs.init;
     res->final_residual = hs.cur;
@@ -1986,6 +1600,22 @@ extern "C" int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, co
     std::sort(times.begin(), times.end());
     res->time_ms = times[times.size() / 2];
     res->time_ms_min = times[0];
+    return EVO_OK;
+}
+
+
+// one solve of a cycle whose graph exists, alone on the device, stopped after `cap` iterations (0: to convergence)
+static int solo_run(evo_cycle *c, int cap, float *ms)
+{
+    cudaStream_t s = c->stream;
+    EV(reset_cycle(c, s));
+    c->pristine = false;
+    if (cap > 0) k_set_cap<<<1, 1, 0, s>>>(c->d_state, cap);
+    CU(cudaEventRecord(c->ev0, s));
+    CU(cudaGraphLaunch(c->exec, s));
+    CU(cudaEventRecord(c->ev1, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
     return EVO_OK;
 }
 
@@ -2030,6 +1660,29 @@ extern "C" int evo_batch_solve(evo_cycle **cycles, int n, const evo_solve_params
         std::sort(times[i].begin(), times[i].end());
         results[i].time_ms = times[i][times[i].size() / 2];
         results[i].time_ms_min = times[i][0];
+    }
+    if (prm->flags & EVO_SOLVE_SOLO_TIMING) {
+        // The times above include the contention of everything else that was in flight.  Time is an optimisation
+        // objective (optimization/program.py:413, :449), so every member that converged is timed again with the GPU
+        // to itself: the whole solve when it is short, else 1 and 4 iterations (SolveState::cap) extrapolated to its
+        // iteration count.  Members that hit the iteration limit or diverged keep the batch time (unused: their
+        // fitness is the sentinel).
+        for (int i = 0; i < n; ++i) {
+            const int its = results[i].iterations;
+            if (results[i].status != 0 || its < 1 || its >= prm->max_iters) continue;
+            evo_cycle *c = cycles[i];
+            CU(cudaSetDevice(c->p->desc.device));
+            float t_full = 0.f, t1 = 0.f, t4 = 0.f;
+            if (its <= 6) {
+                EV(solo_run(c, 0, &t_full));
+                results[i].time_ms = results[i].time_ms_min = t_full;
+            } else {
+                EV(solo_run(c, 1, &t1));
+                EV(solo_run(c, 4, &t4));
+                const double per_it = std::max(0.0, ((double)t4 - t1) / 3.0);
+                results[i].time_ms = results[i].time_ms_min = t1 + per_it * (its - 1);
+            }
+        }
     }
     std::sort(wall.begin(), wall.end());
     if (batch_ms) *batch_ms = wall[wall.size() / 2];

@@ -47,6 +47,7 @@ PROBLEM_LINEAR, PROBLEM_FAS, PROBLEM_HELMHOLTZ = 0, 1, 2
 
 SOLVE_NO_GRAPH = 1
 SOLVE_KEEP_STATE = 2
+SOLVE_SOLO_TIMING = 4
 
 
 class CEvoOp(C.Structure):
@@ -77,7 +78,7 @@ class CEvoProblemDesc(C.Structure):
 
 class CEvoSolveParams(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iters", C.c_int32), ("samples", C.c_int32), ("flags", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("timeout_ms", C.c_int32)]
 
 
 class CEvoSolveResult(C.Structure):

@@ -299,6 +299,11 @@ class B200ProgramGenerator:
             return infinity, infinity, infinity
         return time_ms, cf, iters
 
+    def _timeout_ms(self) -> int:
+        """``evaluation_timeout`` (seconds, exastencils.py:42) as the watchdog of the device-side solver loop."""
+        t = self.timeout_evaluate
+        return int(min(max(float(t), 0.0) * 1000.0, 2 ** 31 - 1)) if t else 0
+
     def _evaluate_program(self, prog: ol.Program, min_level, problem, infinity, evaluation_samples):
         dev = self._device_problem(min_level, self.max_level, problem)
         s = dev.problem.settings
@@ -312,13 +317,15 @@ class B200ProgramGenerator:
         cyc = dev.build(prog)
         try:
             if helmholtz:
-                out = cyc.helmholtz_solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
+                out = cyc.helmholtz_solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)), timeout_ms=self._timeout_ms())
             else:
-                out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)))
+                out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(evaluation_samples)), timeout_ms=self._timeout_ms())
         finally:
             cyc.close()
         self.last_outcome = out
         self.total_kernel_launches += out.kernel_launches * max(1, int(evaluation_samples))
+        if out.status == 2:                                     # evaluation timed out (:430-433, :476-483)
+            return infinity, infinity, infinity
         if helmholtz:
             t, cf, its = fitness.helmholtz_fitness(out.residuals, out.time_ms, s.max_iters, infinity,
                                                    self._solver_iteration_limit, s.tol)
@@ -329,12 +336,17 @@ class B200ProgramGenerator:
 
     def generate_and_evaluate(self, expression, storages, min_level: int, max_level: int, solver_program: str,
                               infinity=1e100, evaluation_samples=3, global_variable_values=None):
+        """Same contract as the reference (exastencils.py:485-537): never raises for a *bad individual* -- a tree that
+        cannot be lowered ("code generation failed", :499-510), an op list the library rejects as malformed, a
+        diverging or timed-out solve all give ``(infinity,)*3``.  Failures of the infrastructure (no device, CUDA
+        error, out of memory, a statement the library does not implement) are NOT fitness values and propagate as
+        ``backend.BackendError``."""
         if global_variable_values is None:
             global_variable_values = {}
         start = time.time()
         try:
             prog = self._finalise(self.lower(expression, min_level))
-        except Exception:
+        except lowering.LoweringError:
             return infinity, infinity, infinity                 # "Code generation failed" (:499-510)
         self._counter += 1
         self._average_generation_time += (time.time() - start - self._average_generation_time) / self._counter
@@ -355,7 +367,9 @@ class B200ProgramGenerator:
                     problem.parameters["k"] = float(mapping["k"])
             try:
                 t, cf, its = self._evaluate_program(prog, min_level, problem, infinity, evaluation_samples)
-            except backend.BackendError:
+            except backend.BackendError as e:
+                if e.infrastructure:
+                    raise
                 t, cf, its = infinity, infinity, infinity
             avg[0] += t; avg[1] += cf; avg[2] += its
             if its >= infinity or cf > 1:                       # :529-530
@@ -366,10 +380,18 @@ class B200ProgramGenerator:
 
     # ---- beyond the reference surface: a whole generation in one call -----------------------------------
     def evaluate_population(self, expressions: Sequence, min_level: Optional[int] = None, infinity=1e100,
-                            evaluation_samples: int = 1, max_in_flight: int = 64, programs: Optional[Sequence[ol.Program]] = None):
+                            evaluation_samples: int = 1, max_in_flight: int = 64, programs: Optional[Sequence[ol.Program]] = None,
+                            solo_timing: bool = True):
         """Fitness tuples of many individuals; up to ``max_in_flight`` solves run concurrently on the GPU,
         one CUDA stream and one device-side solver loop each (the reference evaluates one after the other,
-        program.py:491).  Returns (list of tuples, device milliseconds)."""
+        program.py:491).  Returns (list of tuples, device milliseconds).
+
+        ``solo_timing`` (default): the time entry of every converged individual is measured again with the GPU to
+        itself (a few iterations, extrapolated to its iteration count), so that it is the same objective
+        ``generate_and_evaluate`` returns and does not depend on the batch composition.  With ``False`` the time is the
+        individual's span inside the concurrent batch -- higher throughput, but NOT comparable between batches.
+        Helmholtz problems (outer BiCGStab) are evaluated one after the other through the same path as
+        ``generate_and_evaluate``."""
         min_level = self.min_level if min_level is None else min_level
         dev = self._device_problem(min_level, self.max_level)
         s = dev.problem.settings
@@ -382,25 +404,57 @@ class B200ProgramGenerator:
             for e in expressions:
                 try:
                     progs.append(self._finalise(self.lower(e, min_level)))
-                except Exception:
+                except lowering.LoweringError:
                     progs.append(None)
+        sentinel = (infinity, infinity, infinity)
+        if dev.problem.kind == ol.PROBLEM_HELMHOLTZ:
+            for p in progs:
+                if p is None:
+                    results.append(sentinel)
+                    continue
+                try:
+                    results.append(self._evaluate_program(p, min_level, None, infinity, evaluation_samples))
+                    total_ms += self.last_outcome.time_ms * max(1, evaluation_samples)
+                except backend.BackendError as e:
+                    if e.infrastructure:
+                        raise
+                    results.append(sentinel)
+            return results, total_ms
         for a in range(0, len(progs), max_in_flight):
             chunk = progs[a:a + max_in_flight]
-            cycles = [dev.build(p) if p is not None else None for p in chunk]
-            live = [c for c in cycles if c is not None]
-            outs, ms = dev.batch_solve(live, s.tol, s.max_iters, samples=max(1, evaluation_samples)) if live else ([], 0.0)
-            total_ms += ms
-            it = iter(outs)
-            for c in cycles:
-                if c is None:
-                    results.append((infinity, infinity, infinity))
-                    continue
-                o = next(it)
-                self.total_kernel_launches += o.kernel_launches * max(1, evaluation_samples)
-                t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
-                                                          self._solver_iteration_limit)
-                results.append(self._apply_sentinels(t, cf, its, infinity))
-                c.close()
+            cycles: List[Optional[backend.DeviceCycle]] = []
+            try:
+                for p in chunk:
+                    if p is None:
+                        cycles.append(None)
+                        continue
+                    try:
+                        cycles.append(dev.build(p))
+                    except backend.BackendError as e:
+                        if e.infrastructure:
+                            raise
+                        cycles.append(None)
+                live = [c for c in cycles if c is not None]
+                outs, ms = dev.batch_solve(live, s.tol, s.max_iters, samples=max(1, evaluation_samples), solo_timing=solo_timing,
+                                           timeout_ms=self._timeout_ms()) if live else ([], 0.0)
+                total_ms += ms
+                it = iter(outs)
+                for c in cycles:
+                    if c is None:
+                        results.append(sentinel)
+                        continue
+                    o = next(it)
+                    self.total_kernel_launches += o.kernel_launches * max(1, evaluation_samples)
+                    if o.status == 2:
+                        results.append(sentinel)
+                        continue
+                    t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
+                                                              self._solver_iteration_limit)
+                    results.append(self._apply_sentinels(t, cf, its, infinity))
+            finally:
+                for c in cycles:
+                    if c is not None:
+                        c.close()
         return results, total_ms
 
     def close(self):
@@ -531,7 +585,11 @@ class B200ProgramGeneratorFAS:
                 out = cyc.solve(s.tol, s.max_iters, samples=max(1, int(samples)))
             finally:
                 cyc.close()
-        except Exception:
+        except backend.BackendError as e:
+            if e.infrastructure:                                # not a property of the individual
+                raise
+            return infinity, infinity, infinity
+        except lowering.LoweringError:
             return infinity, infinity, infinity
         self._counter += 1
         self._average_generation_time += (time.time() - start - self._average_generation_time) / self._counter

@@ -139,14 +139,19 @@ typedef struct evo_solve_params {
     int32_t max_iters;   /* solver_maxNumIts (:4)                                               */
     int32_t samples;     /* evaluation_samples (exastencils.py:417-443): timing repeats          */
     int32_t flags;       /* EVO_SOLVE_* bits                                                    */
-    int32_t reserved;
+    int32_t timeout_ms;  /* > 0: a solve that runs longer is stopped at the next iteration boundary by the device-side
+                            loop and reports status 2 -- the reference kills the binary after `evaluation_timeout` and
+                            returns (infinity,)*3 (exastencils.py:430-433, :476-483); 0 = no limit                  */
 } evo_solve_params;
 
 #define EVO_SOLVE_NO_GRAPH 1   /* debugging: launch kernels directly, no CUDA-graph capture */
 #define EVO_SOLVE_KEEP_STATE 2 /* do not reset SOL to the initial guess before solving      */
+#define EVO_SOLVE_SOLO_TIMING 4 /* evo_batch_solve: time_ms of every converged member is re-measured with the GPU to itself
+                                   (a few iterations, extrapolated), so that the time objective does not depend on what
+                                   else was in flight -- the reference times one binary at a time (exastencils.py:417-443) */
 
 typedef struct evo_solve_result {
-    int32_t status;       /* 0 ok, 1 non-finite residual encountered                            */
+    int32_t status;       /* 0 ok, 1 non-finite residual encountered, 2 stopped by the timeout_ms watchdog */
     int32_t iterations;   /* outer iterations executed                                          */
     double time_ms;       /* median solve time over `samples` runs, CUDA events (ms)            */
     double time_ms_min;
@@ -166,6 +171,12 @@ const char *evo_last_error(void);
  * the drop-in raises the same way when this returns <= 0.                                      */
 int evo_device_count(void);
 int evo_device_name(int device, char *buf, size_t len, int *sm_count);
+/* Tuning switches (kernel variants / experiments; the defaults are the measured best).  `name` is the name of the
+ * environment variable that initialises the switch (EVO_RB_VARIANT, EVO_RB_FUSE2, EVO_RR_VARIANT, ...; DESIGN.md
+ * lists them).  A new value applies to solver graphs captured afterwards.  The reference's counterpart are the
+ * knowledge-file switches patched per run (exastencils.py:217-266).                                             */
+int evo_set_option(const char *name, int value);
+int evo_get_option(const char *name, int *value);
 
 /* -- problem = discretisation hierarchy + initial guess / rhs (what InitFields and the field
  *    declarations of the generated program hold; exastencils.py:586-592 generate_storage)      */

@@ -77,3 +77,56 @@ def test_population_evaluation_equals_one_by_one(cuda_backend):
         assert a[1] == b[1] or (np.isnan(a[1]) and np.isnan(b[1]))
         assert a[2] == b[2]
     pg.close()
+
+
+def test_timeout_gives_the_sentinel(cuda_backend):
+    """evaluation_timeout (exastencils.py:42, :430-433, :476-483): an evaluation that runs longer returns
+    (infinity,)*3; here the watchdog lives in the device-side solver loop."""
+    prob = problems.Poisson2D(5, 9)
+    slow = tree.build_tree(prob, tree.v_cycle_individual(4, 1, 1, 2, partitioning="single"))   # weak damping: many iterations
+    pg = B200ProgramGenerator(problem=prob, evaluation_timeout=0.002)
+    storages = pg.generate_storage(5, 9, pg.finest_grid)
+    assert pg.generate_and_evaluate(slow, storages, 5, 9, "", evaluation_samples=1) == (1e100, 1e100, 1e100)
+    assert pg.last_outcome.status == 2 and 0 < pg.last_outcome.iterations < 100
+    pg.close()
+    pg = B200ProgramGenerator(problem=prob, evaluation_timeout=300)
+    t, cf, its = pg.generate_and_evaluate(slow, storages, 5, 9, "", evaluation_samples=1)
+    assert pg.last_outcome.status == 0 and cf < 1e100
+    pg.close()
+
+
+def test_infrastructure_errors_are_not_fitness_values(cuda_backend):
+    """A statement the library does not implement must raise, not masquerade as a diverged individual."""
+    from evostencils_b200 import backend, cycles, oplist as ol
+    prob = problems.Poisson2D(3, 5)
+    pg = B200ProgramGenerator(problem=prob)
+    unk = ((0, (0, 0)), (0, (1, 0)))
+    prog = cycles.build_program(prob, [ol.Op(ol.OP_SMOOTH, 5, mode=ol.MODE_REDBLACK, omega=1.0, unknowns=unk)])
+    with pytest.raises(backend.BackendError) as info:
+        pg._evaluate_program(prog, 3, None, 1e100, 1)
+    assert info.value.status == backend.ERR_UNSUPPORTED and info.value.infrastructure
+    pg.close()
+
+
+def test_population_time_objective_is_contention_free(cuda_backend):
+    """solo_timing (default): the time entry of a batch member is measured with the GPU to itself and is
+    comparable with generate_and_evaluate; cf / iterations are unchanged by it."""
+    prob = problems.Poisson2D(5, 9)
+    pg = B200ProgramGenerator(problem=prob)
+    storages = pg.generate_storage(5, 9, pg.finest_grid)
+    rng = random.Random(3)
+    strings = [tree.random_individual(prob, rng) for _ in range(32)]
+    trees = [tree.build_tree(prob, s) for s in strings]
+    pg.evaluate_population(trees[:4])                                      # warm-up
+    solo, _ = pg.evaluate_population(trees, max_in_flight=32, solo_timing=True)
+    crowd, _ = pg.evaluate_population(trees, max_in_flight=32, solo_timing=False)
+    single = [pg.generate_and_evaluate(t, storages, 5, 9, "", evaluation_samples=3) for t in trees]
+    checked = 0
+    for a, b, c in zip(solo, crowd, single):
+        assert a[1] == b[1] == c[1] or (np.isnan(a[1]) and np.isnan(c[1]))
+        assert a[2] == b[2] == c[2]
+        if c[2] < 100 and c[1] < 1:
+            checked += 1
+            assert abs(a[0] - c[0]) <= 0.25 * c[0] + 0.05, (a[0], c[0])     # ms; launch jitter of a short solve
+    assert checked >= 4
+    pg.close()

@@ -1,0 +1,145 @@
+"""Kernel variants and modes that the default configuration does not select: every 3-D RB-GS kernel (lean tile
+kernel, register-carried pair-column kernel, generic multi-stage kernel, two sweeps fused per launch) and the
+lexicographic in-place sweeps of the reference's model-based mode (exastencils.py:64-70, :781-822) -- all
+bit-identical to the plain loops of the oracle."""
+import numpy as np
+import pytest
+
+from evostencils_b200 import cycles, oplist as ol, problems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def option(cuda_backend):
+    """Set tuning switches of the library for one test and restore them afterwards."""
+    saved = {}
+
+    def setter(name, value):
+        if name not in saved:
+            saved[name] = cuda_backend.get_option(name)
+        cuda_backend.set_option(name, value)
+
+    yield setter
+    for name, value in saved.items():
+        cuda_backend.set_option(name, value)
+
+
+def _equal(gc, oc, prob, levels, bufs):
+    for l in levels:
+        for b in bufs:
+            for f in range(prob.n_fields):
+                x, y = gc.get_field(l, b, f), oc.get_field(l, b, f)
+                assert np.array_equal(x, y), f"level {l} buf {b} field {f}: max diff {np.abs(x - y).max()}"
+
+
+def test_option_api(cuda_backend, option):
+    assert cuda_backend.get_option("EVO_RB_FUSE2") in (0, 1)
+    option("EVO_RB_VARIANT", 30)
+    assert cuda_backend.get_option("EVO_RB_VARIANT") == 30
+    with pytest.raises(cuda_backend.BackendError):
+        cuda_backend.set_option("EVO_NO_SUCH_SWITCH", 1)
+
+
+# variants: 0 default, 10 lean, 20 generic multi-stage, 30-35 pair-column kernels
+@pytest.mark.parametrize("variant", [0, 10, 20, 30, 31, 32, 33, 34, 35])
+@pytest.mark.parametrize("level,sweeps", [(5, 1), (6, 3), (7, 2)])
+def test_rbgs_kernel_variants_bit_exact(cuda_backend, oracle_mod, option, variant, level, sweeps):
+    option("EVO_RB_VARIANT", variant)
+    prob = problems.Poisson3D(level - 1, level)
+    z = (0, 0, 0)
+    ops = [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_JACOBI, omega=0.9, unknowns=((0, z),))]
+    ops += [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_REDBLACK, omega=1.25, unknowns=((0, z),)) for _ in range(sweeps)]
+    ops += [ol.Op(ol.OP_RESIDUAL, level, dst=ol.BUF_RES)]
+    prog = cycles.build_program(prob, ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [level], (ol.BUF_SOL, ol.BUF_RES))
+
+
+@pytest.mark.parametrize("variant", [0, 30])
+@pytest.mark.parametrize("fuse2", [0, 1])
+def test_rbgs_two_sweeps_per_launch(cuda_backend, oracle_mod, option, variant, fuse2):
+    """EVO_RB_FUSE2: consecutive identical sweeps are executed two per launch (temporal blocking); the solve
+    history must not change."""
+    option("EVO_RB_VARIANT", variant)
+    option("EVO_RB_FUSE2", fuse2)
+    prob = problems.Poisson3D(2, 6)
+    prog = cycles.default_solver_cycle(prob)       # V(2,1): the two pre-smoothing sweeps are merged
+    s = prob.settings
+    a = cuda_backend.DeviceProblem(prob).build(prog).solve(s.tol, s.max_iters, 1)
+    b = oracle_mod.OracleProblem(prob).build(prog).solve(s.tol, s.max_iters, 1)
+    assert a.iterations == b.iterations
+    assert np.array_equal(a.residuals, b.residuals)
+
+
+# ---- lexicographic in-place sweeps ---------------------------------------------------------------------------
+def _lex_ops(level, unknowns, n=2, omega=0.9):
+    return [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_LEX, omega=omega, unknowns=unknowns) for _ in range(n)] + \
+           [ol.Op(ol.OP_RESIDUAL, level, dst=ol.BUF_RES)]
+
+
+@pytest.mark.parametrize("lex_variant", [0, 1])
+@pytest.mark.parametrize("name,level", [("p2", 5), ("p2", 7), ("p3", 4), ("p3", 5), ("el", 5)])
+def test_lexicographic_pointwise_bit_exact(cuda_backend, oracle_mod, option, name, level, lex_variant):
+    option("EVO_LEX_VARIANT", lex_variant)
+    prob = {"p2": problems.Poisson2D, "p3": problems.Poisson3D, "el": problems.LinearElasticity2D}[name](level - 1, level)
+    z = (0,) * prob.dim
+    if prob.n_fields == 1:
+        ops = _lex_ops(level, ((0, z),))
+    else:   # decoupled (one statement per field) and collective
+        ops = [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_LEX, omega=0.8, unknowns=((0, z),)),
+               ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_LEX, omega=0.8, unknowns=((1, z),))] + _lex_ops(level, ((0, z), (1, z)))
+    prog = cycles.build_program(prob, ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [level], (ol.BUF_SOL, ol.BUF_RES))
+
+
+@pytest.mark.parametrize("shape", [(2, 1), (1, 2), (2, 2), (3, 1), (1, 3)])
+def test_lexicographic_block_bit_exact(cuda_backend, oracle_mod, shape):
+    """Overlapping blocks written in place: the hyperplane skew has to respect the wider footprint."""
+    prob = problems.Poisson2D(4, 5)
+    unk = tuple((0, (i, j)) for i in range(shape[0]) for j in range(shape[1]))
+    prog = cycles.build_program(prob, _lex_ops(5, unk, n=2, omega=0.7))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    gc.apply(1)
+    oc.apply(1)
+    _equal(gc, oc, prob, [5], (ol.BUF_SOL, ol.BUF_RES))
+
+
+def test_lexicographic_block_3d(cuda_backend, oracle_mod):
+    prob = problems.Poisson3D(3, 4)
+    unk = ((0, (0, 0, 0)), (0, (1, 0, 0)), (0, (0, 0, 1)))
+    prog = cycles.build_program(prob, _lex_ops(4, unk, n=1, omega=0.8))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    gc.apply(1)
+    oc.apply(1)
+    _equal(gc, oc, prob, [4], (ol.BUF_SOL, ol.BUF_RES))
+
+
+def test_model_based_mode_through_the_drop_in(cuda_backend, oracle_mod):
+    """model_based_estimation=True (the default of the reference's scripts/optimize.py) lowers every
+    Single-partitioned smoother to an in-place lexicographic sweep: the drop-in must evaluate it (not refuse it)
+    and agree with the oracle."""
+    from evostencils_b200 import fitness, tree
+    from evostencils_b200.program_generator import B200ProgramGenerator
+    prob = problems.Poisson2D(3, 6)
+    gen = B200ProgramGenerator(problem=prob, model_based_estimation=True)
+    expr = tree.build_tree(prob, tree.v_cycle_individual(prob.max_level - prob.min_level, pre=2, post=1, partitioning="single"))
+    prog = gen._finalise(gen.lower(expr, prob.min_level))
+    assert any(o.code == ol.OP_SMOOTH and o.mode == ol.MODE_LEX for o in prog.ops)
+    t, cf, its = gen.generate_and_evaluate(expr, gen.generate_storage(3, 6), 3, 6, "", evaluation_samples=1)
+    ref = oracle_mod.OracleProblem(prob).build(prog).solve(prob.settings.tol, prob.settings.max_iters, 1)
+    rt, rcf, rits = fitness.fitness_from_history(ref.residuals, ref.time_ms, prob.settings.max_iters)
+    assert its == rits and abs(cf - rcf) < 1e-12 and cf < 1
+    assert np.array_equal(gen.last_outcome.residuals, ref.residuals)
+    gen.close()
