@@ -82,6 +82,9 @@ def _sympify(expr: str, symbols: Dict[str, object]):
     return parse_expr(expr, local_dict=local)
 
 
+_CODE_CACHE: Dict[str, object] = {}      # compiled expressions (module level: problems stay picklable)
+
+
 class ExaProblem(Problem):
     """A problem read from ExaSlang layer-2/3 files."""
 
@@ -92,7 +95,6 @@ class ExaProblem(Problem):
         self._stencils, self._equations, self._globals = stencils, equations, dict(globals_)
         self._boundary, self._rhs_expr = boundary, rhs_expr
         self.parameters = {k: float(v) for k, v in globals_.items() if _is_number(v)}
-        self._lambdas = {}
 
     def _symbols(self):
         import sympy
@@ -104,13 +106,27 @@ class ExaProblem(Problem):
             syms[k] = sympy.sympify(self.parameters.get(k, v))
         return syms
 
+    def _namespace(self, extra=None):
+        """Names an ExaSlang expression may use, for LITERAL evaluation (left to right, like the generated C++; a
+        symbolic round trip would reorder the operands and change the last bit)."""
+        import keyword
+        ns = {"PI": math.pi, "sin": np.sin, "cos": np.cos, "exp": np.exp, "sqrt": np.sqrt, "fabs": np.abs,
+              "max": np.maximum, "min": np.minimum, "__builtins__": {}}
+        for k, v in self._globals.items():
+            val = self.parameters.get(k, v)
+            if not _is_number(val):
+                val = eval(_pythonise(str(val)), dict(ns))      # noqa: S307 - a global defined by other globals
+            ns[k + "__" if keyword.iskeyword(k) else k] = float(val) if not isinstance(val, complex) else val
+        if extra:
+            ns.update(extra)
+        return ns
+
     def _operator_stencil(self, name: str, level: int) -> Dict[Tuple[int, ...], complex]:
-        import sympy
         h = self.spacing(level)
-        subs = {sympy.Symbol(f"vf_gridWidth_{a}"): h for a in "xyz"}
+        ns = self._namespace({f"vf_gridWidth_{a}": h for a in "xyz"})
         out = {}
         for offset, expr in self._stencils[name]:
-            val = complex(_sympify(expr, self._symbols()).subs(subs).evalf())
+            val = complex(eval(_pythonise(expr), ns))           # noqa: S307 - arithmetic of the user's problem file
             out[offset] = out.get(offset, 0) + val
         return out
 
@@ -139,13 +155,14 @@ class ExaProblem(Problem):
         return table.real.copy() if np.all(table.imag == 0) else table
 
     def _eval(self, key, expr, coords):
-        import sympy
-        if key not in self._lambdas:
-            e = _sympify(expr, self._symbols())
-            syms = [sympy.Symbol(a) for a in "xyz"[: self.dim]]
-            self._lambdas[key] = (sympy.lambdify(syms, e, "numpy"), e.free_symbols)
-        fn, _ = self._lambdas[key]
-        val = fn(*coords)
+        code = _CODE_CACHE.get(expr)
+        if code is None:
+            code = _CODE_CACHE[expr] = compile(_pythonise(expr), "<exaslang>", "eval")
+        extra = {}
+        for a, c in zip("xyz", coords):
+            for base in ("vf_nodePos", "vf_boundaryPos", "vf_boundaryCoord", "vf_nodePosition"):
+                extra[f"{base}_{a}"] = c
+        val = eval(code, self._namespace(extra))                 # noqa: S307 - arithmetic of the user's problem file
         return np.broadcast_to(np.asarray(val, dtype=np.float64), np.broadcast(*coords).shape).copy()
 
     def boundary_value(self, fi, level, *coords):
@@ -161,6 +178,14 @@ class ExaProblem(Problem):
         if expr is None or _is_zero(expr):
             return None
         return self._eval(("rhs", fi), expr, coords)
+
+
+def _pythonise(expr: str) -> str:
+    """ExaSlang arithmetic -> Python source: ``^`` is the power operator, identifiers that are Python keywords (the
+    elasticity file has a global named ``lambda``) get a trailing ``__``."""
+    import keyword
+    expr = expr.replace("^", "**")
+    return re.sub(r"[A-Za-z_]\w*", lambda m: m.group(0) + "__" if keyword.iskeyword(m.group(0)) else m.group(0), expr)
 
 
 def _is_number(s) -> bool:

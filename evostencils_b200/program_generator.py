@@ -27,25 +27,44 @@ from .problems import Problem
 JACOBI_COMPAT_MODES = ("intended", "exastencils_v1_1_noop")
 
 
+# problems the reference defines on ExaSlang layer 3 / 4 only (no .exa2 to read): hand-written descriptors
+_LAYER34_DESCRIPTORS = {"2D_FD_Helmholtz_fromL3": problems.Helmholtz2D, "FAS_2D_Basic": problems.FAS2D}
+# the shipped layer-2 problems, used only when the configuration files are not on disk
+_SHIPPED_DESCRIPTORS = {"2D_FD_Poisson_fromL2": problems.Poisson2D, "3D_FD_Poisson_fromL2": problems.Poisson3D,
+                        "2D_FD_LinearElasticity_fromL2": problems.LinearElasticity2D, **_LAYER34_DESCRIPTORS}
+
+
 def _problem_from_paths(settings_path: Optional[str], knowledge_path: Optional[str], base_path: Optional[str]) -> Problem:
-    """Map the reference's configuration files to a problem descriptor.  Levels/dimension come from the
-    .knowledge file when it exists (same keys as parser.extract_knowledge_information, parser.py:114-125)."""
-    text = f"{settings_path or ''} {knowledge_path or ''}"
-    if "Helmholtz" in text:
-        prob: Problem = problems.Helmholtz2D()
-    elif "LinearElasticity" in text:
-        prob = problems.LinearElasticity2D()
-    elif "FAS" in text:
-        prob = problems.FAS2D()
-    elif "3D_FD_Poisson" in text:
-        prob = problems.Poisson3D()
-    elif "Poisson" in text:
-        prob = problems.Poisson2D()
+    """The problem the reference's configuration triple describes (exastencils.py:39-110 + parser.py:25-143, which
+    need the Java generator's debug output): the ``.settings`` file names the configuration, its ``.exa2`` / ``.exa3``
+    files are read by :mod:`evostencils_b200.frontend` (equations, operators, boundary and right-hand-side
+    expressions, globals, solver block), the ``.knowledge`` file gives dimensionality and levels (parser.py:114-125).
+    Any user problem written on layer 2 works, not only the shipped ones; the two shipped problems that exist on
+    layer 3 / 4 only (Helmholtz, FAS) use their descriptors."""
+    from . import frontend
+    base = base_path or ""
+    sfile = os.path.join(base, settings_path) if settings_path else None
+    kfile = os.path.join(base, knowledge_path) if knowledge_path else None
+    if sfile and os.path.isfile(sfile):
+        settings = frontend.read_settings(sfile)
+        name = settings.get("configName")
+        if not name:
+            raise RuntimeError(f"{sfile}: configName missing")
+        prefix = os.path.join(base, settings.get("basePathPrefix", "."))
+        if os.path.isfile(os.path.join(prefix, f"{name}.exa2")):
+            if not (kfile and os.path.isfile(kfile)):
+                raise RuntimeError(f"knowledge file '{kfile}' not found")
+            return frontend.load_problem(base, settings_path, knowledge_path)
+        if name not in _LAYER34_DESCRIPTORS:
+            raise RuntimeError(f"configuration '{name}' has no layer-2 file ({name}.exa2) and no descriptor")
+        prob: Problem = _LAYER34_DESCRIPTORS[name]()
     else:
-        raise RuntimeError(f"no problem descriptor for settings '{settings_path}' / knowledge '{knowledge_path}'")
-    if knowledge_path and base_path and os.path.exists(os.path.join(base_path, knowledge_path)):
-        from .frontend import read_knowledge
-        dim, lo, hi = read_knowledge(os.path.join(base_path, knowledge_path))
+        stem = os.path.basename(settings_path or knowledge_path or "").split(".")[0].strip()
+        if stem not in _SHIPPED_DESCRIPTORS:
+            raise RuntimeError(f"settings file '{sfile}' not found and '{stem}' is not a shipped configuration")
+        prob = _SHIPPED_DESCRIPTORS[stem]()
+    if kfile and os.path.isfile(kfile):
+        dim, lo, hi = frontend.read_knowledge(kfile)
         if dim != prob.dim:
             raise RuntimeError("dimensionality of the knowledge file does not match the problem")
         prob = prob.with_levels(lo, hi)

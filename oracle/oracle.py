@@ -117,7 +117,7 @@ class OracleCycle:
         _check(self._lib.orc_residual_norm(self.problem._h, C.byref(v)), "orc_residual_norm")
         return float(v.value)
 
-    def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0) -> SolveOutcome:
+    def solve(self, tol: float, max_iters: int, samples: int = 1, flags: int = 0, timeout_ms: int = 0) -> SolveOutcome:
         self._bind()
         prm = ol.CEvoSolveParams(tol, max_iters, samples, flags, 0)
         res = ol.CEvoSolveResult()
@@ -126,7 +126,7 @@ class OracleCycle:
                                    hist.ctypes.data_as(C.POINTER(C.c_double))), "orc_solve")
         return SolveOutcome(res, hist)
 
-    def helmholtz_solve(self, tol: float, max_iters: int, samples: int = 1) -> SolveOutcome:
+    def helmholtz_solve(self, tol: float, max_iters: int, samples: int = 1, timeout_ms: int = 0) -> SolveOutcome:
         """Outer preconditioned BiCGStab with this cycle as the preconditioner (Helmholtz problems)."""
         self._bind()
         prob = self.problem.problem
