@@ -1,14 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the evaluate hot path (contract: see the task statement).
 
-A *step* is one fitness evaluation = one pass of the hot path: the generated solver's outer loop
-(residual, V-cycles until ``res < 1e-12 res0``) for one individual on synthetic (analytic) input that
-is already resident in HBM.  Default workload (BASELINE.json configs[1]): Poisson 3D 7-point, 513^3
-finest grid, levels 9..2, the problem's own V(2,1) red-black Gauss-Seidel cycle (omega 1.25) + CG.
+BASELINE.json's metric is "evolved-cycle fitness evals/s on 8xB200; smoother GDOF/s vs HBM roofline".  The default
+line therefore carries both halves:
 
-  python bench.py --gpus 1 --steps 5 --warmup 3            our arm (CUDA library through the C-ABI)
-  python bench.py --impl reference ...                     the CPU arm: oracle port on the host cores
-  torchrun ... bench.py --gpus N ...                       one rank per GPU, population-sharded
+* ``value`` / ``e2e``: ONE G3P GENERATION (configs[4]) -- 256 evolved cycles, half Poisson 2D (513^2, levels 9..5), half
+  LinearElasticity (257^2, 2 fields, levels 8..4), sharded round-robin over the N GPUs (``i % N == rank``, reference:
+  optimization/program.py:534-538), fitness tuples gathered on the host.  A *step* is one generation = 256 fitness
+  evaluations (each one: lower the tree, run the generated solver's outer loop to 1e-12, return (ms, cf, iterations)).
+  The work is fixed as N grows: ``scaling = "strong"``.
+* ``grid513``: ONE evaluation of the Poisson 3D 513^3 V(2,1) red-black GS cycle (configs[1]) -- on one GPU at N = 1, the
+  same grid domain-decomposed into z-slabs over all N GPUs at N > 1 (halo exchange over NCCL; strong scaling), with the
+  residual history compared bit for bit against the single-GPU run.
+* ``roofline``: the dominant kernel of the 513^3 evaluation (finest-level RB-GS sweep) against the measured HBM peak.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            our arm (CUDA library through the C-ABI / drop-in generator)
+  python bench.py --impl reference ...                     the CPU arm: oracle port on the host cores, same workload
+  torchrun ... bench.py --gpus N ...                       one rank per GPU
+  python bench.py --workload poisson3d_513 [--no-graph]    single-workload modes (profiling, other BASELINE configs)
 
 Prints ONE JSON line (rank 0).
 """
@@ -32,6 +41,12 @@ import numpy as np  # noqa: E402
 from evostencils_b200 import cycles, fitness, oplist as ol, problems  # noqa: E402
 
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+DEFAULT_WORKLOAD = "generation256+grid513"
+METRIC = ("evolved-cycle fitness evals/s (one G3P generation of 256 evolved cycles = 256 evals per step; "
+          "one eval = lower the tree + solve to 1e-12 with the cycle); smoother GDOF/s in roofline")
+GRID_WORKLOAD = "poisson3d_513"
+# individuals of the generation the CPU arm solves per step (2 Poisson 2D + 2 elasticity, evenly spread)
+CPU_SAMPLE = (0, 99, 132, 231)
 
 
 def measured_peak():
@@ -67,6 +82,22 @@ def make_workload(name: str, fuse: bool = True):
         from evostencils_b200 import lowering
         prog = lowering.optimise(prog)
     return prob, prog
+
+
+def workload_tree(name: str, prob):
+    """The same cycle as a grammar individual (what Optimizer hands to generate_and_evaluate)."""
+    from evostencils_b200 import tree
+    s_ = prob.settings
+    if name.endswith("_w"):
+        return None
+    # weight index of the solver block's damping on the grammar's grid linspace(0.1, 1.9, 37)
+    grid = np.linspace(0.1, 1.9, 37)
+    idx = int(np.argmin(np.abs(grid - s_.damping)))
+    if abs(grid[idx] - s_.damping) > 1e-12:
+        return None
+    string = tree.v_cycle_individual(prob.max_level - prob.min_level, s_.num_pre, s_.num_post, idx,
+                                     partitioning="red_black" if s_.red_black else "single", cgc_weight_index=18)
+    return tree.build_tree(prob, string)
 
 
 class ClockSampler:
@@ -123,344 +154,101 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_arm_sample(workload: str, threads: int | None = None):
-    """Oracle (CPU port of the generated solver) on a bounded sample of the workload.
+class Dist:
+    """torch.distributed plumbing (NCCL, one rank per GPU); a no-op at world size 1."""
 
-    Sample = ONE V-cycle + residual norm on the largest level that fits comfortably in host memory;
-    the iteration count of the full solve comes from running the same cycle to convergence on a
-    65^3 / 129^2-class grid (multigrid convergence is h-independent; the GPU parity tests assert the
-    counts agree).  Returns (evals_per_s, dict)."""
+    def __init__(self, rank, world, local_rank):
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dist = None
+        self.torch = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max(self, *vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def sum_int(self, v):
+        if self.dist is None:
+            return int(v)
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C/OpenMP restatement of the generated solver) on the host cores
+def _cpu_threads(threads=None):
+    """All host threads unless told otherwise.  torchrun exports OMP_NUM_THREADS=1 to its workers: that is a launcher
+    default, not a property of the reference, so the thread count is set explicitly."""
+    from oracle import oracle as orc
+    n = threads or os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    orc.set_num_threads(max(1, n))
+    return orc.num_threads()
+
+
+def cpu_grid_sample(workload: str, threads=None, budget_s: float = 12.0):
+    """Oracle on the grid workload: ONE COMPLETE SOLVE (initial residual, V-cycles to 1e-12) at the finest level whose
+    solve fits the time budget, scaled to the workload's DOF count.  Multigrid cost is linear in the DOFs and the
+    iteration count is h-independent (the parity tests assert equal counts), so the only extrapolation is the DOF
+    ratio; when level == the workload's finest level there is none."""
     from oracle import oracle as orc
     prob, _ = make_workload(workload)
-    if threads:
-        orc.set_num_threads(threads)
-    nthreads = orc.num_threads()
+    nthreads = _cpu_threads(threads)
     try:
         avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
     except (ValueError, OSError):
         avail = 16 << 30
-    level = prob.max_level
-    while level > prob.min_level + 1:
-        need = 5.5 * 8 * (prob.nodes(level) ** prob.dim) * prob.n_fields
-        if need < 0.4 * avail and need < (24 << 30):
+    # probe: one full solve two levels below, predicts the cost of the finer ones (x 2^dim per level)
+    probe_level = max(prob.min_level + 1, prob.max_level - 2)
+    probe = prob.with_levels(prob.min_level, probe_level)
+    oc = orc.OracleProblem(probe).build(cycles.default_solver_cycle(probe))
+    oc.solve(probe.settings.tol, probe.settings.max_iters, 1)
+    t0 = time.perf_counter()
+    ref = oc.solve(probe.settings.tol, probe.settings.max_iters, 1)
+    t_probe = time.perf_counter() - t0
+    level, t_solve, its = probe_level, t_probe, ref.iterations
+    for cand in range(prob.max_level, probe_level, -1):
+        need = 5.5 * 8 * (prob.nodes(cand) ** prob.dim) * prob.n_fields
+        predicted = t_probe * (2 ** prob.dim) ** (cand - probe_level)
+        if need < 0.4 * avail and need < (24 << 30) and predicted <= budget_s:
+            sp = prob.with_levels(prob.min_level, cand)
+            oc = orc.OracleProblem(sp).build(cycles.default_solver_cycle(sp))
+            t0 = time.perf_counter()
+            ref = oc.solve(sp.settings.tol, sp.settings.max_iters, 1)
+            t_solve, level, its = time.perf_counter() - t0, cand, ref.iterations
             break
-        level -= 1
-    sample_prob = prob.with_levels(prob.min_level, level)
-    prog = cycles.default_solver_cycle(sample_prob)
-    oc = orc.OracleProblem(sample_prob).build(prog)
-    oc.apply(1)                              # warm the pages
-    t0 = time.perf_counter()
-    oc.apply(1)
-    oc.residual_norm()
-    t_cycle = time.perf_counter() - t0
-    # iterations to convergence on a small grid of the same problem
-    small_level = min(level, 6 if prob.dim == 3 else 8)
-    small = prob.with_levels(prob.min_level, small_level)
-    its = orc.OracleProblem(small).build(cycles.default_solver_cycle(small)).solve(
-        small.settings.tol, small.settings.max_iters, 1).iterations
     scale = float((prob.nodes(prob.max_level) - 2) ** prob.dim) / float((prob.nodes(level) - 2) ** prob.dim)
-    t_eval = t_cycle * scale * its
-    # the reference's own OpenMP setting is 4 threads (example_problems/lib/parallelization_pureOmp.knowledge:3)
-    value_4 = None
-    if threads is None and nthreads > 4:
-        orc.set_num_threads(4)
-        t0 = time.perf_counter()
-        oc.apply(1)
-        oc.residual_norm()
-        value_4 = 1.0 / ((time.perf_counter() - t0) * scale * its)
-        orc.set_num_threads(nthreads)
-    info = {"value": 1.0 / t_eval, "unit": "evals/s", "cores": nthreads, "kind": "port",
-            "sample": f"1 V-cycle + residual norm of the workload's cycle at level {level} "
-                      f"({prob.nodes(level)}^{prob.dim} nodes, {t_cycle * 1e3:.1f} ms) x {scale:.3g} (DOF ratio to "
-                      f"level {prob.max_level}) x {its} iterations (full solve at level {small_level}); "
+    return {"value": 1.0 / (t_solve * scale), "unit": "evals/s", "cores": nthreads, "kind": "port",
+            "sample": f"one complete solve ({its} iterations to 1e-12) of the workload's cycle at level {level} "
+                      f"({prob.nodes(level)}^{prob.dim} nodes, {t_solve:.2f} s) x {scale:.3g} (DOF ratio to level {prob.max_level}); "
                       f"oracle = C/OpenMP restatement, gcc -O3 -fopenmp, {nthreads} threads",
-            "ms_per_cycle_at_sample_level": t_cycle * 1e3, "iterations": its, "value_4_threads": value_4}
-    return info
+            "seconds_per_solve_at_sample_level": t_solve, "iterations": its}
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    prob, _ = make_workload(args.workload)
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        info = cpu_arm_sample(args.workload)
-        if i >= args.warmup:
-            vals.append(info["value"])
-        if i == 0 and args.warmup + args.steps > 1 and 1.0 / info["value"] > 0:
-            pass
-    value = statistics.mean(vals)
-    info["value"] = value
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, prob, world),
-            "cpu_baseline": info,
-            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
-
-
-METRIC = "evolved-cycle fitness evals/s (one eval = solve to 1e-12 with the cycle); smoother GDOF/s in roofline"
-
-
-def workload_config(name, prob, world):
-    return {"workload": name, "problem": prob.name, "finest_nodes": f"{prob.nodes(prob.max_level)}^{prob.dim}",
-            "levels": f"{prob.max_level}..{prob.min_level}",
-            "cycle": f"{'W' if name.endswith('_w') else 'V'}({prob.settings.num_pre},{prob.settings.num_post}) red-black GS omega={prob.settings.damping} + CG",
-            "tol": prob.settings.tol, "max_iters": prob.settings.max_iters,
-            "parallelism": "1 GPU" if world == 1 else f"population-sharded x{world} (one evaluation per GPU per step)",
-            "l2_policy": "inputs larger than L2 (finest fields 1.1 GB each)" if prob.dim == 3 and prob.max_level >= 8
-            else "working set fits L2 (latency-bound regime; no flush)"}
-
-
-def run_ours(args, rank, world, local_rank):
-    from evostencils_b200 import backend
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_
-        dist = dist_
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    prob, prog = make_workload(args.workload)
-    dev = backend.DeviceProblem(prob, device=local_rank)
-    cyc = dev.build(prog)
-    s = prob.settings
-
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident throughput ("value") -------------------------------------------------------
-    flags = ol.SOLVE_NO_GRAPH if args.no_graph else 0
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()          # nvidia-smi needs ~0.2 s to start: begin before the warm-up, sample through the timed region
-    for _ in range(args.warmup):
-        out = cyc.solve(s.tol, s.max_iters, 1, flags)
-    barrier()
-    t_dev = 0.0
-    launches = 0
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = cyc.solve(s.tol, s.max_iters, 1, flags)
-        t_dev += out.time_ms
-        launches += out.kernel_launches
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        import torch
-        t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev = float(t.item())
-        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        launches = int(ln.item())
-    evals = args.steps * world
-    value = evals / (t_dev * 1e-3)
-    ndof = float((prob.nodes(prob.max_level) - 2) ** prob.dim) * prob.n_fields
-    cf = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters)[1]
-
-    # ---- end to end through the host API: build (lowered op list -> device), solve, read back --------
-    h2d = len(prog.ops) * 160 + len(prog.operators) * (8 + 2 * 2 * 27 * 2 * 8)
-    d2h = (s.max_iters + 1) * 8 + 48
-    for _ in range(min(args.warmup, 2)):
-        c2 = dev.build(prog); c2.solve(s.tol, s.max_iters, 1); c2.close()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        c2 = dev.build(prog)
-        o2 = c2.solve(s.tol, s.max_iters, 1)
-        fitness.fitness_from_history(o2.residuals, o2.time_ms, s.max_iters)
-        c2.close()
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = evals / t_e2e
-
-    # ---- roofline of the dominant kernel: finest-level RB-GS sweep -----------------------------------
-    roof = None
-    cpu = None
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        zero = (0,) * prob.dim
-        sm_op = ol.Op(ol.OP_SMOOTH, prob.max_level, mode=ol.MODE_REDBLACK, omega=s.damping,
-                      unknowns=tuple((f, zero) for f in range(prob.n_fields)))
-        ms, n_launch = cyc.profile_op(sm_op, repeat=10)
-        alg_bytes = 24.0 * ndof                      # SURVEY.md 8(d): read u, f, write u per full sweep
-        achieved = alg_bytes / (ms * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this size
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as fh:
-                traffic = json.load(fh).get(args.workload, {}).get("dram_bytes_per_launch")
-        except (OSError, ValueError):
-            pass
-        roof = {"bound": "hbm", "kernel": "RB-GS sweep, finest level (both colours)", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": ms, "launches_per_sweep": n_launch,
-                "smoother_gdof_s": ndof / (ms * 1e-3) / 1e9}
-        other = {}
-        for nm, op, b in (("residual", ol.Op(ol.OP_RESIDUAL, prob.max_level, dst=ol.BUF_RES), 24.0),
-                          ("restrict", ol.Op(ol.OP_RESTRICT, prob.max_level, dst=ol.BUF_RHS, src=ol.BUF_RES),
-                           8.0 + 8.0 / 2 ** prob.dim),
-                          ("prolong_add", ol.Op(ol.OP_PROLONG_ADD, prob.max_level, src=ol.BUF_SOL, omega=1.0),
-                           16.0 + 8.0 / 2 ** prob.dim)):
-            try:
-                m2, _ = cyc.profile_op(op, repeat=10)
-                other[nm] = {"ms": m2, "GB/s": b * ndof / (m2 * 1e-3) / 1e9, "frac": b * ndof / (m2 * 1e-3) / 1e9 / peak}
-            except Exception as e:   # pragma: no cover
-                other[nm] = {"error": str(e)}
-        roof["other_kernels"] = other
-        if not args.no_cpu_baseline and world == 1:
-            cpu = cpu_arm_sample(args.workload)
-    # ---- N > 1: the same evaluation decomposed over the GPUs (SURVEY.md 8e.2), reported beside the weak number ----
-    dd_info = None
-    line_state = {}
-
-    def emit_line():
-        if rank == 0 and not line_state.get("printed"):
-            line_state["printed"] = True
-            line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-                    "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
-                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "domain_decomposition": dd_info,
-                    "config": workload_config(args.workload, prob, world),
-                    "iterations_per_eval": out.iterations, "convergence_factor": cf,
-                    "cycle_gdof_s": ndof * out.iterations * evals / (t_dev * 1e-3) / 1e9,
-                    "ms_per_cycle": t_dev / args.steps / max(out.iterations, 1),
-                    "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                            "note": "build (op list + operator tables H2D) + solve + history D2H through the C-ABI; "
-                                    "the reference-facing call carries no field data (the problem is analytic)"},
-                    "gpu_launches": launches, "wall_s_timed_region": t_wall, "clocks": clocks,
-                    "roofline": roof, "cpu_baseline": cpu}
-            print(json.dumps(line), flush=True)
-
-    if dist is not None and prob.dim == 3 and not args.no_domain:
-        import signal
-        import torch
-        from evostencils_b200 import domain
-
-        def give_up(signum, frame):   # the secondary measurement must never cost the primary line
-            nonlocal dd_info
-            dd_info = {"error": "domain-decomposed measurement did not finish within the time limit"}
-            emit_line()
-            os._exit(0)
-
-        signal.signal(signal.SIGALRM, give_up)
-        signal.alarm(int(os.environ.get("EVO_DOMAIN_TIME_LIMIT", "240")))
-        cyc.close()
-        solver = domain.DomainSolver.distributed(prob, prog, rank, world, local_rank)
-        solver.overlap = not args.domain_no_overlap
-        dd_solve = solver.solve if args.domain_eager else solver.solve_captured
-        o3 = solver.solve(s.tol, s.max_iters)          # creates the NCCL communicators (not capturable)
-        for _ in range(2):
-            o3 = dd_solve(s.tol, s.max_iters)
-        barrier()
-        t_dd = 0.0
-        for _ in range(args.steps):
-            o3 = dd_solve(s.tol, s.max_iters)
-            t_dd += o3.time_ms
-        barrier()
-        t = torch.tensor([t_dd], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dd = float(t.item())
-        dd_info = {"value": args.steps / (t_dd * 1e-3), "unit": "evals/s", "scaling": "strong", "ms_per_eval": t_dd / args.steps,
-                   "iterations": o3.iterations, "identical_history": bool(np.array_equal(o3.residuals, out.residuals)),
-                   "halo_exchanges_per_eval": o3.exchanges, "overlap": solver.overlap, "levels_distributed": f"{prob.max_level}..{solver.layout.lc}",
-                   "note": "ONE evaluation split into z-slabs over all GPUs, NCCL send/recv halos; "
-                           + ("host-orchestrated statements" if args.domain_eager else
-                              "each iteration (kernels + exchanges) replayed as one CUDA graph")}
-        solver.close()
-        signal.alarm(0)
-    emit_line()
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-# ------------------------------------------------------------------------------------------------
-# SURVEY.md 8e.2: ONE evaluation spread over the GPUs (z-slab domain decomposition, halo exchange over NCCL).
-# Strong scaling; results are bit-identical to the single-GPU evaluation (tests/test_gpu_domain.py).
-def run_domain(args, rank, world, local_rank):
-    import torch
-    from evostencils_b200 import domain
-    dist = None
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    prob, prog = make_workload(args.workload)
-    s = prob.settings
-    slabs = world if world > 1 else max(1, args.slabs)
-    if world > 1:
-        solver = domain.DomainSolver.distributed(prob, prog, rank, world, local_rank, lc=args.lc or None)
-    else:
-        solver = domain.DomainSolver.emulate(prob, prog, slabs, lc=args.lc or None)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    solver.overlap = not args.domain_no_overlap
-    dd_solve = solver.solve if (args.domain_eager or world == 1) else solver.solve_captured
-    out = solver.solve(s.tol, s.max_iters)
-    for _ in range(args.warmup):
-        out = dd_solve(s.tol, s.max_iters)
-    barrier()
-    t_dev = 0.0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = dd_solve(s.tol, s.max_iters)
-        t_dev += out.time_ms
-    barrier()
-    t_wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev = float(t.item())
-    value = args.steps / (t_dev * 1e-3)
-    ndof = float((prob.nodes(prob.max_level) - 2) ** prob.dim)
-    cf = fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters)[1]
-    if rank == 0:
-        cfg = workload_config(args.workload, prob, world)
-        cfg["parallelism"] = (f"z-slab domain decomposition x{slabs} "
-                              f"({'NCCL send/recv' if world > 1 else 'slabs emulated on one GPU'}), "
-                              f"levels < {solver.layout.lc} replicated")
-        line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_dev / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "iterations_per_eval": out.iterations, "convergence_factor": cf,
-                "residuals_last": float(out.residuals[-1]),
-                "ms_per_cycle": t_dev / args.steps / max(out.iterations, 1),
-                "cycle_gdof_s": ndof * out.iterations * args.steps / (t_dev * 1e-3) / 1e9,
-                "halo_exchanges_per_eval": out.exchanges, "wall_s_timed_region": t_wall, "clocks": clocks,
-                "e2e": None, "gpu_launches": None, "roofline": None, "cpu_baseline": None,
-                "note": "secondary mode (--domain): the default bench line is the population-sharded one"}
-        print(json.dumps(line), flush=True)
-    solver.close()
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-# ------------------------------------------------------------------------------------------------
-# BASELINE.json configs[4]: one G3P generation = 256 evolved cycles, half on Poisson 2D (levels 5..9),
-# half on LinearElasticity (levels 4..8), individuals sharded round-robin over the GPUs
-# (reference: optimization/program.py:534-535 distributes `i % nprocs == rank`).
 def population_individuals(n_total: int, seed: int = 0):
+    """BASELINE.json configs[4]: grammar-valid random individuals, alternating Poisson 2D (levels 5..9) and
+    LinearElasticity (levels 4..8)."""
     import random
     from evostencils_b200 import tree
     probs = [problems.Poisson2D(5, 9), problems.LinearElasticity2D(4, 8)]
@@ -472,123 +260,364 @@ def population_individuals(n_total: int, seed: int = 0):
     return probs, out
 
 
-def run_population(args, rank, world, local_rank):
-    from evostencils_b200 import backend, tree
+def cpu_population_sample(n_total: int, threads=None, sample=CPU_SAMPLE):
+    """Oracle on the generation workload: complete solves of a fixed, evenly spread sample of the SAME individuals."""
+    from evostencils_b200 import lowering, tree
+    from oracle import oracle as orc
+    nthreads = _cpu_threads(threads)
+    probs, individuals = population_individuals(n_total)
+    idx = [i for i in sample if i < n_total] or list(range(min(4, n_total)))
+    hosts = [orc.OracleProblem(p) for p in probs]
+    t0 = time.perf_counter()
+    for i in idx:
+        k, s = individuals[i]
+        p = probs[k]
+        prog = lowering.lower_cycle(tree.build_tree(p, s), p.min_level, p.max_level, p.n_fields, p.dim,
+                                    cgs_max_iters=p.settings.cgs_max_iters, cgs_tol=p.settings.cgs_tol,
+                                    default_restrict=p.restrict_weights(), default_prolong=p.prolong_weights())
+        prog = lowering.optimise(prog)
+        out = hosts[k].build(prog).solve(p.settings.tol, p.settings.max_iters, 1)
+        fitness.fitness_from_history(out.residuals, out.time_ms, p.settings.max_iters)
+    t = time.perf_counter() - t0
+    return {"value": len(idx) / t, "unit": "evals/s", "cores": nthreads, "kind": "port",
+            "sample": f"complete evaluations (lowering + solve to 1e-12 or 100 iterations) of individuals {list(idx)} of the "
+                      f"{n_total}-individual generation ({sum(1 for i in idx if i % 2 == 0)} Poisson 2D 513^2, "
+                      f"{sum(1 for i in idx if i % 2 == 1)} LinearElasticity 257^2), one after the other, oracle = C/OpenMP "
+                      f"restatement with {nthreads} threads, {t:.1f} s; solve time only -- the reference additionally runs "
+                      f"the Java generator twice and make per individual",
+            "seconds": t, "individuals": len(idx)}
+
+
+def workload_config(name, prob, world):
+    return {"workload": name, "problem": prob.name, "finest_nodes": f"{prob.nodes(prob.max_level)}^{prob.dim}",
+            "levels": f"{prob.max_level}..{prob.min_level}",
+            "cycle": f"{'W' if name.endswith('_w') else 'V'}({prob.settings.num_pre},{prob.settings.num_post}) red-black GS omega={prob.settings.damping} + CG",
+            "tol": prob.settings.tol, "max_iters": prob.settings.max_iters,
+            "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (one evaluation per GPU per step)",
+            "l2_policy": "inputs larger than L2 (finest fields 1.1 GB each)" if prob.dim == 3 and prob.max_level >= 8
+            else "working set fits L2 (latency-bound regime; no flush)"}
+
+
+def generation_config(n_total, world, in_flight):
+    return {"workload": DEFAULT_WORKLOAD, "individuals": n_total,
+            "problems": "Poisson 2D levels 9..5 (513^2) + LinearElasticity 2D levels 8..4 (257^2, 2 fields), alternating",
+            "generator": "evostencils_b200.tree.random_individual, seed 0, local systems <= 4",
+            "tol": 1e-12, "max_iters": 100, "in_flight_per_gpu": in_flight,
+            "parallelism": f"population sharded round-robin over {world} GPU(s), fitness gathered on the host; "
+                           f"grid513: one 513^3 evaluation " + ("on one GPU" if world == 1 else f"domain-decomposed into {world} z-slabs"),
+            "grid513": "Poisson 3D 7-point, 513^3, levels 9..2, V(2,1) red-black GS omega=1.25 + CG, tol 1e-12",
+            "l2_policy": "generation: working sets fit L2 (latency / launch bound regime, no flush); grid513 and roofline: "
+                         "inputs larger than L2 (finest fields 1.1 GB each)"}
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle port: ExaStencils cannot be generated here) on the arm's workload, all host
+    threads, rank 0 only; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    vals, info = [], None
+    if args.workload == DEFAULT_WORKLOAD:
+        cfg = generation_config(args.population, world, args.in_flight)
+        for i in range(args.warmup + args.steps):
+            info = cpu_population_sample(args.population)
+            if i >= args.warmup:
+                vals.append(info["value"])
+    else:
+        prob, _ = make_workload(args.workload)
+        cfg = workload_config(args.workload, prob, world)
+        for i in range(args.warmup + args.steps):
+            info = cpu_grid_sample(args.workload)
+            if i >= args.warmup:
+                vals.append(info["value"])
+    value = statistics.mean(vals)
+    info["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+            "scaling": "strong" if args.workload == DEFAULT_WORKLOAD else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def roofline_of(cyc, prob, workload):
+    """Dominant kernel of the grid evaluation: finest-level RB-GS sweep, CUDA-event timed through evo_cycle_profile_op."""
+    peak, peak_src = measured_peak()
+    s = prob.settings
+    ndof = float((prob.nodes(prob.max_level) - 2) ** prob.dim) * prob.n_fields
+    zero = (0,) * prob.dim
+    sm_op = ol.Op(ol.OP_SMOOTH, prob.max_level, mode=ol.MODE_REDBLACK, omega=s.damping,
+                  unknowns=tuple((f, zero) for f in range(prob.n_fields)))
+    ms, n_launch = cyc.profile_op(sm_op, repeat=10)
+    alg_bytes = 24.0 * ndof                      # SURVEY.md 8(d): read u, f, write u per full sweep
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this size
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            traffic = json.load(fh).get(workload, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roof = {"bound": "hbm", "kernel": "RB-GS sweep, finest level (both colours): k3_rbgs_col", "achieved": achieved,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_sweep": alg_bytes, "ms_per_sweep": ms, "launches_per_sweep": n_launch,
+            "smoother_gdof_s": ndof / (ms * 1e-3) / 1e9}
+    other = {}
+    for nm, op, b in (("residual", ol.Op(ol.OP_RESIDUAL, prob.max_level, dst=ol.BUF_RES), 24.0),
+                      ("residual+restrict", ol.Op(ol.OP_RESIDUAL_RESTRICT, prob.max_level, dst=ol.BUF_RHS, src=ol.BUF_RES),
+                       16.0 + 8.0 / 2 ** prob.dim),
+                      ("prolong_add", ol.Op(ol.OP_PROLONG_ADD, prob.max_level, src=ol.BUF_SOL, omega=1.0),
+                       16.0 + 8.0 / 2 ** prob.dim)):
+        try:
+            m2, _ = cyc.profile_op(op, repeat=10)
+            other[nm] = {"ms": m2, "GB/s": b * ndof / (m2 * 1e-3) / 1e9, "frac": b * ndof / (m2 * 1e-3) / 1e9 / peak}
+        except Exception as e:   # pragma: no cover
+            other[nm] = {"error": str(e)}
+    roof["other_kernels"] = other
+    return roof
+
+
+def measure_grid(args, D: Dist, workload: str, want_roofline: bool):
+    """One evaluation of the grid workload: device-resident solves (value), the reference-facing plugin call with the
+    tree as input (e2e), and at N > 1 the same evaluation domain-decomposed over all GPUs."""
+    from evostencils_b200 import backend
     from evostencils_b200.program_generator import B200ProgramGenerator
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_
-        dist = dist_
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prob, prog = make_workload(workload)
+    s = prob.settings
+    flags = ol.SOLVE_NO_GRAPH if args.no_graph else 0
+    ndof = float((prob.nodes(prob.max_level) - 2) ** prob.dim) * prob.n_fields
+    res = {"workload": workload}
+    single = None
+    roof = None
+    if D.world == 1 or D.rank == 0 or args.replicas:
+        dev = backend.DeviceProblem(prob, device=D.local_rank)
+        cyc = dev.build(prog)
+        for _ in range(args.warmup):
+            out = cyc.solve(s.tol, s.max_iters, 1, flags)
+        t_dev, launches = 0.0, 0
+        for _ in range(args.steps):
+            out = cyc.solve(s.tol, s.max_iters, 1, flags)
+            t_dev += out.time_ms
+            launches += out.kernel_launches
+        single = out
+        res.update({"single_gpu_ms_per_eval": t_dev / args.steps, "single_gpu_evals_per_s": args.steps / (t_dev * 1e-3),
+                    "iterations": out.iterations, "gpu_launches": launches,
+                    "convergence_factor": fitness.fitness_from_history(out.residuals, out.time_ms, s.max_iters)[1],
+                    "ms_per_cycle": t_dev / args.steps / max(out.iterations, 1),
+                    "cycle_gdof_s": ndof * out.iterations * args.steps / (t_dev * 1e-3) / 1e9})
+        if want_roofline and D.rank == 0:
+            roof = roofline_of(cyc, prob, workload)
+        cyc.close()
+        # e2e: the call Optimizer makes -- generate_and_evaluate(tree, storages, ...): lowering, op list / operator tables
+        # host -> device, solve, residual history device -> host, fitness tuple
+        expr = workload_tree(workload, prob)
+        if expr is not None and D.rank == 0 and not args.no_graph:
+            pg = B200ProgramGenerator(problem=prob, device=D.local_rank)
+            storages = pg.generate_storage(prob.min_level, prob.max_level, None)
+            for _ in range(min(args.warmup, 2)):
+                fit = pg.generate_and_evaluate(expr, storages, prob.min_level, prob.max_level, "", evaluation_samples=1)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fit = pg.generate_and_evaluate(expr, storages, prob.min_level, prob.max_level, "", evaluation_samples=1)
+            t_e2e = time.perf_counter() - t0
+            lowered = pg._finalise(pg.lower(expr, prob.min_level))
+            res["e2e"] = {"value": args.steps / t_e2e, "unit": "evals/s", "ms_per_eval": 1e3 * t_e2e / args.steps,
+                          "h2d_bytes_per_step": len(lowered.ops) * 160 + len(lowered.operators) * (8 + 2 * 2 * 27 * 2 * 8),
+                          "d2h_bytes_per_step": (s.max_iters + 1) * 8 + 48,
+                          "fitness": [float(v) for v in fit], "identical_history": bool(np.array_equal(pg.last_outcome.residuals, out.residuals)),
+                          "note": "B200ProgramGenerator.generate_and_evaluate(tree, storages, ...): lowering + evo_cycle_build + "
+                                  "evo_cycle_solve + history read-back + fitness; the call carries no field data (the problem is analytic)"}
+            pg.close()
+        dev.close()
+    if D.world > 1 and prob.dim == 3 and not args.no_domain:
+        import signal
+        from evostencils_b200 import domain
 
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+        def give_up(signum, frame):   # the decomposed measurement must never cost the line
+            raise TimeoutError("domain-decomposed measurement did not finish within the time limit")
 
-    from evostencils_b200 import population as popmod
+        signal.signal(signal.SIGALRM, give_up)
+        signal.alarm(int(os.environ.get("EVO_DOMAIN_TIME_LIMIT", "300")))
+        try:
+            D.barrier()
+            solver = domain.DomainSolver.distributed(prob, prog, D.rank, D.world, D.local_rank, lc=args.lc or None)
+            solver.overlap = not args.domain_no_overlap
+            dd_solve = solver.solve if args.domain_eager else solver.solve_captured
+            o3 = solver.solve(s.tol, s.max_iters)          # creates the NCCL communicators (not capturable)
+            for _ in range(2):
+                o3 = dd_solve(s.tol, s.max_iters)
+            D.barrier()
+            t_dd = 0.0
+            for _ in range(args.steps):
+                o3 = dd_solve(s.tol, s.max_iters)
+                t_dd += o3.time_ms
+            D.barrier()
+            (t_dd,) = D.max(t_dd)
+            same = None
+            if single is not None:
+                same = bool(np.array_equal(o3.residuals, single.residuals))
+            res["domain_decomposition"] = {
+                "n_gpus": D.world, "ms_per_eval": t_dd / args.steps, "evals_per_s": args.steps / (t_dd * 1e-3), "scaling": "strong",
+                "iterations": o3.iterations, "identical_history": same, "halo_exchanges_per_eval": o3.exchanges,
+                "overlap": solver.overlap, "levels_distributed": f"{prob.max_level}..{solver.layout.lc}",
+                "speedup_vs_one_gpu": (res["single_gpu_ms_per_eval"] / (t_dd / args.steps)) if "single_gpu_ms_per_eval" in res else None,
+                "note": "ONE evaluation split into z-slabs over all GPUs, halos over NCCL send/recv; "
+                        + ("host-orchestrated statements" if args.domain_eager else "each iteration (kernels + exchanges) replayed as one CUDA graph")}
+            solver.close()
+        except Exception as e:   # pragma: no cover - reported, never fatal
+            res["domain_decomposition"] = {"error": f"{type(e).__name__}: {e}"}
+        signal.alarm(0)
+    # headline numbers of this block: N = 1 -> the single GPU, N > 1 -> the decomposed evaluation
+    dd = res.get("domain_decomposition")
+    if dd and "ms_per_eval" in dd:
+        res.update({"n_gpus": D.world, "ms_per_eval": dd["ms_per_eval"], "evals_per_s": dd["evals_per_s"], "scaling": "strong"})
+    elif "single_gpu_ms_per_eval" in res:
+        res.update({"n_gpus": 1, "ms_per_eval": res["single_gpu_ms_per_eval"], "evals_per_s": res["single_gpu_evals_per_s"],
+                    "scaling": "strong"})
+    return res, roof
+
+
+def measure_generation(args, D: Dist):
+    """One G3P generation sharded over the ranks.  Returns the timings (max over ranks) and the gathered fitness list."""
+    from evostencils_b200 import population as popmod, tree
+    from evostencils_b200.program_generator import B200ProgramGenerator
     n_total = args.population
     probs, individuals = population_individuals(n_total)
-    mine = [individuals[i] for i in popmod.shard_indices(n_total, rank, world)]
-    gens = [B200ProgramGenerator(problem=p, device=local_rank) for p in probs]
+    mine = [individuals[i] for i in popmod.shard_indices(n_total, D.rank, D.world)]
+    gens = [B200ProgramGenerator(problem=p, device=D.local_rank) for p in probs]
     for g in gens:
         g.initialize_code_generation(g.min_level, g.max_level)
-    # host side of the hot path: string -> tree -> lowered program (done per step, inside the e2e region)
-    def lower_all():
+
+    def lower_all():   # host side of the hot path: grammar string -> tree -> lowered program
         progs = [[], []]
         for k, s in mine:
             progs[k].append(gens[k].lower(tree.build_tree(probs[k], s), gens[k].min_level))
         return progs
-    progs = lower_all()
 
-    def evaluate(progs):
+    def evaluate(progs, solo=True):
         ms, res, launches0 = 0.0, [], sum(g.total_kernel_launches for g in gens)
         for k in (0, 1):
-            r, t = gens[k].evaluate_population([], programs=progs[k], max_in_flight=args.in_flight)
+            r, t = gens[k].evaluate_population([], programs=progs[k], max_in_flight=args.in_flight, solo_timing=solo)
             ms += t
             res += r
         return ms, res, sum(g.total_kernel_launches for g in gens) - launches0
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    def ordered(progs, res):
+        order, out, n0 = {0: 0, 1: 0}, [], len(progs[0])
+        split = {0: res[:n0], 1: res[n0:]}
+        for k, _ in mine:
+            out.append(split[k][order[k]])
+            order[k] += 1
+        return out
+
+    progs = lower_all()
     for _ in range(args.warmup):
         evaluate(progs)
-    barrier()
+    # ---- device-resident: programs already lowered ------------------------------------------------------------
+    D.barrier()
     t_dev, launches = 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ms, res, ln = evaluate(progs)
         t_dev += ms
         launches += ln
-    barrier()
+        all_fitness = popmod.evaluate_sharded(individuals, lambda _m: ordered(progs, res), D.rank, D.world, D.dist)
+    D.barrier()
     t_wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    # e2e: strings -> trees -> lowering -> build -> solve -> fitness tuples on the host
-    barrier()
+    # ---- the same without the solo re-timing of the time objective (throughput of the concurrent batch alone) ----
+    D.barrier()
+    t0 = time.perf_counter()
+    evaluate(progs, solo=False)
+    D.barrier()
+    t_batch_only = time.perf_counter() - t0
+    # ---- end to end: strings -> trees -> lowering -> build -> solve -> fitness tuples gathered on the host --------
+    D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        evaluate(lower_all())
-    barrier()
+        pr = lower_all()
+        _, res2, _ = evaluate(pr)
+        all_fitness = popmod.evaluate_sharded(individuals, lambda _m: ordered(pr, res2), D.rank, D.world, D.dist)
+    D.barrier()
     t_e2e = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([t_dev, t_wall, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_wall, t_e2e = [float(v) for v in t.tolist()]
-        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        launches = int(ln.item())
-    # the complete, ordered fitness list on every rank (the reference's allgather, program.py:285-291)
-    order = {0: 0, 1: 0}
-    local_fitness = []
-    n0 = len(progs[0])
-    split = {0: res[:n0], 1: res[n0:]}
-    for k, _ in mine:
-        local_fitness.append(split[k][order[k]])
-        order[k] += 1
-    all_fitness = popmod.evaluate_sharded(individuals, lambda _m: local_fitness, rank, world, dist)
+    # ---- the literal plugin call, one individual after the other (what Optimizer's toolbox.map does) ---------------
+    seq = None
+    if D.rank == 0:
+        k_seq = min(16, len(mine))
+        trees = [(k, tree.build_tree(probs[k], s)) for k, s in mine[:k_seq]]
+        storages = [g.generate_storage(g.min_level, g.max_level, None) for g in gens]
+        t0 = time.perf_counter()
+        for k, e in trees:
+            gens[k].generate_and_evaluate(e, storages[k], gens[k].min_level, gens[k].max_level, "", evaluation_samples=1)
+        seq = k_seq / (time.perf_counter() - t0)
+    t_dev, t_wall, t_e2e, t_batch_only = D.max(t_dev, t_wall, t_e2e, t_batch_only)
+    launches = D.sum_int(launches)
+    h2d = D.sum_int(sum(len(p.ops) * 160 + len(p.operators) * 1736 for ps in progs for p in ps))
+    for g in gens:
+        g.close()
+    return {"t_dev_ms": t_dev, "t_wall": t_wall, "t_e2e": t_e2e, "t_batch_only": t_batch_only, "launches": launches, "h2d": h2d,
+            "d2h": n_total * (101 * 8 + 48), "fitness": all_fitness, "sequential_plugin_evals_per_s": seq}
+
+
+def run_default(args, rank, world, local_rank):
+    D = Dist(rank, world, local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.2 s to start: begin before the warm-up, sample through the timed regions
+    gen = measure_generation(args, D)
+    grid, roof = measure_grid(args, D, GRID_WORKLOAD, want_roofline=True)
+    clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # CPU port on a bounded sample: the first 4 individuals (2 per problem), complete solves
-        from oracle import oracle as orc
-        t0c = time.perf_counter()
-        n_cpu = 0
-        for k, s_ in individuals[:4]:
-            g = gens[k]
-            prog = g._finalise(g.lower(tree.build_tree(probs[k], s_), g.min_level))
-            orc.OracleProblem(probs[k]).build(prog).solve(probs[k].settings.tol, probs[k].settings.max_iters, 1)
-            n_cpu += 1
-        t_cpu = time.perf_counter() - t0c
-        cpu = {"value": n_cpu / t_cpu, "unit": "evals/s", "cores": orc.num_threads(), "kind": "port",
-               "sample": f"complete solves of the first {n_cpu} individuals of the generation (2 Poisson 2D, 2 elasticity) "
-                         f"with the C/OpenMP oracle, one after the other, {orc.num_threads()} threads; solve time only "
-                         f"(the reference additionally runs the Java generator twice and make per individual)"}
+        cpu = cpu_population_sample(args.population)
+        grid["cpu_port"] = cpu_grid_sample(GRID_WORKLOAD)
     if rank == 0:
+        n_total = args.population
         evals = n_total * args.steps
-        converged = sum(1 for r in all_fitness if r[1] < 1)
-        line = {"metric": METRIC, "value": evals / t_wall, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_wall * 1e3 / args.steps, "higher_is_better": True,
+        converged = sum(1 for r in gen["fitness"] if r[1] < 1)
+        line = {"metric": METRIC, "value": evals / gen["t_wall"], "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": gen["t_wall"] * 1e3 / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "population", "individuals": n_total,
-                           "problems": "Poisson 2D levels 9..5 (513^2) + LinearElasticity 2D levels 8..4 (257^2, 2 fields), alternating",
-                           "generator": "evostencils_b200.tree.random_individual, seed 0, local systems <= 4",
-                           "tol": 1e-12, "max_iters": 100, "in_flight_per_gpu": args.in_flight,
-                           "parallelism": f"population sharded round-robin over {world} GPU(s)",
-                           "l2_policy": "working sets fit L2 (latency / launch bound regime; no flush)"},
-                "device_busy_ms_per_step": t_dev / args.steps,
-                "e2e": {"value": evals / t_e2e, "unit": "evals/s",
-                        "h2d_bytes_per_step": sum(len(p.ops) * 160 + len(p.operators) * 1736 for ps in progs for p in ps),
-                        "d2h_bytes_per_step": len(mine) * (101 * 8 + 48),
-                        "note": "grammar strings -> trees -> lowering -> evo_cycle_build -> evo_batch_solve -> fitness tuples"},
-                "gpu_launches": launches, "clocks": clocks, "converging_individuals": converged,
-                "roofline": None, "cpu_baseline": cpu}
+                "config": generation_config(n_total, world, args.in_flight),
+                "device_busy_ms_per_step": gen["t_dev_ms"] / args.steps,
+                "value_without_solo_retiming": n_total / gen["t_batch_only"],
+                "e2e": {"value": evals / gen["t_e2e"], "unit": "evals/s", "h2d_bytes_per_step": gen["h2d"],
+                        "d2h_bytes_per_step": gen["d2h"],
+                        "sequential_plugin_evals_per_s": gen["sequential_plugin_evals_per_s"],
+                        "note": "grammar strings -> trees -> lowering -> B200ProgramGenerator.evaluate_population (evo_cycle_build, "
+                                "evo_batch_solve incl. the contention-free re-timing of the time objective) -> fitness tuples gathered "
+                                "on the host; sequential_plugin = generate_and_evaluate one individual after the other (1 GPU)"},
+                "gpu_launches": gen["launches"] + int(grid.get("gpu_launches") or 0), "clocks": clocks,
+                "converging_individuals": converged, "grid513": grid, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    D.close()
+
+
+def run_single(args, rank, world, local_rank):
+    """One grid workload (profiling / other BASELINE configurations); at N > 1 every rank solves a replica."""
+    D = Dist(rank, world, local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    args.replicas = True
+    prob, _ = make_workload(args.workload)
+    D.barrier()
+    grid, roof = measure_grid(args, D, args.workload, want_roofline=not args.no_graph)
+    (t_ms,) = D.max(grid["single_gpu_ms_per_eval"])
+    launches = D.sum_int(grid["gpu_launches"])
+    clocks = sampler.stop() if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_grid_sample(args.workload)
+    if rank == 0:
+        e2e = grid.get("e2e") or {"value": None, "unit": "evals/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}
+        line = {"metric": METRIC, "value": world / (t_ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, prob, world),
+                "iterations_per_eval": grid["iterations"], "convergence_factor": grid["convergence_factor"],
+                "cycle_gdof_s": grid["cycle_gdof_s"], "ms_per_cycle": grid["ms_per_cycle"], "e2e": e2e,
+                "domain_decomposition": grid.get("domain_decomposition"), "gpu_launches": launches, "clocks": clocks,
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    D.close()
 
 
 def main():
@@ -599,32 +628,30 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="poisson3d_513")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--population", type=int, default=256)
     ap.add_argument("--in-flight", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch kernels directly (host-side solver loop) so that ncu can see them; not a bench value")
-    ap.add_argument("--domain", action="store_true",
-                    help="strong scaling: ONE evaluation decomposed into z-slabs over the GPUs (SURVEY.md 8e.2)")
     ap.add_argument("--domain-no-overlap", action="store_true",
                     help="domain decomposition: exchange after the whole sweep instead of boundary planes first")
     ap.add_argument("--domain-eager", action="store_true", help="domain decomposition without CUDA-graph capture")
-    ap.add_argument("--no-domain", action="store_true", help="N > 1: skip the additional domain-decomposed measurement")
-    ap.add_argument("--slabs", type=int, default=2, help="--domain on one GPU: number of emulated slabs")
-    ap.add_argument("--lc", type=int, default=0, help="--domain: coarsest distributed level (default: automatic)")
+    ap.add_argument("--no-domain", action="store_true", help="N > 1: skip the domain-decomposed measurement")
+    ap.add_argument("--lc", type=int, default=0, help="domain decomposition: coarsest distributed level (default: automatic)")
     args = ap.parse_args()
+    args.replicas = False
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "population" and args.impl != "reference":
-        run_population(args, rank, world, local_rank)
-    elif args.impl == "reference":
+    if args.workload == "population":
+        args.workload = DEFAULT_WORKLOAD
+    if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.domain:
-        run_domain(args, rank, world, local_rank)
+    elif args.workload == DEFAULT_WORKLOAD:
+        run_default(args, rank, world, local_rank)
     else:
-        run_ours(args, rank, world, local_rank)
+        run_single(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -12,8 +12,9 @@
 //   * the z-neighbours, the centre value and the pair partner live in REGISTERS (4-deep rotating window per
 //     column, loop unrolled by 4 so that every index is static); only the three other in-plane neighbours are
 //     read from the shared-memory planes, at immediate offsets from one per-thread base address
-//   * planes arrive by TMA (cp.async.bulk.tensor.3d + mbarrier) into a 4-slot ring, one plane of prefetch;
-//     the right-hand side pair is loaded with one 16-byte LDG two planes ahead
+//   * u AND f planes arrive by TMA (cp.async.bulk.tensor.3d + mbarrier, one barrier per ring slot for both boxes)
+//     into an NPS-slot shared-memory ring, NPS - 2 planes of prefetch: with few resident CTAs per SM it is the
+//     depth of this ring, not occupancy, that covers the HBM latency (a 1-plane prefetch ran at 60 % of peak)
 //   * step t: stage 0 = first colour on plane t (result to registers + one STS so that the neighbours see it),
 //     stage 1 = second colour on plane t-1, which is then final and leaves with one coalesced 16-byte STG per
 //     thread -- no copy-out pass through shared memory, ONE block barrier per plane
@@ -28,14 +29,17 @@
 namespace evo {
 namespace star {
 
-template <int TY> struct ColCfg {
+template <int TY, int NPS> struct ColCfg {
     static constexpr int TXN = 64;                       // nodes per tile row: 32 x-pairs = one warp
     static constexpr int LX = TXN + 4, LY = TY + 4;      // TMA box: x = X0-2 .. X0+65 (even start), y = y0-2 .. y0+TY+1
-    static constexpr int NP = 4;                         // ring: planes t-1, t, t+1 and t+2 in flight
+    static constexpr int PF = NPS - 2;                   // ring: planes t-1 .. t+PF (plane t+PF is issued in step t)
     static constexpr int PSTRIDE = (LX * LY + 15) / 16 * 16;
     static constexpr uint32_t PB = PSTRIDE * 8, LXB = LX * 8, PLANE_BYTES = LX * LY * 8;
+    static constexpr uint32_t SB = 2 * PB;               // one ring slot = the u box followed by the f box of a plane
     static constexpr int NW = TY + 3, NT = NW * 32;      // TY core rows + 2 halo rows + 1 warp for the halo columns
+    static constexpr size_t SMEM = (size_t)NPS * SB;
     static_assert(TY % 2 == 0 && TY + 1 <= 32, "halo columns are handled as vertical pairs by one warp");
+    static_assert(NPS >= 4, "planes t-1, t, t+1 and at least one in flight");
 };
 
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b)
@@ -43,22 +47,25 @@ __device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b)
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 __device__ __forceinline__ void bar_sync0() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ double pin_reg(double v)
+{
+    double r;
+    asm volatile("mov.f64 %0, %1;" : "=d"(r) : "d"(v));
+    return r;
+}
 
-// per-thread state of the z march.  val[c][s]: current value (raw or first-colour updated) of node column c on
-// the plane held in window slot s; fv: right-hand sides.  Plane t + d of a step with phase V sits in slot
-// (V + 1 + d) & 3 of both the register window and the shared-memory ring.
+// per-thread state of the z march.  val[c][s]: current value (raw or first-colour updated) of node column c on the
+// plane held in window slot s.  Plane t + d of a step with phase V = (t - t0) & 3 sits in window slot (V + 1 + d) & 3.
 struct ColState {
     double val[2][4];
-    double fv[2][4];
+    uint32_t a_m1, a_0, a_p1;  // shared byte address of node 0 in the ring slots of planes t-1, t, t+1 (u box; f box = + PB)
+    int s_p1, par_p1;          // ring slot / mbarrier phase of plane t+1
 };
 
 struct ColArgs {
-    uint32_t sbase;            // shared byte address of node 0 of this thread in ring slot 0
-    const double *fptr;        // &f[node 0] on the plane whose right-hand side is fetched next (t + 2)
+    uint32_t ring0;            // shared byte address of node 0 of this thread in ring slot 0
     double *optr;              // &uout[node 0] on plane t - 1
     long long plane;
-    int gd1;                   // global element offset node 0 -> node 1 (1 or the row pitch)
-    int fok;                   // right-hand-side loads are in bounds for this thread
     int v0, v1;                // node 0 / node 1 is an inner node of the grid
     int sok;                   // the thread stores its pair (core rows, pair inside the grid)
     Star7 c;
@@ -66,11 +73,10 @@ struct ColArgs {
 };
 
 // ORIENT 0: node 1 = right neighbour of node 0 (x-pair);  ORIENT 1: node 1 = lower neighbour (y + 1) of node 0
-template <int TY, int ORIENT, int PH>
-__device__ __forceinline__ double col_update(const ColArgs &a, uint32_t pbase /* node 0 in the plane */, double zm, double zp, double old,
-                                             double partner, double fval)
+template <typename C, int ORIENT, int PH>
+__device__ __forceinline__ double col_update(const ColArgs &a, uint32_t pbase /* node 0 in the plane's u box */, double zm, double zp,
+                                             double old, double partner)
 {
-    using C = ColCfg<TY>;
     constexpr uint32_t D1 = ORIENT == 0 ? 8u : C::LXB;         // byte offset node 0 -> node 1
     const uint32_t ac = pbase + (PH ? D1 : 0u);                // active node
     double ym, xm, xp, yp;
@@ -85,6 +91,7 @@ __device__ __forceinline__ double col_update(const ColArgs &a, uint32_t pbase /*
         if constexpr (PH == 0) { ym = lds_f64_off<-(int)C::LXB>(ac); yp = partner; }
         else { ym = partner; yp = lds_f64_off<(int)C::LXB>(ac); }
     }
+    const double fval = lds_f64_off<(int)C::PB>(ac);           // right-hand side: same position in the f box of the slot
     double sum = 0.0;
     sum = sum + a.c.zm * zm;
     sum = sum + a.c.ym * ym;
@@ -97,50 +104,40 @@ __device__ __forceinline__ double col_update(const ColArgs &a, uint32_t pbase /*
 }
 
 // one plane step.  V = (t - t0) & 3, PH = column that carries the first colour on plane t.
-template <int TY, int ORIENT, bool FINAL, int V, int PH, bool CHECK>
-__device__ __forceinline__ void col_step(ColState &st, ColArgs &a, uint64_t *bars, const CUtensorMap *umap, double *ring, int xb, int yb,
-                                         int t, int kpar, int pmax, int lo0, int hi0, int za, int zb, bool leader)
+template <typename C, int NPS, int ORIENT, bool FINAL, int V, int PH, bool CHECK>
+__device__ __forceinline__ void col_step(ColState &st, ColArgs &a, uint64_t *bars, const CUtensorMap *umap, const CUtensorMap *fmap,
+                                         double *ring, int xb, int yb, int t, int pmax, int lo0, int hi0, int za, int zb, bool leader)
 {
-    using C = ColCfg<TY>;
-    constexpr int SM1 = V & 3, S0 = (V + 1) & 3, SP1 = (V + 2) & 3, SP2 = (V + 3) & 3;   // slots of planes t-1, t, t+1, t+2
+    constexpr int SM1 = V & 3, S0 = (V + 1) & 3, SP1 = (V + 2) & 3, SM2 = (V + 3) & 3;   // window slots of planes t-1, t, t+1, t-2
     constexpr int A = PH, B = 1 - PH;
     constexpr uint32_t D1 = ORIENT == 0 ? 8u : C::LXB;
-    // right-hand sides two planes ahead (consumed by stage 0 of step t+2 and stage 1 of step t+3)
-    if (a.fok && (!CHECK || (t + 2 >= lo0 && t + 2 <= hi0))) {
-        if constexpr (ORIENT == 0) {
-            const double2 f2 = __ldg(reinterpret_cast<const double2 *>(a.fptr));
-            st.fv[0][SP2] = f2.x; st.fv[1][SP2] = f2.y;
-        } else {
-            st.fv[0][SP2] = __ldg(a.fptr);
-            st.fv[1][SP2] = __ldg(a.fptr + a.gd1);
-        }
-    }
-    // plane t+2 into the slot plane t-2 occupied (its last readers finished before the previous barrier)
-    if (leader && (!CHECK || t + 2 <= pmax)) {
+    // planes t+PF (u and f) into the ring slot plane t-2 occupied: its last readers finished before the previous barrier
+    if (leader && (!CHECK || t + C::PF <= pmax)) {
+        const int tgt = st.s_p1 >= 3 ? st.s_p1 - 3 : st.s_p1 + NPS - 3;
+        double *dst = ring + (size_t)tgt * (2 * C::PSTRIDE);
         fence_proxy_async();
-        mbar_expect_tx(&bars[SP2], C::PLANE_BYTES);
-        tma_load_plane(ring + (size_t)SP2 * C::PSTRIDE, umap, xb, yb, t + 2, &bars[SP2]);
+        mbar_expect_tx(&bars[tgt], 2 * C::PLANE_BYTES);
+        tma_load_plane(dst, umap, xb, yb, t + C::PF, &bars[tgt]);
+        tma_load_plane(dst + C::PSTRIDE, fmap, xb, yb, t + C::PF, &bars[tgt]);
     }
     // plane t+1 has landed: its pair joins the register window
     if (!CHECK || t + 1 <= pmax) {
-        mbar_wait(&bars[SP1], (uint32_t)((kpar + (V + 2) / 4) & 1));
-        if constexpr (ORIENT == 0) lds_f64x2(a.sbase + SP1 * C::PB, st.val[0][SP1], st.val[1][SP1]);
-        else { st.val[0][SP1] = lds_f64(a.sbase + SP1 * C::PB); st.val[1][SP1] = lds_f64(a.sbase + SP1 * C::PB + D1); }
+        mbar_wait(&bars[st.s_p1], (uint32_t)st.par_p1);
+        if constexpr (ORIENT == 0) lds_f64x2(st.a_p1, st.val[0][SP1], st.val[1][SP1]);
+        else { st.val[0][SP1] = lds_f64(st.a_p1); st.val[1][SP1] = lds_f64_off<(int)D1>(st.a_p1); }
     }
     // stage 0: first colour on plane t
     if (!CHECK || (t >= lo0 && t <= hi0)) {
-        const double nv = col_update<TY, ORIENT, PH>(a, a.sbase + S0 * C::PB, st.val[A][SM1], st.val[A][SP1], st.val[A][S0], st.val[B][S0],
-                                                     st.fv[A][S0]);
+        const double nv = col_update<C, ORIENT, PH>(a, st.a_0, st.val[A][SM1], st.val[A][SP1], st.val[A][S0], st.val[B][S0]);
         if (A == 0 ? a.v0 : a.v1) {
             st.val[A][S0] = nv;
-            sts_f64(a.sbase + S0 * C::PB + (A ? D1 : 0u), nv);
+            sts_f64(st.a_0 + (A ? D1 : 0u), nv);
         }
     }
     // stage 1: second colour on plane t-1; the pair is final and leaves for HBM
     if constexpr (FINAL) {
         if (!CHECK || (t - 1 >= za && t - 1 <= zb)) {
-            const double nv = col_update<TY, ORIENT, PH>(a, a.sbase + SM1 * C::PB, st.val[A][SP2], st.val[A][S0], st.val[A][SM1],
-                                                         st.val[B][SM1], st.fv[A][SM1]);
+            const double nv = col_update<C, ORIENT, PH>(a, st.a_m1, st.val[A][SM2], st.val[A][S0], st.val[A][SM1], st.val[B][SM1]);
             const double fin = (A == 0 ? a.v0 : a.v1) ? nv : st.val[A][SM1];
             if (a.sok) {
                 double2 o2;
@@ -151,52 +148,48 @@ __device__ __forceinline__ void col_step(ColState &st, ColArgs &a, uint64_t *bar
         }
         a.optr += a.plane;
     }
-    a.fptr += a.plane;
+    // advance the ring cursors
+    st.a_m1 = st.a_0;
+    st.a_0 = st.a_p1;
+    if (++st.s_p1 == NPS) { st.s_p1 = 0; st.par_p1 ^= 1; }
+    st.a_p1 = a.ring0 + (uint32_t)st.s_p1 * C::SB;
     bar_sync0();
 }
 
-template <int TY, int ORIENT, bool FINAL, int P0>
-__device__ __forceinline__ void col_march(ColState &st, ColArgs &a, uint64_t *bars, const CUtensorMap *umap, double *ring, int xb, int yb,
-                                          int t0, int t1, int pmax, int lo0, int hi0, int za, int zb, bool leader)
+template <typename C, int NPS, int ORIENT, bool FINAL, int P0>
+__device__ __forceinline__ void col_march(ColState &st, ColArgs &a, uint64_t *bars, const CUtensorMap *umap, const CUtensorMap *fmap,
+                                          double *ring, int xb, int yb, int t0, int t1, int pmax, int lo0, int hi0, int za, int zb,
+                                          bool leader)
 {
-    int kpar = 0;
     for (int t = t0; t <= t1; t += 4) {
-        if (t >= za + 1 && t + 3 <= hi0 - 2) {
+        if (t >= za + 1 && t + 3 <= hi0 - 2 && t + 3 + C::PF <= pmax) {
             // steady state: every plane touched by these four steps exists and is updated -- no range checks
-            col_step<TY, ORIENT, FINAL, 0, P0, false>(st, a, bars, umap, ring, xb, yb, t, kpar, pmax, lo0, hi0, za, zb, leader);
-            col_step<TY, ORIENT, FINAL, 1, 1 - P0, false>(st, a, bars, umap, ring, xb, yb, t + 1, kpar, pmax, lo0, hi0, za, zb, leader);
-            col_step<TY, ORIENT, FINAL, 2, P0, false>(st, a, bars, umap, ring, xb, yb, t + 2, kpar, pmax, lo0, hi0, za, zb, leader);
-            col_step<TY, ORIENT, FINAL, 3, 1 - P0, false>(st, a, bars, umap, ring, xb, yb, t + 3, kpar, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 0, P0, false>(st, a, bars, umap, fmap, ring, xb, yb, t, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 1, 1 - P0, false>(st, a, bars, umap, fmap, ring, xb, yb, t + 1, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 2, P0, false>(st, a, bars, umap, fmap, ring, xb, yb, t + 2, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 3, 1 - P0, false>(st, a, bars, umap, fmap, ring, xb, yb, t + 3, pmax, lo0, hi0, za, zb, leader);
         } else {
-            col_step<TY, ORIENT, FINAL, 0, P0, true>(st, a, bars, umap, ring, xb, yb, t, kpar, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 0, P0, true>(st, a, bars, umap, fmap, ring, xb, yb, t, pmax, lo0, hi0, za, zb, leader);
             if (t + 1 > t1) break;
-            col_step<TY, ORIENT, FINAL, 1, 1 - P0, true>(st, a, bars, umap, ring, xb, yb, t + 1, kpar, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 1, 1 - P0, true>(st, a, bars, umap, fmap, ring, xb, yb, t + 1, pmax, lo0, hi0, za, zb, leader);
             if (t + 2 > t1) break;
-            col_step<TY, ORIENT, FINAL, 2, P0, true>(st, a, bars, umap, ring, xb, yb, t + 2, kpar, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 2, P0, true>(st, a, bars, umap, fmap, ring, xb, yb, t + 2, pmax, lo0, hi0, za, zb, leader);
             if (t + 3 > t1) break;
-            col_step<TY, ORIENT, FINAL, 3, 1 - P0, true>(st, a, bars, umap, ring, xb, yb, t + 3, kpar, pmax, lo0, hi0, za, zb, leader);
+            col_step<C, NPS, ORIENT, FINAL, 3, 1 - P0, true>(st, a, bars, umap, fmap, ring, xb, yb, t + 3, pmax, lo0, hi0, za, zb, leader);
         }
-        kpar ^= 1;
     }
-}
-
-__device__ __forceinline__ double pin_reg(double v)
-{
-    double r;
-    asm volatile("mov.f64 %0, %1;" : "=d"(r) : "d"(v));
-    return r;
 }
 
 // RC: the eight coefficients are pinned in registers (otherwise every use reloads them from the constant bank
 // through the uniform datapath: 16 more issue slots per plane); MINB: resident CTAs per SM the register budget allows
-template <int TY, bool RC, int MINB>
-__global__ void __launch_bounds__(ColCfg<TY>::NT, MINB)
-k3_rbgs_col(const __grid_constant__ CUtensorMap umap, const double *__restrict__ f, double *__restrict__ uout, const Geom g,
+template <int TY, int NPS, bool RC, int MINB>
+__global__ void __launch_bounds__(ColCfg<TY, NPS>::NT, MINB)
+k3_rbgs_col(const __grid_constant__ CUtensorMap umap, const __grid_constant__ CUtensorMap fmap, double *__restrict__ uout, const Geom g,
             const Star7 c, const double inv_c, const double omega, const int tz)
 {
-    using C = ColCfg<TY>;
+    using C = ColCfg<TY, NPS>;
     extern __shared__ __align__(128) double ring[];
-    __shared__ __align__(8) uint64_t bars[C::NP];
+    __shared__ __align__(8) uint64_t bars[NPS];
     const int n = g.n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int X0 = blockIdx.x * C::TXN, y0 = 1 + blockIdx.y * TY;      // tile: x = X0 .. X0+63 (pairs start at even x), y = y0 ..
@@ -209,15 +202,16 @@ k3_rbgs_col(const __grid_constant__ CUtensorMap umap, const double *__restrict__
     const bool leader = tid == 0;
 
     if (leader) {
-        for (int i = 0; i < C::NP; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < NPS; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
     if (leader) {
-        for (int p = pbase; p <= min(pbase + 2, pmax); ++p) {
-            const int sl = p - pbase;
-            mbar_expect_tx(&bars[sl], C::PLANE_BYTES);
-            tma_load_plane(ring + (size_t)sl * C::PSTRIDE, &umap, xb, yb, p, &bars[sl]);
+        for (int i = 0; i < NPS - 1 && pbase + i <= pmax; ++i) {       // planes t0-1 .. t0+PF-1; step t adds plane t+PF
+            double *dst = ring + (size_t)i * (2 * C::PSTRIDE);
+            mbar_expect_tx(&bars[i], 2 * C::PLANE_BYTES);
+            tma_load_plane(dst, &umap, xb, yb, pbase + i, &bars[i]);
+            tma_load_plane(dst + C::PSTRIDE, &fmap, xb, yb, pbase + i, &bars[i]);
         }
     }
 
@@ -246,72 +240,57 @@ k3_rbgs_col(const __grid_constant__ CUtensorMap umap, const double *__restrict__
     a.v0 = used && inner(x_0, y_0);
     a.v1 = used && inner(x_1, y_1);
     a.sok = final_row && a.v1;           // x_1 <= n-2 (then x_0 >= 0; x_0 = 0 carries the boundary value of both slots)
-    a.fok = a.v0 || a.v1;                // then both nodes lie inside the allocated array (boundary layer included)
-    a.gd1 = orient1 ? g.pitch : 1;
-    a.sbase = smem_u32(ring) + (uint32_t)(((y_0 - yb) * C::LX + (x_0 - xb)) * 8);
-    const long long goff = (long long)y_0 * g.pitch + x_0;
+    a.ring0 = smem_u32(ring) + (uint32_t)(((y_0 - yb) * C::LX + (x_0 - xb)) * 8);
+    a.optr = uout + (long long)(t0 - 1) * g.plane + (long long)y_0 * g.pitch + x_0;
     // whole pair rows outside the grid only keep the barrier count (warp uniform: the halo-column warp always runs)
     const bool idle = !orient1 && (y_0 < 1 || y_0 > n - 2);
+    if (idle) {
+        for (int t = t0; t <= t1; ++t) bar_sync0();
+        return;
+    }
 
     // colour phase: node 0 carries the first colour on plane t iff (x_0 + y_0 + t + zpar) is even
     const int p0 = (x_0 + y_0 + t0 + g.zpar) & 1;
     ColState st;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) { st.val[0][s] = st.val[1][s] = 0.0; st.fv[0][s] = st.fv[1][s] = 0.0; }
-
-    // window: planes t0-1 (slot 0) and t0 (slot 1); plane t0+1 joins in the first step
+    for (int s = 0; s < 4; ++s) st.val[0][s] = st.val[1][s] = 0.0;
+    // window: planes t0-1 (ring slot 0, window slot 0) and t0 (slot 1); plane t0+1 (slot 2) joins in the first step
+    st.a_m1 = a.ring0; st.a_0 = a.ring0 + C::SB; st.a_p1 = a.ring0 + 2 * C::SB;
+    st.s_p1 = 2; st.par_p1 = 0;
     if (pbase <= pmax) mbar_wait(&bars[0], 0u);
     if (pbase + 1 <= pmax) mbar_wait(&bars[1], 0u);
     {
         const uint32_t d1 = orient1 ? C::LXB : 8u;
-        st.val[0][0] = lds_f64(a.sbase); st.val[1][0] = lds_f64(a.sbase + d1);
-        st.val[0][1] = lds_f64(a.sbase + C::PB); st.val[1][1] = lds_f64(a.sbase + C::PB + d1);
-    }
-    // right-hand sides of planes t0 and t0+1 (slots 1, 2); the loop fetches plane t+2
-    const long long d1g = a.gd1;
-    if (a.fok) {
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            const int p = t0 + d;
-            if (p >= lo0 && p <= hi0) {
-                st.fv[0][1 + d] = __ldg(f + (long long)p * g.plane + goff);
-                st.fv[1][1 + d] = __ldg(f + (long long)p * g.plane + goff + d1g);
-            }
-        }
-    }
-    a.fptr = f + (long long)(t0 + 2) * g.plane + goff;
-    a.optr = uout + (long long)(t0 - 1) * g.plane + goff;
-
-    if (idle) {
-        for (int t = t0; t <= t1; ++t) bar_sync0();
-        return;
+        st.val[0][0] = lds_f64(st.a_m1); st.val[1][0] = lds_f64(st.a_m1 + d1);
+        st.val[0][1] = lds_f64(st.a_0); st.val[1][1] = lds_f64(st.a_0 + d1);
     }
     if (!orient1) {
         if (final_row) {
-            if (p0 == 0) col_march<TY, 0, true, 0>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, leader);
-            else col_march<TY, 0, true, 1>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, leader);
+            if (p0 == 0) col_march<C, NPS, 0, true, 0>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, leader);
+            else col_march<C, NPS, 0, true, 1>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, leader);
         } else {
-            if (p0 == 0) col_march<TY, 0, false, 0>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
-            else col_march<TY, 0, false, 1>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
+            if (p0 == 0) col_march<C, NPS, 0, false, 0>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
+            else col_march<C, NPS, 0, false, 1>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
         }
     } else {
-        if (p0 == 0) col_march<TY, 1, false, 0>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
-        else col_march<TY, 1, false, 1>(st, a, bars, &umap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
+        if (p0 == 0) col_march<C, NPS, 1, false, 0>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
+        else col_march<C, NPS, 1, false, 1>(st, a, bars, &umap, &fmap, ring, xb, yb, t0, t1, pmax, lo0, hi0, za, zb, false);
     }
 }
 
-template <int TY, bool RC, int MINB>
+template <int TY, int NPS, bool RC, int MINB>
 static bool launch_rbgs_col(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout, double omega,
                             cudaStream_t s)
 {
-    using C = ColCfg<TY>;
-    CUtensorMap map;
-    if (!make_plane_map(&map, g, u, C::LX, C::LY)) return false;
-    const size_t smem = (size_t)C::NP * C::PSTRIDE * 8;
+    using C = ColCfg<TY, NPS>;
+    CUtensorMap umap, fmap;
+    if (!make_plane_map(&umap, g, u, C::LX, C::LY) || !make_plane_map(&fmap, g, f, C::LX, C::LY)) return false;
     static int occ = 0;
     if (occ == 0) {
-        if (cudaFuncSetAttribute(k3_rbgs_col<TY, RC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_col<TY, RC, MINB>, C::NT, smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaFuncSetAttribute(k3_rbgs_col<TY, NPS, RC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
+            return false;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3_rbgs_col<TY, NPS, RC, MINB>, C::NT, C::SMEM) != cudaSuccess || occ < 1)
+            occ = 1;
     }
     const int planes = g.zhi - g.zlo + 1;
     if (planes <= 0) return true;
@@ -323,12 +302,12 @@ static bool launch_rbgs_col(int sm_count, const Geom &g, const Star7 &c, const d
         const int tzc = (planes + slabs - 1) / slabs;
         const long long ctas = (long long)tx * ty * ((planes + tzc - 1) / tzc);
         const double waves = (double)((ctas + slots - 1) / slots);
-        const double cost = waves * (tzc + 5);
+        const double cost = waves * (tzc + 3 + NPS);
         if (cost < best_cost) { best_cost = cost; best = slabs; }
     }
     const int tz = (planes + best - 1) / best;
     const int slabs = (planes + tz - 1) / tz;
-    k3_rbgs_col<TY, RC, MINB><<<dim3(tx, ty, slabs), C::NT, smem, s>>>(map, f, uout, g, c, 1.0 / c.c, omega, tz);
+    k3_rbgs_col<TY, NPS, RC, MINB><<<dim3(tx, ty, slabs), C::NT, C::SMEM, s>>>(umap, fmap, uout, g, c, 1.0 / c.c, omega, tz);
     return cudaGetLastError() == cudaSuccess;
 }
 

@@ -583,7 +583,7 @@ static bool launch_rbgs_stream(int sm_count, const Geom &g, const Star7 &c, cons
 }
 
 // register-carried pair-column kernel (evo_kernels_rbcol.cuh)
-template <int TY, bool RC, int MINB>
+template <int TY, int NPS, bool RC, int MINB>
 static bool launch_rbgs_col(int sm_count, const Geom &g, const Star7 &c, const double *u, const double *f, double *uout, double omega,
                             cudaStream_t s);
 
@@ -611,14 +611,19 @@ static bool try_rbgs_stream(int sm_count, const Geom &g, const OpSten &st, Field
             if (variant == 12) return launch_rbgs_lean<32, 256>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 13) return launch_rbgs_lean<16, 512>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 14) return launch_rbgs_lean<8, 128>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 30) return launch_rbgs_col<8, false, 3>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 31) return launch_rbgs_col<16, false, 1>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 32) return launch_rbgs_col<8, true, 2>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 33) return launch_rbgs_col<16, true, 1>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 34) return launch_rbgs_col<8, false, 2>(sm_count, g, c, up, fp, op, omega, s);
-            if (variant == 35) return launch_rbgs_col<8, true, 3>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 30) return launch_rbgs_col<8, 6, true, 2>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 31) return launch_rbgs_col<8, 5, true, 3>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 32) return launch_rbgs_col<8, 8, true, 2>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 33) return launch_rbgs_col<16, 6, true, 1>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 34) return launch_rbgs_col<8, 6, false, 2>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 35) return launch_rbgs_col<8, 4, true, 3>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 36) return launch_rbgs_col<16, 8, true, 1>(sm_count, g, c, up, fp, op, omega, s);
+            if (variant == 37) return launch_rbgs_col<8, 5, false, 3>(sm_count, g, c, up, fp, op, omega, s);
             if (variant == 20) return launch_rbgs_stream<2, 8, 256>(sm_count, g, c, up, fp, op, omega, s);   // generic multi-stage kernel: 65-68 %
-            return launch_rbgs_lean<8, 256>(sm_count, g, c, up, fp, op, omega, s);   // best measured: 73 % of HBM peak
+            // default: register-carried pair-column kernel (evo_kernels_rbcol.cuh), 97 % of the measured HBM peak at 513^3
+            // (16-row tiles, 8-slot ring, one CTA per SM); smaller grids need more CTAs than 16-row tiles give
+            if (g.n >= 385) return launch_rbgs_col<16, 8, true, 1>(sm_count, g, c, up, fp, op, omega, s);
+            return launch_rbgs_col<8, 5, true, 3>(sm_count, g, c, up, fp, op, omega, s);
         }
         if (sweeps == 2) {
             if (variant == 1) return launch_rbgs_stream<4, 32, 512>(sm_count, g, c, up, fp, op, omega, s);

@@ -516,18 +516,22 @@ class DomainSolver:
         r = self.ranks[0]
         levels = range(self.layout.lc, self.problem.max_level + 1)
         self._graphs = []
+        self._graph_exchanges = []             # halo exchanges / gathers one replay of each graph performs
         before = {l: r.cycle.buffer_ptr(l, ol.BUF_SOL) for l in levels}
         for k in range(2):
             g = torch.cuda.CUDAGraph()
             self._canonical_validity()
+            e0 = self.exchanges
             with torch.cuda.graph(g, stream=r.stream):
                 self._run_cycle_eager()
                 self._norm_partial()
             self._graphs.append(g)
+            self._graph_exchanges.append(self.exchanges - e0)
             if k == 0:
                 self._flipping = [l for l in levels if r.cycle.buffer_ptr(l, ol.BUF_SOL) != before[l]]
                 if not self._flipping:
                     self._graphs.append(g)     # nothing swaps: one graph serves every iteration
+                    self._graph_exchanges.append(self._graph_exchanges[0])
                     break
         after = {l: r.cycle.buffer_ptr(l, ol.BUF_SOL) for l in levels}
         if after != before:
@@ -555,6 +559,7 @@ class DomainSolver:
             it = 0
             while it < max_iters and math.isfinite(hist[-1]):
                 self._graphs[it & 1].replay()
+                self.exchanges += self._graph_exchanges[it & 1]
                 it += 1
                 hist.append(math.sqrt(r.cycle.read_sum()))
                 if hist[-1] < tol * hist[0]:

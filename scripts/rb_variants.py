@@ -11,7 +11,7 @@ from evostencils_b200 import backend, cycles, oplist as ol, problems  # noqa: E4
 
 def main():
     level = int(sys.argv[1]) if len(sys.argv) > 1 else 9
-    variants = [int(v) for v in sys.argv[2:]] or [10, 30, 31, 32, 33, 34, 35]
+    variants = [int(v) for v in sys.argv[2:]] or [10, 30, 31, 32, 33, 34, 35, 36, 37]
     prob = problems.Poisson3D(2, level)
     peak = 6554.6
     try:

@@ -42,7 +42,7 @@ def test_option_api(cuda_backend, option):
 
 
 # variants: 0 default, 10 lean, 20 generic multi-stage, 30-35 pair-column kernels
-@pytest.mark.parametrize("variant", [0, 10, 20, 30, 31, 32, 33, 34, 35])
+@pytest.mark.parametrize("variant", [0, 10, 20, 30, 31, 32, 33, 34, 35, 36, 37])
 @pytest.mark.parametrize("level,sweeps", [(5, 1), (6, 3), (7, 2)])
 def test_rbgs_kernel_variants_bit_exact(cuda_backend, oracle_mod, option, variant, level, sweeps):
     option("EVO_RB_VARIANT", variant)
