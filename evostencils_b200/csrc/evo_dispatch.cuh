@@ -2,6 +2,7 @@
 // safe under stream capture).  Included by evo_dispatch_inst.cu only.
 #pragma once
 #include "evo_runtime_internal.cuh"
+#include "evo_kernels_run.cuh"
 
 template <typename T, int DIM, int NF> struct Launch {
     // d_partials holds the canonical row sums [NF][nzi][ni]; reduce them to SolveState::sum
@@ -449,6 +450,161 @@ template <typename T, int DIM, int NF> int enqueue_op(evo_cycle *c, const evo_op
     }
 }
 
+
+// ---- fused runs of statements on small levels (evo_kernels_run.cuh) -------------------------------------------------
+// can this statement be part of a fused run?
+template <typename T, int DIM, int NF> bool run_eligible(const evo_cycle *c, const evo_op &op)
+{
+    if constexpr (!std::is_same<T, double>::value) {
+        return false;
+    } else {
+        const evo_problem *p = c->p;
+        if (p->desc.kind != EVO_PROBLEM_LINEAR || p->slab_lc > 0 || option(OPT_COARSE_FUSE) == 0) return false;
+        const int l = op.level;
+        if (l < p->desc.min_level || l > p->desc.max_level) return false;
+        if (l - p->desc.min_level >= RUN_MAX_LEVELS) return false;
+        if (p->geom[l].n > (DIM == 2 ? 257 : 33)) return false;
+        switch (op.code) {
+        case EVO_OP_ZERO: case EVO_OP_COPY: return true;
+        case EVO_OP_RESIDUAL: return c->has_sten[l];
+        case EVO_OP_RESTRICT: case EVO_OP_PROLONG_ADD: case EVO_OP_PROLONG_SET: return l > p->desc.min_level;
+        case EVO_OP_RESIDUAL_RESTRICT: return l > p->desc.min_level && c->has_sten[l];
+        case EVO_OP_SMOOTH: {
+            if (op.kind != EVO_KIND_LINEAR || !c->has_sten[l] || op.n_unknowns < 1 || op.n_unknowns > EVO_MAX_UNKNOWNS) return false;
+            SmoothParams sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.nu = op.n_unknowns;
+            bool has_own[EVO_MAX_FIELDS] = {false, false}, written[EVO_MAX_FIELDS] = {false, false};
+            for (int a = 0; a < sp.nu; ++a) {
+                sp.field[a] = op.unk_field[a];
+                if (sp.field[a] < 0 || sp.field[a] >= NF) return false;
+                for (int d = 0; d < 3; ++d) sp.off[a][d] = d < DIM ? op.unk_off[a][d] : 0;
+                written[sp.field[a]] = true;
+                if (sp.off[a][0] == 0 && sp.off[a][1] == 0 && sp.off[a][2] == 0) has_own[sp.field[a]] = true;
+            }
+            for (int i = 0; i < NF; ++i)
+                if (written[i] && !has_own[i]) return false;
+            if (op.mode == EVO_SMOOTH_JACOBI) {
+                for (int i = 0; i < NF; ++i)
+                    if (written[i] && !c->lv[l].slot[i]) return false;
+                return true;
+            }
+            if (op.mode == EVO_SMOOTH_REDBLACK) return !Launch<T, DIM, NF>::color_order_dependent(c->sten[l], sp, NF);
+            return false;
+        }
+        default: return false;
+        }
+    }
+}
+
+// enqueue ops[0..n) (all run_eligible) as fused launches; buffer exchanges of out-of-place statements are applied to
+// the cycle's pointers exactly as the stand-alone dispatch applies them
+template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_op *ops, int n, cudaStream_t s)
+{
+    if constexpr (!std::is_same<T, double>::value) {
+        return fail(EVO_ERR_UNSUPPORTED, "fused runs: real problems only");
+    } else {
+        evo_problem *p = c->p;
+        const int lbase = p->desc.min_level;
+        for (int i0 = 0; i0 < n; i0 += RUN_MAX_OPS) {
+            const int m = std::min(RUN_MAX_OPS, n - i0);
+            static RunTable tab;     // ~25 KB: keep it off the stack (the launch copies it; single-threaded host)
+            memset(&tab, 0, sizeof(tab));
+            tab.n = m;
+            tab.R = p->R;
+            tab.P = p->P;
+            long long nodes_max = 1;
+            for (int q = 0; q < m; ++q) {
+                const evo_op &op = ops[i0 + q];
+                const int l = op.level;
+                RunOp &r = tab.op[q];
+                r.code = op.code;
+                r.li = l - lbase;
+                r.lj = l - 1 - lbase;
+                r.reps = op.count > 1 ? op.count : 1;
+                r.mode = op.mode;
+                r.omega = op.omega;
+                tab.geom[r.li] = p->geom[l];
+                if (c->has_sten[l]) tab.sten[r.li] = c->sten[l];
+                if (r.lj >= 0) {
+                    tab.geom[r.lj] = p->geom[l - 1];
+                    if (c->has_sten[l - 1]) tab.sten[r.lj] = c->sten[l - 1];
+                }
+                const Geom &g = p->geom[l];
+                nodes_max = std::max(nodes_max, (long long)(g.n - 2) * (g.n - 2) * (DIM == 3 ? g.n - 2 : 1));
+                LevelMem &lv = c->lv[l];
+                switch (op.code) {
+                case EVO_OP_ZERO:
+                    for (int f = 0; f < NF; ++f) r.b[f] = lv.buf[op.dst][f];
+                    break;
+                case EVO_OP_COPY:
+                    for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[op.src][f]; r.b[f] = lv.buf[op.dst][f]; }
+                    break;
+                case EVO_OP_RESIDUAL:
+                    for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[EVO_BUF_SOL][f]; r.b[f] = lv.buf[EVO_BUF_RHS][f]; r.c[f] = lv.buf[EVO_BUF_RES][f]; }
+                    break;
+                case EVO_OP_RESTRICT:
+                    for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[op.src][f]; r.b[f] = c->lv[l - 1].buf[op.dst][f]; }
+                    break;
+                case EVO_OP_RESIDUAL_RESTRICT:
+                    for (int f = 0; f < NF; ++f) {
+                        r.a[f] = lv.buf[EVO_BUF_SOL][f]; r.c[f] = lv.buf[EVO_BUF_RHS][f]; r.b[f] = c->lv[l - 1].buf[EVO_BUF_RHS][f];
+                    }
+                    break;
+                case EVO_OP_PROLONG_ADD:
+                case EVO_OP_PROLONG_SET:
+                    for (int f = 0; f < NF; ++f) {
+                        r.a[f] = c->lv[l - 1].buf[op.src][f];
+                        r.b[f] = lv.buf[op.code == EVO_OP_PROLONG_ADD ? EVO_BUF_SOL : op.dst][f];
+                    }
+                    break;
+                case EVO_OP_SMOOTH: {
+                    SmoothParams &sp = r.sp;
+                    sp.nu = op.n_unknowns;
+                    sp.omega = op.omega;
+                    sp.write_all = 0;
+                    sp.color = -1;
+                    for (int a = 0; a < sp.nu; ++a) {
+                        sp.field[a] = op.unk_field[a];
+                        for (int d = 0; d < 3; ++d) sp.off[a][d] = d < DIM ? op.unk_off[a][d] : 0;
+                        r.written |= 1u << sp.field[a];
+                    }
+                    for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[EVO_BUF_SOL][f]; r.b[f] = lv.slot[f]; r.c[f] = lv.buf[EVO_BUF_RHS][f]; }
+                    if (op.mode == EVO_SMOOTH_JACOBI && (r.reps & 1)) {
+                        // an odd number of out-of-place sweeps leaves the result in the [next] slots
+                        for (int f = 0; f < NF; ++f)
+                            if ((r.written >> f) & 1u) {
+                                const bool cor_alias = lv.buf[EVO_BUF_COR][f] == lv.buf[EVO_BUF_SOL][f];
+                                std::swap(lv.buf[EVO_BUF_SOL][f], lv.slot[f]);
+                                lv.swapped[f] = !lv.swapped[f];
+                                if (cor_alias) lv.buf[EVO_BUF_COR][f] = lv.buf[EVO_BUF_SOL][f];
+                            }
+                    }
+                    break;
+                }
+                default: return fail(EVO_ERR_INVALID, "statement %d cannot be part of a fused run", op.code);
+                }
+            }
+            // one cluster: ~4 nodes per thread, at most 8 CTAs of 512 threads
+            int ctas = 1;
+            while (ctas < 8 && nodes_max > (long long)ctas * 2048) ctas *= 2;
+            const int threads = nodes_max >= 512 ? 512 : (int)((nodes_max + 31) / 32 * 32);
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(ctas);
+            cfg.blockDim = dim3(threads);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF>, tab));
+            c->launch_counter++;
+        }
+        return EVO_OK;
+    }
+}
 
 template <typename T, int DIM, int NF> int op_residual(evo_cycle *c, int level, bool norm, cudaStream_t s)
 {

@@ -21,3 +21,5 @@ template int enqueue_op<EVO_INST_ARGS>(evo_cycle *, const evo_op &, cudaStream_t
 template int op_residual<EVO_INST_ARGS>(evo_cycle *, int, bool, cudaStream_t);
 template int op_restrict<EVO_INST_ARGS>(evo_cycle *, const evo_op &, cudaStream_t);
 template int op_reduce_rows<EVO_INST_ARGS>(evo_cycle *, int, cudaStream_t);
+template bool run_eligible<EVO_INST_ARGS>(const evo_cycle *, const evo_op &);
+template int enqueue_run<EVO_INST_ARGS>(evo_cycle *, const evo_op *, int, cudaStream_t);

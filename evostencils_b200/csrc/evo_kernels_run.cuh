@@ -1,0 +1,213 @@
+// evo_kernels_run.cuh -- a maximal run of consecutive statements on small levels executed by ONE kernel launch.
+//
+// On the latency-bound levels (2-D up to 257^2, 3-D up to 33^3) a statement is a few microseconds of work and a cycle
+// is dozens of dependent kernel launches; a generation of 256 individuals is ~1.4 million launches and the GPU's
+// launch rate, not its SMs, bounds the evaluation rate (north star: "launch overhead on the latency-bound coarse
+// levels is amortised").  Here the host resolves a run of statements (buffers, geometry, stencils) into a table that
+// travels as a __grid_constant__ kernel parameter, and one thread-block cluster (1..8 CTAs, hardware cluster barrier
+// between statements, colours and repetitions) interprets it.  Per node every statement performs exactly the
+// arithmetic of its stand-alone kernel (same device functions: apply_row, local_solve), so results are bit-identical
+// whether a statement runs fused or alone.
+#pragma once
+#include "evo_kernels.cuh"
+
+namespace evo {
+
+constexpr int RUN_MAX_OPS = 40;
+constexpr int RUN_MAX_LEVELS = 6;
+
+struct RunOp {
+    int code;                       // evo_opcode
+    int li, lj;                     // geometry / stencil table index of the statement's level and of level - 1
+    int reps;                       // smoothing repetitions
+    int mode;                       // evo_smooth_mode
+    unsigned written;               // bit i: field i is written by the smoother (Jacobi: it alternates between its two slots)
+    double omega;
+    SmoothParams sp;
+    void *a[EVO_MAX_FIELDS];        // smooth: current slot | residual: u | restrict: src (fine) | prolong: src (coarse) | copy: src
+    void *b[EVO_MAX_FIELDS];        // smooth: [next] slot  | residual: f | restrict: dst (coarse) | prolong: dst (fine) | copy / zero: dst
+    void *c[EVO_MAX_FIELDS];        // smooth: rhs          | residual: r | residual+restrict: f (fine; a = u, b = dst coarse)
+};
+
+struct RunTable {
+    int n;
+    int nthreads_hint;
+    Geom geom[RUN_MAX_LEVELS];
+    OpSten sten[RUN_MAX_LEVELS];
+    TransferW R, P;
+    RunOp op[RUN_MAX_OPS];
+};
+
+template <typename T> __device__ __forceinline__ Fields<T> run_fields(void *const *p)
+{
+    Fields<T> f;
+#pragma unroll
+    for (int i = 0; i < EVO_MAX_FIELDS; ++i) f.p[i] = (T *)p[i];
+    return f;
+}
+
+// inner node number t of a level -> coordinates
+template <int DIM> __device__ __forceinline__ void run_node(int t, int ni, int &x, int &y, int &z)
+{
+    x = 1 + t % ni;
+    const int r = t / ni;
+    if (DIM == 3) { y = 1 + r % ni; z = 1 + r / ni; }
+    else { y = 1 + r; z = 0; }
+}
+
+template <int DIM, int NF, int NU>
+__device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
+{
+    const Geom &g = tab.geom[op.li];
+    const OpSten &st = tab.sten[op.li];
+    const int ni = g.n - 2, count = ni * ni * (DIM == 3 ? ni : 1);
+    const Fields<double> rhs = run_fields<double>(op.c);
+    if (op.mode == EVO_SMOOTH_JACOBI) {
+        for (int rep = 0; rep < op.reps; ++rep) {
+            Fields<double> src, dst;
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                const bool w = (op.written >> i) & 1u;
+                double *cur = (double *)op.a[i], *nxt = (double *)op.b[i];
+                src.p[i] = (w && (rep & 1)) ? nxt : cur;
+                dst.p[i] = w ? ((rep & 1) ? cur : nxt) : cur;
+            }
+            for (int t = gtid; t < count; t += nthreads) {
+                int x, y, z;
+                run_node<DIM>(t, ni, x, y, z);
+                local_solve<double, DIM, NF, NU>(g, st, op.sp, src, dst, rhs, x, y, z);
+            }
+            cluster_barrier();
+        }
+    } else {   // red-black, order independent: colour 0 then colour 1, in place
+        const Fields<double> u = run_fields<double>(op.a);
+        const int pairs = (ni + 1) / 2, rows = DIM == 3 ? ni * ni : ni;
+        for (int rep = 0; rep < op.reps; ++rep)
+            for (int color = 0; color < 2; ++color) {
+                for (int t = gtid; t < pairs * rows; t += nthreads) {
+                    const int k = t % pairs, r = t / pairs;
+                    const int y = 1 + (DIM == 3 ? r % ni : r), z = DIM == 3 ? 1 + r / ni : 0;
+                    const int x = 1 + 2 * k + ((1 + y + z + color) & 1);
+                    if (x <= ni) local_solve<double, DIM, NF, NU>(g, st, op.sp, u, u, rhs, x, y, z);
+                }
+                cluster_barrier();
+            }
+    }
+}
+
+template <int DIM, int NF>
+__device__ __forceinline__ void run_smooth(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
+{
+    switch (op.sp.nu) {
+    case 1: run_smooth_nu<DIM, NF, 1>(tab, op, gtid, nthreads); break;
+    case 2: run_smooth_nu<DIM, NF, 2>(tab, op, gtid, nthreads); break;
+    case 3: run_smooth_nu<DIM, NF, 3>(tab, op, gtid, nthreads); break;
+    case 4: run_smooth_nu<DIM, NF, 4>(tab, op, gtid, nthreads); break;
+    case 5: run_smooth_nu<DIM, NF, 5>(tab, op, gtid, nthreads); break;
+    case 6: run_smooth_nu<DIM, NF, 6>(tab, op, gtid, nthreads); break;
+    case 7: run_smooth_nu<DIM, NF, 7>(tab, op, gtid, nthreads); break;
+    default: run_smooth_nu<DIM, NF, 8>(tab, op, gtid, nthreads); break;
+    }
+}
+
+template <int DIM, int NF>
+__global__ void __launch_bounds__(512) k_run(const __grid_constant__ RunTable tab)
+{
+    const int nthreads = (int)(cluster_nctarank() * blockDim.x), gtid = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+    for (int q = 0; q < tab.n; ++q) {
+        const RunOp &op = tab.op[q];
+        const Geom &g = tab.geom[op.li];
+        const int ni = g.n - 2, count = ni * ni * (DIM == 3 ? ni : 1);
+        switch (op.code) {
+        case EVO_OP_SMOOTH:
+            run_smooth<DIM, NF>(tab, op, gtid, nthreads);   // ends with a barrier
+            continue;
+        case EVO_OP_ZERO:
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                double *d = (double *)op.b[i];
+                for (long long t = gtid; t < g.total; t += nthreads) d[t] = 0.0;
+            }
+            break;
+        case EVO_OP_COPY:
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                double *d = (double *)op.b[i];
+                const double *s = (const double *)op.a[i];
+                if (d != s)
+                    for (long long t = gtid; t < g.total; t += nthreads) d[t] = s[t];
+            }
+            break;
+        case EVO_OP_RESIDUAL: {
+            const Fields<double> u = run_fields<double>(op.a), f = run_fields<double>(op.b), r = run_fields<double>(op.c);
+            for (int t = gtid; t < count; t += nthreads) {
+                int x, y, z;
+                run_node<DIM>(t, ni, x, y, z);
+                const long long idx = node_index(g, x, y, z);
+#pragma unroll
+                for (int i = 0; i < NF; ++i) r.p[i][idx] = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[op.li], u, i, idx);
+            }
+            break;
+        }
+        case EVO_OP_RESTRICT:
+        case EVO_OP_RESIDUAL_RESTRICT: {
+            const Geom &gc = tab.geom[op.lj];
+            const int nc = gc.n - 2, cc = nc * nc * (DIM == 3 ? nc : 1);
+            const Fields<double> u = run_fields<double>(op.a), dst = run_fields<double>(op.b), f = run_fields<double>(op.c);
+            const bool fused = op.code == EVO_OP_RESIDUAL_RESTRICT;
+            for (int t = gtid; t < cc; t += nthreads) {
+                int x, y, z;
+                run_node<DIM>(t, nc, x, y, z);
+                const long long cidx = node_index(gc, x, y, z);
+#pragma unroll
+                for (int i = 0; i < NF; ++i) {
+                    double acc = 0.0;
+                    for (int p = 0; p < tab.R.nnz; ++p) {
+                        const int fx = 2 * x + tab.R.ox[p], fy = 2 * y + tab.R.oy[p], fz = DIM == 3 ? 2 * z + tab.R.oz[p] : 0;
+                        double rv;
+                        if (fused) {
+                            rv = 0.0;  // the residual field is 0 on the boundary layer
+                            if (fx >= 1 && fx <= g.n - 2 && fy >= 1 && fy <= g.n - 2 && (DIM == 2 || (fz >= 1 && fz <= g.n - 2))) {
+                                const long long idx = node_index(g, fx, fy, fz);
+                                rv = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[op.li], u, i, idx);
+                            }
+                        } else {
+                            rv = u.p[i][node_index(g, fx, fy, fz)];
+                        }
+                        acc = acc + tab.R.w[p] * rv;
+                    }
+                    dst.p[i][cidx] = acc;
+                }
+            }
+            break;
+        }
+        case EVO_OP_PROLONG_ADD:
+        case EVO_OP_PROLONG_SET: {
+            const Geom &gc = tab.geom[op.lj];
+            const Fields<double> src = run_fields<double>(op.a), dst = run_fields<double>(op.b);
+            const bool add = op.code == EVO_OP_PROLONG_ADD;
+            for (int t = gtid; t < count; t += nthreads) {
+                int x, y, z;
+                run_node<DIM>(t, ni, x, y, z);
+                const long long idx = node_index(g, x, y, z);
+#pragma unroll
+                for (int i = 0; i < NF; ++i) {
+                    double acc = 0.0;
+                    for (int p = 0; p < tab.P.nnz; ++p) {
+                        const int cx = x + tab.P.ox[p], cy = y + tab.P.oy[p], cz = DIM == 3 ? z + tab.P.oz[p] : 0;
+                        if ((cx & 1) || (cy & 1) || (DIM == 3 && (cz & 1))) continue;
+                        acc = acc + tab.P.w[p] * src.p[i][node_index(gc, cx >> 1, cy >> 1, cz >> 1)];
+                    }
+                    if (add) dst.p[i][idx] = dst.p[i][idx] + op.omega * acc;
+                    else dst.p[i][idx] = acc;
+                }
+            }
+            break;
+        }
+        default: break;
+        }
+        cluster_barrier();
+    }
+}
+
+}  // namespace evo

@@ -407,7 +407,9 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
     extern template int enqueue_op<__VA_ARGS__>(evo_cycle *, const evo_op &, cudaStream_t);    \
     extern template int op_residual<__VA_ARGS__>(evo_cycle *, int, bool, cudaStream_t);        \
     extern template int op_restrict<__VA_ARGS__>(evo_cycle *, const evo_op &, cudaStream_t);   \
-    extern template int op_reduce_rows<__VA_ARGS__>(evo_cycle *, int, cudaStream_t);
+    extern template int op_reduce_rows<__VA_ARGS__>(evo_cycle *, int, cudaStream_t);     \
+    extern template bool run_eligible<__VA_ARGS__>(const evo_cycle *, const evo_op &);      \
+    extern template int enqueue_run<__VA_ARGS__>(evo_cycle *, const evo_op *, int, cudaStream_t);
 EVO_EXTERN_INST(double, 2, 1)
 EVO_EXTERN_INST(double, 2, 2)
 EVO_EXTERN_INST(double, 3, 1)
@@ -652,9 +654,37 @@ static int dispatch_residual_norm(evo_cycle *c, cudaStream_t s, bool force_store
 
 // all statements of the cycle function, then restore the canonical jacobi-slot assignment so that a
 // replay (next outer iteration) starts from the same pointers
+static bool op_run_eligible(const evo_cycle *c, const evo_op &op)
+{
+    const evo_problem_desc &d = c->p->desc;
+    if (d.kind != EVO_PROBLEM_LINEAR || d.scalar_words != 1) return false;
+    if (d.dim == 2) return d.n_fields == 1 ? run_eligible<double, 2, 1>(c, op) : run_eligible<double, 2, 2>(c, op);
+    return d.n_fields == 1 ? run_eligible<double, 3, 1>(c, op) : run_eligible<double, 3, 2>(c, op);
+}
+
+static int enqueue_fused_run(evo_cycle *c, const evo_op *ops, int n, cudaStream_t s)
+{
+    const evo_problem_desc &d = c->p->desc;
+    c->pristine = false;
+    if (d.dim == 2) return d.n_fields == 1 ? enqueue_run<double, 2, 1>(c, ops, n, s) : enqueue_run<double, 2, 2>(c, ops, n, s);
+    return d.n_fields == 1 ? enqueue_run<double, 3, 1>(c, ops, n, s) : enqueue_run<double, 3, 2>(c, ops, n, s);
+}
+
 static int enqueue_cycle_ops(evo_cycle *c, cudaStream_t s)
 {
-    for (const evo_op &op : c->ops) EV(dispatch_op(c, op, s));
+    // maximal runs of >= 2 consecutive statements on the small levels go out as ONE launch (evo_kernels_run.cuh)
+    const size_t n = c->ops.size();
+    for (size_t t = 0; t < n;) {
+        size_t e = t;
+        while (e < n && op_run_eligible(c, c->ops[e])) ++e;
+        if (e - t >= 2) {
+            EV(enqueue_fused_run(c, &c->ops[t], (int)(e - t), s));
+            t = e;
+        } else {
+            EV(dispatch_op(c, c->ops[t], s));
+            ++t;
+        }
+    }
     return EVO_OK;
 }
 

@@ -132,3 +132,5 @@ template <typename T, int DIM, int NF> int enqueue_op(evo_cycle *c, const evo_op
 template <typename T, int DIM, int NF> int op_residual(evo_cycle *c, int level, bool norm, cudaStream_t s);
 template <typename T, int DIM, int NF> int op_restrict(evo_cycle *c, const evo_op &op, cudaStream_t s);
 template <typename T, int DIM, int NF> int op_reduce_rows(evo_cycle *c, int ni, cudaStream_t s);
+template <typename T, int DIM, int NF> bool run_eligible(const evo_cycle *c, const evo_op &op);
+template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_op *ops, int n, cudaStream_t s);

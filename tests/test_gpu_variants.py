@@ -143,3 +143,39 @@ def test_model_based_mode_through_the_drop_in(cuda_backend, oracle_mod):
     assert its == rits and abs(cf - rcf) < 1e-12 and cf < 1
     assert np.array_equal(gen.last_outcome.residuals, ref.residuals)
     gen.close()
+
+
+# ---- fused runs of statements on the small levels (evo_kernels_run.cuh) -------------------------------------------
+@pytest.mark.parametrize("name", ["p2", "el", "p3"])
+def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name):
+    """EVO_COARSE_FUSE: maximal runs of statements on small levels are interpreted by one cluster kernel; the residual
+    history must be bit-identical to one launch per statement (and to the oracle), with far fewer launches."""
+    import random
+    from evostencils_b200 import lowering, tree
+    prob = {"p2": problems.Poisson2D(3, 8), "el": problems.LinearElasticity2D(3, 7), "p3": problems.Poisson3D(2, 5)}[name]
+    rng = random.Random(5)
+    progs = [cycles.default_solver_cycle(prob), lowering.optimise(cycles.default_solver_cycle(prob))]
+    for _ in range(6):
+        s = tree.random_individual(prob, rng, maximum_local_system_size=4)
+        progs.append(lowering.optimise(lowering.lower_cycle(tree.build_tree(prob, s), prob.min_level, prob.max_level, prob.n_fields,
+                                                            prob.dim, cgs_max_iters=prob.settings.cgs_max_iters,
+                                                            cgs_tol=prob.settings.cgs_tol,
+                                                            default_restrict=prob.restrict_weights(),
+                                                            default_prolong=prob.prolong_weights())))
+    dev = cuda_backend.DeviceProblem(prob)
+    ref = oracle_mod.OracleProblem(prob)
+    st = prob.settings
+    fewer = 0
+    for prog in progs:
+        option("EVO_COARSE_FUSE", 0)
+        a = dev.build(prog).solve(st.tol, st.max_iters, 1)
+        option("EVO_COARSE_FUSE", 1)
+        b = dev.build(prog).solve(st.tol, st.max_iters, 1)
+        c = dev.build(prog).solve(st.tol, st.max_iters, 1, ol.SOLVE_NO_GRAPH)
+        o = ref.build(prog).solve(st.tol, st.max_iters, 1)
+        assert a.iterations == b.iterations == c.iterations == o.iterations
+        assert np.array_equal(a.residuals, b.residuals, equal_nan=True)
+        assert np.array_equal(b.residuals, c.residuals, equal_nan=True)
+        assert np.array_equal(b.residuals, o.residuals, equal_nan=True)
+        fewer += b.kernel_launches < a.kernel_launches
+    assert fewer >= len(progs) - 1
