@@ -30,7 +30,7 @@ enum {
     OPT_FAS_CGS_GLOBAL,  // EVO_FAS_CGS_GLOBAL  FAS coarse solver without shared memory
     OPT_LEX_VARIANT,     // EVO_LEX_VARIANT     lexicographic sweeps: 0 cluster wavefront, 1 single CTA
     OPT_STAR2D,          // EVO_STAR2D          0 = generic 2-D kernels only (no specialised 5-point path)
-    OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     0 = one launch per statement on the coarse levels
+    OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     fused runs on small levels: 0 off, 1 one CTA (default), 2 also clusters, 3 smallest only
     OPT_COUNT
 };
 struct OptionTable {

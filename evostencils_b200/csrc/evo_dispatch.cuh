@@ -463,7 +463,11 @@ template <typename T, int DIM, int NF> bool run_eligible(const evo_cycle *c, con
         const int l = op.level;
         if (l < p->desc.min_level || l > p->desc.max_level) return false;
         if (l - p->desc.min_level >= RUN_MAX_LEVELS) return false;
-        if (p->geom[l].n > (DIM == 2 ? 257 : 33)) return false;
+        // EVO_COARSE_FUSE: 1 (default) 2-D up to 129^2 / 3-D up to 17^3 in one CTA; 2 also 257^2 / 33^3 (thread-block
+        // cluster); 3 only up to 65^2 / 17^3
+        const int mode = option(OPT_COARSE_FUSE);
+        const int nmax = DIM == 2 ? (mode == 2 ? 257 : (mode == 3 ? 65 : 129)) : (mode == 2 ? 33 : 17);
+        if (p->geom[l].n > nmax) return false;
         switch (op.code) {
         case EVO_OP_ZERO: case EVO_OP_COPY: return true;
         case EVO_OP_RESIDUAL: return c->has_sten[l];
@@ -585,10 +589,14 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
                 default: return fail(EVO_ERR_INVALID, "statement %d cannot be part of a fused run", op.code);
                 }
             }
-            // one cluster: ~4 nodes per thread, at most 8 CTAs of 512 threads
+            int numax = 1;
+            for (int q = 0; q < m; ++q)
+                if (tab.op[q].code == EVO_OP_SMOOTH) numax = std::max(numax, tab.op[q].sp.nu);
+            // one CTA (block barriers) up to 16 nodes per thread, else a cluster of up to 8 CTAs
+            const int tmax = numax <= 2 ? 1024 : 512;
             int ctas = 1;
-            while (ctas < 8 && nodes_max > (long long)ctas * 2048) ctas *= 2;
-            const int threads = nodes_max >= 512 ? 512 : (int)((nodes_max + 31) / 32 * 32);
+            while (ctas < 8 && nodes_max > (long long)ctas * tmax * 16) ctas *= 2;
+            const int threads = nodes_max >= tmax ? tmax : (int)((nodes_max + 31) / 32 * 32);
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(ctas);
@@ -598,8 +606,16 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
-            cfg.numAttrs = 1;
-            CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF>, tab));
+            cfg.numAttrs = ctas > 1 ? 1 : 0;
+            if (ctas > 1) {
+                if (numax <= 2) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 2, true>, tab));
+                else if (numax <= 4) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 4, true>, tab));
+                else CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 8, true>, tab));
+            } else {
+                if (numax <= 2) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 2, false>, tab));
+                else if (numax <= 4) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 4, false>, tab));
+                else CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 8, false>, tab));
+            }
             c->launch_counter++;
         }
         return EVO_OK;

@@ -55,7 +55,14 @@ template <int DIM> __device__ __forceinline__ void run_node(int t, int ni, int &
     else { y = 1 + r; z = 0; }
 }
 
-template <int DIM, int NF, int NU>
+// barrier between dependent parts of a run: the whole cluster, or just the CTA when the run has one
+template <bool CLUSTER> __device__ __forceinline__ void run_barrier()
+{
+    if constexpr (CLUSTER) cluster_barrier();
+    else __syncthreads();
+}
+
+template <int DIM, int NF, int NU, bool CLUSTER>
 __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
 {
     const Geom &g = tab.geom[op.li];
@@ -77,7 +84,7 @@ __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &
                 run_node<DIM>(t, ni, x, y, z);
                 local_solve<double, DIM, NF, NU>(g, st, op.sp, src, dst, rhs, x, y, z);
             }
-            cluster_barrier();
+            run_barrier<CLUSTER>();
         }
     } else {   // red-black, order independent: colour 0 then colour 1, in place
         const Fields<double> u = run_fields<double>(op.a);
@@ -90,37 +97,43 @@ __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &
                     const int x = 1 + 2 * k + ((1 + y + z + color) & 1);
                     if (x <= ni) local_solve<double, DIM, NF, NU>(g, st, op.sp, u, u, rhs, x, y, z);
                 }
-                cluster_barrier();
+                run_barrier<CLUSTER>();
             }
     }
 }
 
-template <int DIM, int NF>
+// NUMAX: largest local system of the run's smoothers -- the register budget of the kernel is that of its most
+// expensive path, so runs with pointwise smoothers only get their own lean instantiation
+template <int DIM, int NF, int NUMAX, bool CLUSTER>
 __device__ __forceinline__ void run_smooth(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
 {
-    switch (op.sp.nu) {
-    case 1: run_smooth_nu<DIM, NF, 1>(tab, op, gtid, nthreads); break;
-    case 2: run_smooth_nu<DIM, NF, 2>(tab, op, gtid, nthreads); break;
-    case 3: run_smooth_nu<DIM, NF, 3>(tab, op, gtid, nthreads); break;
-    case 4: run_smooth_nu<DIM, NF, 4>(tab, op, gtid, nthreads); break;
-    case 5: run_smooth_nu<DIM, NF, 5>(tab, op, gtid, nthreads); break;
-    case 6: run_smooth_nu<DIM, NF, 6>(tab, op, gtid, nthreads); break;
-    case 7: run_smooth_nu<DIM, NF, 7>(tab, op, gtid, nthreads); break;
-    default: run_smooth_nu<DIM, NF, 8>(tab, op, gtid, nthreads); break;
+    const int nu = op.sp.nu;
+    if (nu == 1) run_smooth_nu<DIM, NF, 1, CLUSTER>(tab, op, gtid, nthreads);
+    if constexpr (NUMAX >= 2) { if (nu == 2) run_smooth_nu<DIM, NF, 2, CLUSTER>(tab, op, gtid, nthreads); }
+    if constexpr (NUMAX >= 4) {
+        if (nu == 3) run_smooth_nu<DIM, NF, 3, CLUSTER>(tab, op, gtid, nthreads);
+        if (nu == 4) run_smooth_nu<DIM, NF, 4, CLUSTER>(tab, op, gtid, nthreads);
+    }
+    if constexpr (NUMAX >= 8) {
+        if (nu == 5) run_smooth_nu<DIM, NF, 5, CLUSTER>(tab, op, gtid, nthreads);
+        if (nu == 6) run_smooth_nu<DIM, NF, 6, CLUSTER>(tab, op, gtid, nthreads);
+        if (nu == 7) run_smooth_nu<DIM, NF, 7, CLUSTER>(tab, op, gtid, nthreads);
+        if (nu == 8) run_smooth_nu<DIM, NF, 8, CLUSTER>(tab, op, gtid, nthreads);
     }
 }
 
-template <int DIM, int NF>
-__global__ void __launch_bounds__(512) k_run(const __grid_constant__ RunTable tab)
+template <int DIM, int NF, int NUMAX, bool CLUSTER>
+__global__ void __launch_bounds__(NUMAX <= 2 ? 1024 : 512) k_run(const __grid_constant__ RunTable tab)
 {
-    const int nthreads = (int)(cluster_nctarank() * blockDim.x), gtid = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+    const int nthreads = CLUSTER ? (int)(cluster_nctarank() * blockDim.x) : (int)blockDim.x;
+    const int gtid = CLUSTER ? (int)(cluster_ctarank() * blockDim.x + threadIdx.x) : (int)threadIdx.x;
     for (int q = 0; q < tab.n; ++q) {
         const RunOp &op = tab.op[q];
         const Geom &g = tab.geom[op.li];
         const int ni = g.n - 2, count = ni * ni * (DIM == 3 ? ni : 1);
         switch (op.code) {
         case EVO_OP_SMOOTH:
-            run_smooth<DIM, NF>(tab, op, gtid, nthreads);   // ends with a barrier
+            run_smooth<DIM, NF, NUMAX, CLUSTER>(tab, op, gtid, nthreads);   // ends with a barrier
             continue;
         case EVO_OP_ZERO:
 #pragma unroll
@@ -206,7 +219,7 @@ __global__ void __launch_bounds__(512) k_run(const __grid_constant__ RunTable ta
         }
         default: break;
         }
-        cluster_barrier();
+        run_barrier<CLUSTER>();
     }
 }
 
