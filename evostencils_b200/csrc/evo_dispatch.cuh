@@ -512,11 +512,14 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
         const int lbase = p->desc.min_level;
         for (int i0 = 0; i0 < n; i0 += RUN_MAX_OPS) {
             const int m = std::min(RUN_MAX_OPS, n - i0);
-            static RunTable tab;     // ~25 KB: keep it off the stack (the launch copies it; single-threaded host)
+            RunTable tab;
+            static_assert(sizeof(RunTable) <= 4000, "the run table travels as a kernel parameter");
             memset(&tab, 0, sizeof(tab));
             tab.n = m;
-            tab.R = p->R;
-            tab.P = p->P;
+            tab.lbase = lbase;
+            tab.sten = c->d_run_sten;
+            tab.sp = c->d_run_sp;
+            tab.rp = c->d_run_rp;
             long long nodes_max = 1;
             for (int q = 0; q < m; ++q) {
                 const evo_op &op = ops[i0 + q];
@@ -529,11 +532,7 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
                 r.mode = op.mode;
                 r.omega = op.omega;
                 tab.geom[r.li] = p->geom[l];
-                if (c->has_sten[l]) tab.sten[r.li] = c->sten[l];
-                if (r.lj >= 0) {
-                    tab.geom[r.lj] = p->geom[l - 1];
-                    if (c->has_sten[l - 1]) tab.sten[r.lj] = c->sten[l - 1];
-                }
+                if (r.lj >= 0) tab.geom[r.lj] = p->geom[l - 1];
                 const Geom &g = p->geom[l];
                 nodes_max = std::max(nodes_max, (long long)(g.n - 2) * (g.n - 2) * (DIM == 3 ? g.n - 2 : 1));
                 LevelMem &lv = c->lv[l];
@@ -563,16 +562,11 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
                     }
                     break;
                 case EVO_OP_SMOOTH: {
-                    SmoothParams &sp = r.sp;
-                    sp.nu = op.n_unknowns;
-                    sp.omega = op.omega;
-                    sp.write_all = 0;
-                    sp.color = -1;
-                    for (int a = 0; a < sp.nu; ++a) {
-                        sp.field[a] = op.unk_field[a];
-                        for (int d = 0; d < 3; ++d) sp.off[a][d] = d < DIM ? op.unk_off[a][d] : 0;
-                        r.written |= 1u << sp.field[a];
-                    }
+                    const ptrdiff_t idx = &op - c->ops.data();
+                    if (idx < 0 || idx >= (ptrdiff_t)c->ops.size()) return fail(EVO_ERR_INVALID, "fused runs take statements of the cycle");
+                    r.spi = (int)idx;
+                    r.nu = op.n_unknowns;
+                    for (int a = 0; a < op.n_unknowns; ++a) r.written |= 1u << op.unk_field[a];
                     for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[EVO_BUF_SOL][f]; r.b[f] = lv.slot[f]; r.c[f] = lv.buf[EVO_BUF_RHS][f]; }
                     if (op.mode == EVO_SMOOTH_JACOBI && (r.reps & 1)) {
                         // an odd number of out-of-place sweeps leaves the result in the [next] slots
@@ -591,7 +585,7 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
             }
             int numax = 1;
             for (int q = 0; q < m; ++q)
-                if (tab.op[q].code == EVO_OP_SMOOTH) numax = std::max(numax, tab.op[q].sp.nu);
+                if (tab.op[q].code == EVO_OP_SMOOTH) numax = std::max(numax, tab.op[q].nu);
             // one CTA (block barriers) up to 16 nodes per thread, else a cluster of up to 8 CTAs
             const int tmax = numax <= 2 ? 1024 : 512;
             int ctas = 1;

@@ -22,19 +22,22 @@ struct RunOp {
     int reps;                       // smoothing repetitions
     int mode;                       // evo_smooth_mode
     unsigned written;               // bit i: field i is written by the smoother (Jacobi: it alternates between its two slots)
+    int spi;                        // index of the smoother's descriptor in RunTable::sp
+    int nu;                         // size of its local system
     double omega;
-    SmoothParams sp;
     void *a[EVO_MAX_FIELDS];        // smooth: current slot | residual: u | restrict: src (fine) | prolong: src (coarse) | copy: src
     void *b[EVO_MAX_FIELDS];        // smooth: [next] slot  | residual: f | restrict: dst (coarse) | prolong: dst (fine) | copy / zero: dst
     void *c[EVO_MAX_FIELDS];        // smooth: rhs          | residual: r | residual+restrict: f (fine; a = u, b = dst coarse)
 };
 
+// < 4 KB: the table is a kernel parameter (copied at every launch); the bulky constants stay in device memory
 struct RunTable {
     int n;
-    int nthreads_hint;
+    int lbase;                       // level of table index 0
     Geom geom[RUN_MAX_LEVELS];
-    OpSten sten[RUN_MAX_LEVELS];
-    TransferW R, P;
+    const OpSten *sten;              // [EVO_MAX_LEVELS], indexed by level
+    const SmoothParams *sp;          // [number of statements of the cycle]
+    const TransferW *rp;             // restriction, prolongation
     RunOp op[RUN_MAX_OPS];
 };
 
@@ -66,7 +69,8 @@ template <int DIM, int NF, int NU, bool CLUSTER>
 __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
 {
     const Geom &g = tab.geom[op.li];
-    const OpSten &st = tab.sten[op.li];
+    const OpSten &st = tab.sten[tab.lbase + op.li];
+    const SmoothParams &sp = tab.sp[op.spi];
     const int ni = g.n - 2, count = ni * ni * (DIM == 3 ? ni : 1);
     const Fields<double> rhs = run_fields<double>(op.c);
     if (op.mode == EVO_SMOOTH_JACOBI) {
@@ -82,7 +86,7 @@ __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &
             for (int t = gtid; t < count; t += nthreads) {
                 int x, y, z;
                 run_node<DIM>(t, ni, x, y, z);
-                local_solve<double, DIM, NF, NU>(g, st, op.sp, src, dst, rhs, x, y, z);
+                local_solve<double, DIM, NF, NU>(g, st, sp, src, dst, rhs, x, y, z);
             }
             run_barrier<CLUSTER>();
         }
@@ -95,7 +99,7 @@ __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &
                     const int k = t % pairs, r = t / pairs;
                     const int y = 1 + (DIM == 3 ? r % ni : r), z = DIM == 3 ? 1 + r / ni : 0;
                     const int x = 1 + 2 * k + ((1 + y + z + color) & 1);
-                    if (x <= ni) local_solve<double, DIM, NF, NU>(g, st, op.sp, u, u, rhs, x, y, z);
+                    if (x <= ni) local_solve<double, DIM, NF, NU>(g, st, sp, u, u, rhs, x, y, z);
                 }
                 run_barrier<CLUSTER>();
             }
@@ -107,7 +111,7 @@ __device__ __forceinline__ void run_smooth_nu(const RunTable &tab, const RunOp &
 template <int DIM, int NF, int NUMAX, bool CLUSTER>
 __device__ __forceinline__ void run_smooth(const RunTable &tab, const RunOp &op, int gtid, int nthreads)
 {
-    const int nu = op.sp.nu;
+    const int nu = op.nu;
     if (nu == 1) run_smooth_nu<DIM, NF, 1, CLUSTER>(tab, op, gtid, nthreads);
     if constexpr (NUMAX >= 2) { if (nu == 2) run_smooth_nu<DIM, NF, 2, CLUSTER>(tab, op, gtid, nthreads); }
     if constexpr (NUMAX >= 4) {
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(NUMAX <= 2 ? 1024 : 512) k_run(const __grid_co
 {
     const int nthreads = CLUSTER ? (int)(cluster_nctarank() * blockDim.x) : (int)blockDim.x;
     const int gtid = CLUSTER ? (int)(cluster_ctarank() * blockDim.x + threadIdx.x) : (int)threadIdx.x;
+    const TransferW &R = tab.rp[0], &P = tab.rp[1];
     for (int q = 0; q < tab.n; ++q) {
         const RunOp &op = tab.op[q];
         const Geom &g = tab.geom[op.li];
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(NUMAX <= 2 ? 1024 : 512) k_run(const __grid_co
                 run_node<DIM>(t, ni, x, y, z);
                 const long long idx = node_index(g, x, y, z);
 #pragma unroll
-                for (int i = 0; i < NF; ++i) r.p[i][idx] = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[op.li], u, i, idx);
+                for (int i = 0; i < NF; ++i) r.p[i][idx] = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[tab.lbase + op.li], u, i, idx);
             }
             break;
         }
@@ -175,19 +180,19 @@ __global__ void __launch_bounds__(NUMAX <= 2 ? 1024 : 512) k_run(const __grid_co
 #pragma unroll
                 for (int i = 0; i < NF; ++i) {
                     double acc = 0.0;
-                    for (int p = 0; p < tab.R.nnz; ++p) {
-                        const int fx = 2 * x + tab.R.ox[p], fy = 2 * y + tab.R.oy[p], fz = DIM == 3 ? 2 * z + tab.R.oz[p] : 0;
+                    for (int p = 0; p < R.nnz; ++p) {
+                        const int fx = 2 * x + R.ox[p], fy = 2 * y + R.oy[p], fz = DIM == 3 ? 2 * z + R.oz[p] : 0;
                         double rv;
                         if (fused) {
                             rv = 0.0;  // the residual field is 0 on the boundary layer
                             if (fx >= 1 && fx <= g.n - 2 && fy >= 1 && fy <= g.n - 2 && (DIM == 2 || (fz >= 1 && fz <= g.n - 2))) {
                                 const long long idx = node_index(g, fx, fy, fz);
-                                rv = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[op.li], u, i, idx);
+                                rv = f.p[i][idx] - apply_row<double, NF>(g, tab.sten[tab.lbase + op.li], u, i, idx);
                             }
                         } else {
                             rv = u.p[i][node_index(g, fx, fy, fz)];
                         }
-                        acc = acc + tab.R.w[p] * rv;
+                        acc = acc + R.w[p] * rv;
                     }
                     dst.p[i][cidx] = acc;
                 }
@@ -206,10 +211,10 @@ __global__ void __launch_bounds__(NUMAX <= 2 ? 1024 : 512) k_run(const __grid_co
 #pragma unroll
                 for (int i = 0; i < NF; ++i) {
                     double acc = 0.0;
-                    for (int p = 0; p < tab.P.nnz; ++p) {
-                        const int cx = x + tab.P.ox[p], cy = y + tab.P.oy[p], cz = DIM == 3 ? z + tab.P.oz[p] : 0;
+                    for (int p = 0; p < P.nnz; ++p) {
+                        const int cx = x + P.ox[p], cy = y + P.oy[p], cz = DIM == 3 ? z + P.oz[p] : 0;
                         if ((cx & 1) || (cy & 1) || (DIM == 3 && (cz & 1))) continue;
-                        acc = acc + tab.P.w[p] * src.p[i][node_index(gc, cx >> 1, cy >> 1, cz >> 1)];
+                        acc = acc + P.w[p] * src.p[i][node_index(gc, cx >> 1, cy >> 1, cz >> 1)];
                     }
                     if (add) dst.p[i][idx] = dst.p[i][idx] + op.omega * acc;
                     else dst.p[i][idx] = acc;

@@ -337,7 +337,13 @@ static int allocate_cycle(evo_cycle *c)
         const Geom &gf = p->geom[hi];
         c->n_partials = nf * (gf.n - 2) * (gf.dim == 3 ? gf.n - 2 : 1);
         c->d_partials = (double *)take(sizeof(double) * ((size_t)c->n_partials + (size_t)nf * gf.n));
+        // constant tables of the fused runs (evo_kernels_run.cuh): behind everything a reset clears
+        const size_t zero_end = off;
+        c->d_run_sten = (OpSten *)take(sizeof(OpSten) * EVO_MAX_LEVELS);
+        c->d_run_sp = (SmoothParams *)take(sizeof(SmoothParams) * std::max<size_t>(1, c->ops.size()));
+        c->d_run_rp = (TransferW *)take(sizeof(TransferW) * 2);
         if (pass == 0) {
+            c->zero_bytes = zero_end;
             c->slab_bytes = off;
             c->slab_cap = off;
             c->slab = nullptr;
@@ -387,7 +393,7 @@ static int reset_cycle(evo_cycle *c, cudaStream_t s)
         if (c->lv[hi].slot[i]) skip.push_back({(char *)c->lv[hi].slot[i], fb});
     }
     std::sort(skip.begin(), skip.end());
-    char *cur = (char *)c->slab, *end = (char *)c->slab + c->slab_bytes;
+    char *cur = (char *)c->slab, *end = (char *)c->slab + c->zero_bytes;
     for (const auto &sk : skip) {
         if (sk.first > cur) CU(cudaMemsetAsync(cur, 0, (size_t)(sk.first - cur), s));
         cur = std::max(cur, sk.first + sk.second);
@@ -736,6 +742,35 @@ static int validate_ops(const evo_cycle *c)
 
 extern "C" int evo_cycle_destroy(evo_cycle *c);
 
+// stencils, transfer weights and the descriptors of the smoothers as the fused-run kernels read them (device memory)
+static int upload_run_tables(evo_cycle *c)
+{
+    evo_problem *p = c->p;
+    if (p->desc.kind != EVO_PROBLEM_LINEAR || p->desc.scalar_words != 1) return EVO_OK;
+    std::vector<SmoothParams> sp(std::max<size_t>(1, c->ops.size()));
+    for (size_t t = 0; t < c->ops.size(); ++t) {
+        const evo_op &op = c->ops[t];
+        SmoothParams &q = sp[t];
+        memset(&q, 0, sizeof(q));
+        if (op.code != EVO_OP_SMOOTH) continue;
+        q.nu = op.n_unknowns;
+        q.omega = op.omega;
+        q.color = -1;
+        q.write_all = 0;
+        for (int a = 0; a < q.nu && a < EVO_MAX_UNKNOWNS; ++a) {
+            q.field[a] = op.unk_field[a];
+            for (int d = 0; d < 3; ++d) q.off[a][d] = d < p->desc.dim ? op.unk_off[a][d] : 0;
+        }
+    }
+    TransferW rp[2] = {p->R, p->P};
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->d_run_sten, c->sten, sizeof(OpSten) * EVO_MAX_LEVELS, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_run_sp, sp.data(), sizeof(SmoothParams) * sp.size(), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->d_run_rp, rp, sizeof(rp), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));   // the sources are locals
+    return EVO_OK;
+}
+
 extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, const evo_level_operator *operators,
                                int n_operators, evo_cycle **out)
 {
@@ -821,6 +856,7 @@ extern "C" int evo_cycle_build(evo_problem *p, const evo_op *ops, int n_ops, con
         CU(cudaMallocHost(&c->h_state, sizeof(SolveState)));
     }
     rc = reset_cycle(c, c->stream);
+    if (rc == EVO_OK) rc = upload_run_tables(c);
     if (rc != EVO_OK) { evo_cycle_destroy(c); return rc; }
     CU(cudaStreamSynchronize(c->stream));
     *out = c;

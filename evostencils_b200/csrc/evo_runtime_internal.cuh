@@ -69,6 +69,10 @@ struct evo_cycle {
     void *slab;
     size_t slab_bytes;                // bytes in use (what a reset clears)
     size_t slab_cap = 0;              // bytes allocated (a recycled slab may be a little larger)
+    size_t zero_bytes = 0;            // a reset clears [slab, slab + zero_bytes); the constant tables below lie behind it
+    OpSten *d_run_sten = nullptr;     // device copies for the fused runs: sten[level], descriptors of the smoothers (per op),
+    SmoothParams *d_run_sp = nullptr; //   restriction / prolongation weights
+    TransferW *d_run_rp = nullptr;
     void *krylov[8][EVO_MAX_FIELDS];  // coarsest-level Krylov vectors
     void *scratch[EVO_MAX_FIELDS];    // finest-level scratch field (Richardson)
     void *helm[9];                    // Helmholtz outer solver: x, r, p, ap, s, t, h, rhat, row sums
