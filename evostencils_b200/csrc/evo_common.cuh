@@ -30,7 +30,7 @@ enum {
     OPT_FAS_CGS_GLOBAL,  // EVO_FAS_CGS_GLOBAL  FAS coarse solver without shared memory
     OPT_LEX_VARIANT,     // EVO_LEX_VARIANT     lexicographic sweeps: 0 cluster wavefront, 1 single CTA
     OPT_STAR2D,          // EVO_STAR2D          0 = generic 2-D kernels only (no specialised 5-point path)
-    OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     fused runs on small levels: 0 off, 1 one CTA (default), 2 also clusters, 3 smallest only
+    OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     fused runs on small levels: 0 off (default: measured slower), 1 one CTA, 2 also clusters, 3 smallest only
     OPT_COUNT
 };
 struct OptionTable {
@@ -49,7 +49,7 @@ inline OptionTable &option_table()
     static OptionTable t = {};
     return t;
 }
-inline int option_default(int id) { return (id == OPT_STAR2D || id == OPT_COARSE_FUSE) ? 1 : 0; }
+inline int option_default(int id) { return id == OPT_STAR2D ? 1 : 0; }
 inline int option(int id)
 {
     OptionTable &t = option_table();

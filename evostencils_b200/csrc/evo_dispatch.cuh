@@ -75,6 +75,29 @@ template <typename T, int DIM, int NF> struct Launch {
         int reps = op.count > 1 ? op.count : 1;
         Geom gsub = g;   // domain decomposition: a sub-range of the owned planes (boundary planes first, interior later)
         if (c->zc_lo >= 0 && slab_level(c->p, l)) { gsub.zlo = c->zc_lo; gsub.zhi = c->zc_hi; }
+        if constexpr (DIM == 2 && NF == 1 && NU == 1 && std::is_same<T, double>::value) {
+            // large 2-D grids, 5-point star: register-streamed warp kernels, up to two sweeps per pass over HBM (temporal
+            // blocking of the consecutive identical statements merged at build time); out of place into the [next] slot
+            if ((op.mode == EVO_SMOOTH_JACOBI || op.mode == EVO_SMOOTH_REDBLACK) && c->lv[l].slot[0] && !slab_level(c->p, l) &&
+                w2::star5_applicable(g, c->sten[l])) {
+                while (reps > 0) {
+                    const int k = reps >= 2 ? 2 : 1;
+                    const double *src = (const double *)c->lv[l].buf[EVO_BUF_SOL][0], *fp = (const double *)rhs.p[0];
+                    double *dst = (double *)c->lv[l].slot[0];
+                    const bool ok = op.mode == EVO_SMOOTH_JACOBI ? w2::try_jacobi(c->p->sm_count, g, c->sten[l], src, fp, dst, op.omega, k, s)
+                                                                 : w2::try_rbgs(c->p->sm_count, g, c->sten[l], src, fp, dst, op.omega, k, s);
+                    if (!ok) return fail(EVO_ERR_CUDA, "2-D streaming sweep: launch failed");
+                    c->launch_counter++;
+                    const bool cor_alias = c->lv[l].buf[EVO_BUF_COR][0] == c->lv[l].buf[EVO_BUF_SOL][0];
+                    std::swap(c->lv[l].buf[EVO_BUF_SOL][0], c->lv[l].slot[0]);
+                    if (cor_alias) c->lv[l].buf[EVO_BUF_COR][0] = c->lv[l].buf[EVO_BUF_SOL][0];
+                    c->lv[l].swapped[0] = !c->lv[l].swapped[0];
+                    reps -= k;
+                }
+                CU(cudaGetLastError());
+                return EVO_OK;
+            }
+        }
         if (NU == 1 && op.mode == EVO_SMOOTH_REDBLACK && c->lv[l].slot[0] && star::rbgs_stream_applicable<T, DIM, NF>(g, c->sten[l])) {
             // fused streaming kernel: up to 2 sweeps per pass, out of place into the [next] slot
             while (reps > 0) {

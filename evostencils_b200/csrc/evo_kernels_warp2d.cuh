@@ -1,0 +1,242 @@
+// evo_kernels_warp2d.cuh -- register-streamed pointwise sweeps for large 2-D grids, 5-point star (sm_100a).
+//
+// Statements: `solve locally at u@l [with jacobi] relax w {...}` with or without `color with { (i0+i1)%2 }`
+// (exastencils.py:659-682, :769-822) on a scalar real 5-point operator, and the Newton / Picard Jacobi smoother of the
+// FAS template (FAS_2D_Basic_template.exa4:65-73).  BASELINE configs[2] (FAS at 4097^2) and Poisson 2-D at 4097^2 ran
+// on the generic one-node-per-thread kernels at 28-36 % of the HBM peak (every sweep = 24 B/node, neighbours through
+// L1/L2, one launch per colour).
+//
+// Design: a WARP owns a strip of 64 consecutive nodes (32 x-pairs, 16-byte aligned) and marches through a chunk of
+// rows.  Rows are contiguous in HBM, so each lane fetches its pair with one coalesced 16-byte load, two rows ahead of
+// its use; the y-neighbours live in a 3-row register window, the x-neighbour outside the pair comes from the adjacent
+// lane by shuffle -- no shared memory, no block barrier, warps are independent.  NSTAGE dependent half-sweeps (RB-GS:
+// colours; Jacobi: whole sweeps) run as pipeline stages one row apart, each with its own register window: temporal
+// blocking -- k consecutive sweeps cost ONE pass over HBM (24 B/node for all of them).  A stage invalidates one more
+// node at each end of the strip (its x-neighbour is missing there), so a strip delivers 64 - 2*NSTAGE nodes; strips
+// and row chunks overlap accordingly (redundant halo work is recomputed identically: exact sequential semantics).
+// Out of place: reads SOL, writes the [next] slot.  Per node the arithmetic is that of the generic kernels / the
+// oracle (sum in ascending table order y-1, x-1, x+1, y+1; x = (f - s)*(1/a); u += w (x - u)), bit for bit.
+#pragma once
+#include "../../include/evo_math.h"
+#include "evo_kernels.cuh"
+
+namespace evo {
+namespace w2 {
+
+struct Star5 {  // ascending table order: y-1, x-1, centre, x+1, y+1
+    double ym, xm, c, xp, yp;
+};
+
+static bool match_star5(const Sten &s, Star5 *out)
+{
+    static const signed char ex[5][2] = {{0, -1}, {-1, 0}, {0, 0}, {1, 0}, {0, 1}};
+    if (s.nnz != 5) return false;
+    for (int q = 0; q < 5; ++q)
+        if (s.ox[q] != ex[q][0] || s.oy[q] != ex[q][1] || s.oz[q] != 0 || s.im[q] != 0.0) return false;
+    out->ym = s.re[0]; out->xm = s.re[1]; out->c = s.re[2]; out->xp = s.re[3]; out->yp = s.re[4];
+    return true;
+}
+
+// pointwise solve of the linear equation (weighted Jacobi / one colour of RB-GS)
+struct LinearPoint {
+    Star5 s;
+    double inv_c, omega;
+    __device__ __forceinline__ double operator()(double ym, double xm, double c, double xp, double yp, double f) const
+    {
+        double sum = 0.0;
+        sum = sum + s.ym * ym;
+        sum = sum + s.xm * xm;
+        sum = sum + s.xp * xp;
+        sum = sum + s.yp * yp;
+        const double xs = (f - sum) * inv_c;
+        return c + omega * (xs - c);
+    }
+};
+
+// `steps` damped Newton (or Picard) steps of  -Lap v + gamma v e^v = f  at one node (fas::fas_point, mg_fas.inc)
+struct FasPoint {
+    Star5 s;
+    double gamma, w;
+    int newton, steps;
+    __device__ __forceinline__ double operator()(double ym, double xm, double c, double xp, double yp, double f) const
+    {
+        double nb = 0.0;
+        nb = nb + s.ym * ym;
+        nb = nb + s.xm * xm;
+        nb = nb + s.xp * xp;
+        nb = nb + s.yp * yp;
+        double v = c;
+        for (int t = 0; t < steps; ++t) {
+            const double e = evo_exp(v);
+            const double num = f - ((nb + s.c * v) + gamma * e * v);
+            const double den = newton ? s.c + gamma * (1.0 + v) * e : s.c;
+            v = v + w * (num / den);
+        }
+        return v;
+    }
+};
+
+constexpr int W2_WARPS = 4;      // warps (adjacent strips) per CTA
+constexpr int W2_PF = 2;         // rows of load prefetch
+
+struct Pair {
+    double l, r;
+};
+
+__device__ __forceinline__ Pair load_pair(const double *__restrict__ row, int xl, int n)
+{
+    Pair p;
+    p.l = 0.0; p.r = 0.0;
+    if (xl >= 0) {
+        if (xl + 1 <= n - 1) {
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(row + xl));
+            p.l = v.x; p.r = v.y;
+        } else if (xl <= n - 1) {
+            p.l = __ldg(row + xl);
+        }
+    }
+    return p;
+}
+
+// NSTAGE pipeline stages; RB: stage s is colour s & 1 of sweep s / 2; else every stage is a whole Jacobi sweep.
+template <class U, int NSTAGE, bool RB>
+__global__ void __launch_bounds__(W2_WARPS * 32) k2_sweep_warp(const Geom g, const U upd, const double *__restrict__ u,
+                                                              const double *__restrict__ f, double *__restrict__ out,
+                                                              const int rows_per_chunk)
+{
+    constexpr int WINT = 64 - 2 * NSTAGE;                 // nodes a strip delivers
+    const int n = g.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * W2_WARPS + warp;
+    const int X0 = strip * WINT;                          // strip = nodes X0 .. X0+63, first pair at even x
+    if (X0 + NSTAGE > n - 2 && strip > 0) return;         // nothing to deliver (warps are independent: no barrier below)
+    const int xl = X0 + 2 * lane, xr = xl + 1;
+    const int out_lo = strip == 0 ? 1 : X0 + NSTAGE, out_hi = min(X0 + 63 - NSTAGE, n - 2);
+    const bool in_l = xl >= 1 && xl <= n - 2, in_r = xr >= 1 && xr <= n - 2;
+    const bool st_l = xl >= out_lo && xl <= out_hi, st_r = xr >= out_lo && xr <= out_hi;
+    const int ya = 1 + blockIdx.y * rows_per_chunk, yb = min(ya + rows_per_chunk - 1, n - 2);
+    const int rlo = max(0, ya - NSTAGE), rhi = min(n - 1, yb + NSTAGE);   // raw rows this chunk reads
+    const long long pitch = g.pitch;
+
+    // win[b]: rows (r-1, r, r+1) of the values entering stage b; fw[s]: right-hand side of the row stage s works on
+    Pair win[NSTAGE][3];
+    Pair fw[NSTAGE];
+    Pair pre_u[W2_PF], pre_f[W2_PF];
+#pragma unroll
+    for (int b = 0; b < NSTAGE; ++b) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { win[b][k].l = 0.0; win[b][k].r = 0.0; }
+        fw[b].l = 0.0; fw[b].r = 0.0;
+    }
+    // step t: stage s works on row t - s; raw row t + 1 and the right-hand side of row t enter the pipeline
+    const int t_first = rlo, t_last = yb + NSTAGE - 1;
+    // prologue: window rows rlo - 1 (unused), rlo; prefetch ring holds raw rows t+1 .. t+PF and f rows t .. t+PF-1
+    win[0][2] = load_pair(u + (long long)rlo * pitch, xl, n);
+#pragma unroll
+    for (int k = 0; k < W2_PF; ++k) {
+        const int ru = t_first + 1 + k, rf = t_first + k;
+        pre_u[k] = ru <= rhi ? load_pair(u + (long long)ru * pitch, xl, n) : Pair{0.0, 0.0};
+        pre_f[k] = rf <= rhi ? load_pair(f + (long long)rf * pitch, xl, n) : Pair{0.0, 0.0};
+    }
+    for (int t = t_first; t <= t_last; ++t) {
+        // rotate the windows, take raw row t+1 / rhs row t out of the prefetch ring, refill the ring
+#pragma unroll
+        for (int b = 0; b < NSTAGE; ++b) { win[b][0] = win[b][1]; win[b][1] = win[b][2]; }
+#pragma unroll
+        for (int s = NSTAGE - 1; s > 0; --s) fw[s] = fw[s - 1];
+        win[0][2] = pre_u[0];
+        fw[0] = pre_f[0];
+#pragma unroll
+        for (int k = 0; k + 1 < W2_PF; ++k) { pre_u[k] = pre_u[k + 1]; pre_f[k] = pre_f[k + 1]; }
+        {
+            const int ru = t + 1 + W2_PF, rf = t + W2_PF;
+            pre_u[W2_PF - 1] = ru <= rhi ? load_pair(u + (long long)ru * pitch, xl, n) : Pair{0.0, 0.0};
+            pre_f[W2_PF - 1] = rf <= rhi ? load_pair(f + (long long)rf * pitch, xl, n) : Pair{0.0, 0.0};
+        }
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            const int r = t - s;
+            if (r < rlo || r > rhi) continue;                                  // warp uniform
+            // rows this stage updates: the chunk plus the halo the later stages still need, inner rows only
+            const int a_lo = max(1, ya - (NSTAGE - 1 - s)), a_hi = min(n - 2, yb + (NSTAGE - 1 - s));
+            Pair o = win[s][1];                                                // default: pass through
+            if (r >= a_lo && r <= a_hi) {
+                const Pair m = win[s][1], up = win[s][0], dn = win[s][2];
+                // x-neighbours outside the pair come from the adjacent lanes
+                const double left = __shfl_up_sync(0xffffffffu, m.r, 1);
+                const double right = __shfl_down_sync(0xffffffffu, m.l, 1);
+                if (RB) {
+                    // colour of stage s: nodes with (x + y) % 2 == s % 2; x_l is even
+                    const bool l_active = ((r + s) & 1) == 0;
+                    if (l_active) { if (in_l) o.l = upd(up.l, left, m.l, m.r, dn.l, fw[s].l); }
+                    else { if (in_r) o.r = upd(up.r, m.l, m.r, right, dn.r, fw[s].r); }
+                } else {
+                    if (in_l) o.l = upd(up.l, left, m.l, m.r, dn.l, fw[s].l);
+                    if (in_r) o.r = upd(up.r, m.l, m.r, right, dn.r, fw[s].r);
+                }
+            }
+            if (s + 1 < NSTAGE) {
+                win[s + 1][2] = o;
+            } else if (r >= ya && r <= yb) {
+                double *dst = out + (long long)r * pitch + xl;
+                if (st_l && st_r) *reinterpret_cast<double2 *>(dst) = make_double2(o.l, o.r);
+                else if (st_l) dst[0] = o.l;
+                else if (st_r) dst[1] = o.r;
+            }
+        }
+    }
+}
+
+template <class U, int NSTAGE, bool RB>
+static bool launch_sweep(int sm_count, const Geom &g, const U &upd, const double *u, const double *f, double *out, cudaStream_t s)
+{
+    constexpr int WINT = 64 - 2 * NSTAGE;
+    const int inner = g.n - 2;
+    // strips: strip k delivers nodes k*WINT + NSTAGE .. k*WINT + 63 - NSTAGE (strip 0 from node 1)
+    int strips = 1;
+    while (strips * WINT + 63 - NSTAGE - WINT < inner) ++strips;     // last delivered node >= n - 2
+    const int bx = (strips + W2_WARPS - 1) / W2_WARPS;
+    // row chunks: enough CTAs for ~2 waves of full occupancy, at least 16 rows each (halo rows are redundant work)
+    const long long want = (long long)sm_count * 16;
+    int chunks = (int)std::min<long long>(std::max<long long>(1, want / bx), std::max(1, inner / 16));
+    int rows = (inner + chunks - 1) / chunks;
+    chunks = (inner + rows - 1) / rows;
+    k2_sweep_warp<U, NSTAGE, RB><<<dim3(bx, chunks), W2_WARPS * 32, 0, s>>>(g, upd, u, f, out, rows);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+// minimum grid size for the streaming path (smaller grids are latency bound: the generic kernels are as good)
+constexpr int W2_MIN_N = 129;
+
+// k (1 or 2) consecutive weighted-Jacobi sweeps u -> out
+static bool try_jacobi(int sm_count, const Geom &g, const OpSten &st, const double *u, const double *f, double *out, double omega, int k,
+                       cudaStream_t s)
+{
+    Star5 c;
+    if (g.dim != 2 || g.n < W2_MIN_N || option(OPT_STAR2D) == 0 || !match_star5(st.s[0][0], &c)) return false;
+    LinearPoint upd{c, 1.0 / c.c, omega};
+    if (k == 1) return launch_sweep<LinearPoint, 1, false>(sm_count, g, upd, u, f, out, s);
+    if (k == 2) return launch_sweep<LinearPoint, 2, false>(sm_count, g, upd, u, f, out, s);
+    return false;
+}
+
+// k (1 or 2) consecutive red-black Gauss-Seidel sweeps u -> out
+static bool try_rbgs(int sm_count, const Geom &g, const OpSten &st, const double *u, const double *f, double *out, double omega, int k,
+                     cudaStream_t s)
+{
+    Star5 c;
+    if (g.dim != 2 || g.n < W2_MIN_N || option(OPT_STAR2D) == 0 || !match_star5(st.s[0][0], &c)) return false;
+    LinearPoint upd{c, 1.0 / c.c, omega};
+    if (k == 1) return launch_sweep<LinearPoint, 2, true>(sm_count, g, upd, u, f, out, s);
+    if (k == 2) return launch_sweep<LinearPoint, 4, true>(sm_count, g, upd, u, f, out, s);
+    return false;
+}
+
+static bool star5_applicable(const Geom &g, const OpSten &st)
+{
+    Star5 c;
+    return g.dim == 2 && g.n >= W2_MIN_N && option(OPT_STAR2D) != 0 && match_star5(st.s[0][0], &c);
+}
+
+}  // namespace w2
+}  // namespace evo

@@ -263,8 +263,10 @@ extern "C" int evo_problem_set_field(evo_problem *p, int level, int buf, int fie
 static bool rb_stream_candidate(const evo_cycle *c, const evo_op &op)
 {
     const evo_problem_desc &d = c->p->desc;
+    // (3-D: k3_rbgs_col from 33^3; 2-D: the register-streamed warp kernels from 129^2)
     return op.code == EVO_OP_SMOOTH && op.mode == EVO_SMOOTH_REDBLACK && op.kind == EVO_KIND_LINEAR && op.n_unknowns == 1 &&
-           d.dim == 3 && d.n_fields == 1 && d.scalar_words == 1 && c->p->geom[op.level].n >= 33;
+           d.n_fields == 1 && d.scalar_words == 1 && d.kind == EVO_PROBLEM_LINEAR &&
+           ((d.dim == 3 && c->p->geom[op.level].n >= 33) || (d.dim == 2 && c->p->geom[op.level].n >= w2::W2_MIN_N));
 }
 static bool level_needs_slot(const evo_cycle *c, int level)
 {
@@ -457,6 +459,17 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
         const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
         if (op.mode == EVO_SMOOTH_JACOBI) {
             if (!c->lv[l].slot[0]) return fail(EVO_ERR_INVALID, "missing jacobi slot");
+            w2::Star5 c5;
+            if (w2::star5_applicable(g, c->sten[l]) && w2::match_star5(c->sten[l].s[0][0], &c5)) {
+                // large grids: register-streamed warp kernel (evo_kernels_warp2d.cuh)
+                w2::FasPoint upd{c5, gamma, op.omega, newton, steps};
+                if (!w2::launch_sweep<w2::FasPoint, 1, false>(c->p->sm_count, g, upd, (const double *)c->lv[l].buf[EVO_BUF_SOL][0], f,
+                                                              (double *)c->lv[l].slot[0], s))
+                    return fail(EVO_ERR_CUDA, "FAS streaming sweep: launch failed");
+                c->launch_counter++;
+                swap_slot(l);
+                return EVO_OK;
+            }
             fas::k2_fas_smooth<<<row_grid(g), BX, 0, s>>>(g, L, gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
                                                          (double *)c->lv[l].slot[0], f, newton, steps, op.omega, -1);
             c->launch_counter++;
@@ -546,9 +559,26 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
             // a "coarsest" grid too large for one CTA (BASELINE config 4097^2 has 257^2 there): one launch per sweep
             // over all SMs, ping-pong between the two SOL slots; the per-node arithmetic is that of k2_fas_coarse
             const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
-            for (int t = 0; t < op.count; ++t) {
-                fas::k2_fas_smooth<<<row_grid(g), BX, 0, s>>>(g, L, gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
-                                                             (double *)c->lv[l].slot[0], f, 1, 1, op.omega, -1);
+            w2::Star5 c5;
+            const bool stream = w2::star5_applicable(g, c->sten[l]) && w2::match_star5(c->sten[l].s[0][0], &c5);
+            for (int t = 0; t < op.count;) {
+                if (stream) {
+                    // four (two, one) Newton-Jacobi sweeps per launch: the pipeline stages of the streaming kernel
+                    w2::FasPoint upd{c5, gamma, op.omega, 1, 1};
+                    const int k = op.count - t >= 4 ? 4 : (op.count - t >= 2 ? 2 : 1);
+                    const double *src = (const double *)c->lv[l].buf[EVO_BUF_SOL][0];
+                    double *dst = (double *)c->lv[l].slot[0];
+                    bool ok;
+                    if (k == 4) ok = w2::launch_sweep<w2::FasPoint, 4, false>(c->p->sm_count, g, upd, src, f, dst, s);
+                    else if (k == 2) ok = w2::launch_sweep<w2::FasPoint, 2, false>(c->p->sm_count, g, upd, src, f, dst, s);
+                    else ok = w2::launch_sweep<w2::FasPoint, 1, false>(c->p->sm_count, g, upd, src, f, dst, s);
+                    if (!ok) return fail(EVO_ERR_CUDA, "FAS streaming sweep: launch failed");
+                    t += k;
+                } else {
+                    fas::k2_fas_smooth<<<row_grid(g), BX, 0, s>>>(g, L, gamma, (const double *)c->lv[l].buf[EVO_BUF_SOL][0],
+                                                                 (double *)c->lv[l].slot[0], f, 1, 1, op.omega, -1);
+                    ++t;
+                }
                 c->launch_counter++;
                 swap_slot(l);
             }

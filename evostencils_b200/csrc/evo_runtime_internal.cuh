@@ -14,6 +14,7 @@
 #include "evo_kernels.cuh"
 #include "evo_kernels_star.cuh"
 #include "evo_kernels_rbcol.cuh"
+#include "evo_kernels_warp2d.cuh"
 #include "evo_kernels_fas.cuh"
 #include "evo_kernels_helm.cuh"
 

@@ -179,3 +179,49 @@ def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name
         assert np.array_equal(b.residuals, o.residuals, equal_nan=True)
         fewer += b.kernel_launches < a.kernel_launches
     assert fewer >= len(progs) - 1
+
+
+# ---- register-streamed 2-D sweeps (evo_kernels_warp2d.cuh) ---------------------------------------------------------
+@pytest.mark.parametrize("star2d", [1, 0])
+@pytest.mark.parametrize("level,mode,sweeps", [(7, "rb", 1), (8, "rb", 2), (9, "rb", 3), (10, "rb", 2), (7, "jac", 1), (8, "jac", 2),
+                                               (9, "jac", 3), (10, "jac", 1)])
+def test_streamed_2d_sweeps_bit_exact(cuda_backend, oracle_mod, option, star2d, level, mode, sweeps):
+    """Pointwise Jacobi / RB-GS on large 2-D grids: up to two consecutive sweeps per pass (temporal blocking), strips and
+    row chunks with redundant halo work -- bit-identical to the plain loops of the oracle; EVO_STAR2D=0 = generic kernels."""
+    option("EVO_STAR2D", star2d)
+    prob = problems.Poisson2D(level - 1, level)
+    z = (0, 0)
+    m = ol.MODE_REDBLACK if mode == "rb" else ol.MODE_JACOBI
+    ops = [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_JACOBI, omega=0.9, unknowns=((0, z),))]
+    ops += [ol.Op(ol.OP_SMOOTH, level, mode=m, omega=1.15 if mode == "rb" else 0.8, unknowns=((0, z),)) for _ in range(sweeps)]
+    ops += [ol.Op(ol.OP_RESIDUAL, level, dst=ol.BUF_RES)]
+    prog = cycles.build_program(prob, ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [level], (ol.BUF_SOL, ol.BUF_RES))
+
+
+def test_streamed_2d_default_solver_1025(cuda_backend, oracle_mod):
+    prob = problems.Poisson2D(5, 10)
+    prog = cycles.default_solver_cycle(prob)
+    s = prob.settings
+    a = cuda_backend.DeviceProblem(prob).build(prog).solve(s.tol, s.max_iters, 1)
+    b = oracle_mod.OracleProblem(prob).build(prog).solve(s.tol, s.max_iters, 1)
+    assert a.iterations == b.iterations and np.array_equal(a.residuals, b.residuals)
+
+
+@pytest.mark.parametrize("star2d", [1, 0])
+def test_streamed_fas_sweeps(cuda_backend, oracle_mod, option, star2d):
+    """FAS Newton-Jacobi smoother and the 200-sweep coarse solver on a 129^2 coarsest grid (4 / 2 / 1 sweeps per launch)."""
+    option("EVO_STAR2D", star2d)
+    prob = problems.FAS2D(7, 9)
+    prog = cycles.fas_v_cycle(prob)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [7, 8, 9], (ol.BUF_SOL,))
