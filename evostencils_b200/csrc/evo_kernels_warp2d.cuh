@@ -196,24 +196,29 @@ static bool launch_sweep(int sm_count, const Geom &g, const U &upd, const double
     int strips = 1;
     while (strips * WINT + 63 - NSTAGE - WINT < inner) ++strips;     // last delivered node >= n - 2
     const int bx = (strips + W2_WARPS - 1) / W2_WARPS;
-    // row chunks: enough CTAs for ~2 waves of full occupancy, at least 16 rows each (halo rows are redundant work)
-    const long long want = (long long)sm_count * 16;
-    int chunks = (int)std::min<long long>(std::max<long long>(1, want / bx), std::max(1, inner / 16));
+    // row chunks: ~32 warps per SM when the grid allows it, at least max(4, 2 NSTAGE) rows each (a chunk recomputes
+    // NSTAGE halo rows at both ends)
+    const long long want_warps = (long long)sm_count * 32;
+    const int min_rows = std::max(4, 2 * NSTAGE);
+    int chunks = (int)std::min<long long>(std::max<long long>(1, want_warps / strips), std::max(1, inner / min_rows));
     int rows = (inner + chunks - 1) / chunks;
     chunks = (inner + rows - 1) / rows;
     k2_sweep_warp<U, NSTAGE, RB><<<dim3(bx, chunks), W2_WARPS * 32, 0, s>>>(g, upd, u, f, out, rows);
     return cudaGetLastError() == cudaSuccess;
 }
 
-// minimum grid size for the streaming path (smaller grids are latency bound: the generic kernels are as good)
-constexpr int W2_MIN_N = 129;
+// minimum grid size for the streaming path (smaller grids are latency bound: the one-node-per-thread kernels are as
+// good or better).  EVO_STAR2D: 0 = never, 1 = default threshold, n >= 2 = use the streaming kernels from n nodes per
+// dimension (tests).  W2_MIN_N is the smallest size the kernels support at all (slot allocation).
+constexpr int W2_MIN_N = 65;
+inline int min_n() { const int v = option(OPT_STAR2D); return v <= 0 ? (1 << 30) : (v == 1 ? 513 : std::max(v, W2_MIN_N)); }
 
 // k (1 or 2) consecutive weighted-Jacobi sweeps u -> out
 static bool try_jacobi(int sm_count, const Geom &g, const OpSten &st, const double *u, const double *f, double *out, double omega, int k,
                        cudaStream_t s)
 {
     Star5 c;
-    if (g.dim != 2 || g.n < W2_MIN_N || option(OPT_STAR2D) == 0 || !match_star5(st.s[0][0], &c)) return false;
+    if (g.dim != 2 || g.n < min_n() || !match_star5(st.s[0][0], &c)) return false;
     LinearPoint upd{c, 1.0 / c.c, omega};
     if (k == 1) return launch_sweep<LinearPoint, 1, false>(sm_count, g, upd, u, f, out, s);
     if (k == 2) return launch_sweep<LinearPoint, 2, false>(sm_count, g, upd, u, f, out, s);
@@ -225,7 +230,7 @@ static bool try_rbgs(int sm_count, const Geom &g, const OpSten &st, const double
                      cudaStream_t s)
 {
     Star5 c;
-    if (g.dim != 2 || g.n < W2_MIN_N || option(OPT_STAR2D) == 0 || !match_star5(st.s[0][0], &c)) return false;
+    if (g.dim != 2 || g.n < min_n() || !match_star5(st.s[0][0], &c)) return false;
     LinearPoint upd{c, 1.0 / c.c, omega};
     if (k == 1) return launch_sweep<LinearPoint, 2, true>(sm_count, g, upd, u, f, out, s);
     if (k == 2) return launch_sweep<LinearPoint, 4, true>(sm_count, g, upd, u, f, out, s);
@@ -235,7 +240,7 @@ static bool try_rbgs(int sm_count, const Geom &g, const OpSten &st, const double
 static bool star5_applicable(const Geom &g, const OpSten &st)
 {
     Star5 c;
-    return g.dim == 2 && g.n >= W2_MIN_N && option(OPT_STAR2D) != 0 && match_star5(st.s[0][0], &c);
+    return g.dim == 2 && g.n >= min_n() && match_star5(st.s[0][0], &c);
 }
 
 }  // namespace w2

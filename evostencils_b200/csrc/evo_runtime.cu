@@ -560,7 +560,8 @@ static int fas_dispatch(evo_cycle *c, const evo_op &op, cudaStream_t s)
             // over all SMs, ping-pong between the two SOL slots; the per-node arithmetic is that of k2_fas_coarse
             const double *f = (const double *)c->lv[l].buf[EVO_BUF_RHS][0];
             w2::Star5 c5;
-            const bool stream = w2::star5_applicable(g, c->sten[l]) && w2::match_star5(c->sten[l].s[0][0], &c5);
+            // (a coarsest grid below ~1025^2 is latency bound: one launch per sweep over all SMs is faster than fused sweeps)
+            const bool stream = g.n >= 1025 && w2::star5_applicable(g, c->sten[l]) && w2::match_star5(c->sten[l].s[0][0], &c5);
             for (int t = 0; t < op.count;) {
                 if (stream) {
                     // four (two, one) Newton-Jacobi sweeps per launch: the pipeline stages of the streaming kernel

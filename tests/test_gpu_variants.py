@@ -182,12 +182,13 @@ def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name
 
 
 # ---- register-streamed 2-D sweeps (evo_kernels_warp2d.cuh) ---------------------------------------------------------
-@pytest.mark.parametrize("star2d", [1, 0])
+@pytest.mark.parametrize("star2d", [65, 1, 0])
 @pytest.mark.parametrize("level,mode,sweeps", [(7, "rb", 1), (8, "rb", 2), (9, "rb", 3), (10, "rb", 2), (7, "jac", 1), (8, "jac", 2),
                                                (9, "jac", 3), (10, "jac", 1)])
 def test_streamed_2d_sweeps_bit_exact(cuda_backend, oracle_mod, option, star2d, level, mode, sweeps):
     """Pointwise Jacobi / RB-GS on large 2-D grids: up to two consecutive sweeps per pass (temporal blocking), strips and
-    row chunks with redundant halo work -- bit-identical to the plain loops of the oracle; EVO_STAR2D=0 = generic kernels."""
+    row chunks with redundant halo work -- bit-identical to the plain loops of the oracle; EVO_STAR2D = 0: generic kernels,
+    1: streaming from 513^2 (default), n: streaming from n^2."""
     option("EVO_STAR2D", star2d)
     prob = problems.Poisson2D(level - 1, level)
     z = (0, 0)
@@ -213,7 +214,7 @@ def test_streamed_2d_default_solver_1025(cuda_backend, oracle_mod):
     assert a.iterations == b.iterations and np.array_equal(a.residuals, b.residuals)
 
 
-@pytest.mark.parametrize("star2d", [1, 0])
+@pytest.mark.parametrize("star2d", [65, 1, 0])
 def test_streamed_fas_sweeps(cuda_backend, oracle_mod, option, star2d):
     """FAS Newton-Jacobi smoother and the 200-sweep coarse solver on a 129^2 coarsest grid (4 / 2 / 1 sweeps per launch)."""
     option("EVO_STAR2D", star2d)
