@@ -323,7 +323,11 @@ template <typename T, int DIM, int NF> struct Launch {
         if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
-        if (!star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
+        bool done2d = false;
+        if constexpr (DIM == 2 && NF == 1 && std::is_same<T, double>::value)
+            done2d = !slab_level(c->p, l) && w2::try_residual_restrict(c->p->sm_count, gf, gc, c->sten[l], c->p->R, (const double *)u.p[0],
+                                                                      (const double *)f.p[0], (double *)dst.p[0], s);
+        if (!done2d && !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
             if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
             k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
         }
@@ -341,7 +345,10 @@ template <typename T, int DIM, int NF> struct Launch {
         auto src = fields_of<T>(c->lv[l - 1].buf[op.src], NF);
         auto dst = fields_of<T>(c->lv[l].buf[add ? EVO_BUF_SOL : op.dst], NF);
         if (add) {
-            if (!star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s)) {
+            bool done2d = false;
+            if constexpr (DIM == 2 && NF == 1 && std::is_same<T, double>::value)
+                done2d = !slab_level(c->p, l) && w2::try_prolong_add(gf, gc, c->p->P, (const double *)src.p[0], (double *)dst.p[0], op.omega, s);
+            if (!done2d && !star::try_prolong_add<T, DIM, NF>(c->p->sm_count, gf, gc, c->p->P, src, dst, op.omega, s)) {
                 if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: prolongation needs the fast path");
                 k_prolong<T, DIM, NF, true><<<row_grid(gf), BX, 0, s>>>(gf, gc, c->p->P, src, dst, op.omega);
             }

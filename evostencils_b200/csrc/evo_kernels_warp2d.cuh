@@ -243,5 +243,163 @@ static bool star5_applicable(const Geom &g, const OpSten &st)
     return g.dim == 2 && g.n >= min_n() && match_star5(st.s[0][0], &c);
 }
 
+// ---------------------------------------------------------------------------------------------
+// u@l += w * (P@(l-1) * e@(l-1)), bilinear prolongation, 2-D: one thread per coarse cell (X, Y) updates the four fine
+// nodes (2X..2X+1, 2Y..2Y+1) with two coalesced 16-byte read-modify-writes.  Per fine node the terms are added in
+// ascending stencil-table order of the offsets o with x + o even (the order of k_prolong and of the oracle).
+struct Dense9 { double w[9]; };   // index (oy + 1) * 3 + (ox + 1)
+
+static __global__ void __launch_bounds__(128) k2_prolong_add(const Geom gf, const Geom gc, const Dense9 P, const double *__restrict__ ec,
+                                                      double *__restrict__ u, const double weight)
+{
+    const int X = blockIdx.x * 128 + threadIdx.x, Y = blockIdx.y;
+    if (X > gc.n - 2) return;
+    const double *r0 = ec + (long long)Y * gc.pitch + X, *r1 = r0 + gc.pitch;
+    const double e00 = r0[0], e01 = r0[1], e10 = r1[0], e11 = r1[1];     // e[dy][dx]
+    const int n2 = gf.n - 2;
+    // fine row 2Y (even): even x takes o = (0, 0); odd x takes o = (0, -1) then (0, +1)
+    if (Y > 0) {
+        double2 *up = reinterpret_cast<double2 *>(u + (long long)(2 * Y) * gf.pitch + 2 * X);
+        double2 v = *up;
+        double p0 = 0.0, p1 = 0.0;
+        p0 = p0 + P.w[4] * e00;
+        p1 = p1 + P.w[3] * e00;
+        p1 = p1 + P.w[5] * e01;
+        if (X > 0) v.x = v.x + weight * p0;     // fine x = 0 is the boundary layer
+        v.y = v.y + weight * p1;                // fine x = 2X+1 <= n-2 always
+        *up = v;
+    }
+    // fine row 2Y+1 (odd): even x takes o = (-1, 0) then (+1, 0); odd x the four corners in table order
+    if (2 * Y + 1 <= n2) {
+        double2 *up = reinterpret_cast<double2 *>(u + (long long)(2 * Y + 1) * gf.pitch + 2 * X);
+        double2 v = *up;
+        double p0 = 0.0, p1 = 0.0;
+        p0 = p0 + P.w[1] * e00;
+        p0 = p0 + P.w[7] * e10;
+        p1 = p1 + P.w[0] * e00;
+        p1 = p1 + P.w[2] * e01;
+        p1 = p1 + P.w[6] * e10;
+        p1 = p1 + P.w[8] * e11;
+        if (X > 0) v.x = v.x + weight * p0;
+        v.y = v.y + weight * p1;
+        *up = v;
+    }
+}
+
+static bool try_prolong_add(const Geom &gf, const Geom &gc, const TransferW &P, const double *src, double *dst, double weight, cudaStream_t s)
+{
+    if (gf.dim != 2 || gf.n < min_n()) return false;
+    Dense9 W;
+    for (int i = 0; i < 9; ++i) W.w[i] = 0.0;
+    for (int q = 0; q < P.nnz; ++q) {
+        if (P.oz[q] != 0) return false;
+        W.w[(P.oy[q] + 1) * 3 + (P.ox[q] + 1)] = P.w[q];
+    }
+    const int cells = gc.n - 1;
+    k2_prolong_add<<<dim3((cells + 127) / 128, cells), 128, 0, s>>>(gf, gc, W, src, dst, weight);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused RHS@(l-1) = R@l * (f@l - A@l u@l), 2-D 5-point operator, dense 9-point restriction: the fine residual never
+// reaches HBM (16 B per fine node read + 2 B written instead of 24 + 10).  Same warp-strip streaming as the sweeps:
+// a lane owns the fine pair (2X, 2X+1) and the coarse node X; the residual rows 2Y-1, 2Y, 2Y+1 live in a register
+// window, the residual at 2X-1 comes from the left lane by shuffle.  The 9 terms are added in ascending table order
+// like k_residual_restrict / the oracle; the residual counts as 0 on the boundary layer.
+static __global__ void __launch_bounds__(W2_WARPS * 32) k2_residual_restrict_warp(const Geom gf, const Geom gc, const Star5 c, const Dense9 R,
+                                                                          const double *__restrict__ u, const double *__restrict__ f,
+                                                                          double *__restrict__ dst, const int rows_per_chunk)
+{
+    const int n = gf.n, nc = gc.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * W2_WARPS + warp;
+    const int X0 = strip * 62;                             // fine nodes X0 .. X0+63; lanes 1..31 deliver coarse nodes X0/2 + lane
+    if (X0 / 2 + 1 > nc - 2) return;
+    const int xl = X0 + 2 * lane, xr = xl + 1;
+    const int X = xl / 2;
+    const bool in_l = xl >= 1 && xl <= n - 2, in_r = xr >= 1 && xr <= n - 2;
+    const bool deliver = lane >= 1 && X >= 1 && X <= nc - 2;
+    const int Ya = 1 + blockIdx.y * rows_per_chunk, Yb = min(Ya + rows_per_chunk - 1, nc - 2);
+    const long long pitch = gf.pitch;
+    const int r_first = 2 * Ya - 1, r_last = 2 * Yb + 1;    // fine residual rows of the chunk (all inner rows)
+    Pair um, u0, up;                                        // u rows r-1, r, r+1
+    Pair rm = {0.0, 0.0}, r0 = {0.0, 0.0};                  // residual rows r-2, r-1
+    um = load_pair(u + (long long)(r_first - 1) * pitch, xl, n);
+    u0 = load_pair(u + (long long)r_first * pitch, xl, n);
+    Pair pre_u[W2_PF], pre_f[W2_PF];
+#pragma unroll
+    for (int k = 0; k < W2_PF; ++k) {
+        const int ru = r_first + 1 + k, rf = r_first + k;
+        pre_u[k] = ru <= n - 1 ? load_pair(u + (long long)ru * pitch, xl, n) : Pair{0.0, 0.0};
+        pre_f[k] = rf <= r_last ? load_pair(f + (long long)rf * pitch, xl, n) : Pair{0.0, 0.0};
+    }
+    // the right neighbour of the strip's last node (lane 31 needs it for the residual at its own right node)
+    double xtra0 = (lane == 31 && xr + 1 <= n - 1) ? __ldg(u + (long long)r_first * pitch + xr + 1) : 0.0;
+    for (int r = r_first; r <= r_last; ++r) {
+        up = pre_u[0];
+        const Pair fv = pre_f[0];
+#pragma unroll
+        for (int k = 0; k + 1 < W2_PF; ++k) { pre_u[k] = pre_u[k + 1]; pre_f[k] = pre_f[k + 1]; }
+        {
+            const int ru = r + 1 + W2_PF, rf = r + W2_PF;
+            pre_u[W2_PF - 1] = ru <= min(r_last + 1, n - 1) ? load_pair(u + (long long)ru * pitch, xl, n) : Pair{0.0, 0.0};
+            pre_f[W2_PF - 1] = rf <= r_last ? load_pair(f + (long long)rf * pitch, xl, n) : Pair{0.0, 0.0};
+        }
+        const double xtra_next = (lane == 31 && xr + 1 <= n - 1 && r + 1 <= r_last) ? __ldg(u + (long long)(r + 1) * pitch + xr + 1) : 0.0;
+        const double left = __shfl_up_sync(0xffffffffu, u0.r, 1);
+        double right = __shfl_down_sync(0xffffffffu, u0.l, 1);
+        if (lane == 31) right = xtra0;
+        // residual of row r (A u in ascending table order: y-1, x-1, centre, x+1, y+1)
+        Pair res = {0.0, 0.0};
+        if (in_l) {
+            double sum = 0.0;
+            sum = sum + c.ym * um.l; sum = sum + c.xm * left; sum = sum + c.c * u0.l; sum = sum + c.xp * u0.r; sum = sum + c.yp * up.l;
+            res.l = fv.l - sum;
+        }
+        if (in_r) {
+            double sum = 0.0;
+            sum = sum + c.ym * um.r; sum = sum + c.xm * u0.l; sum = sum + c.c * u0.r; sum = sum + c.xp * right; sum = sum + c.yp * up.r;
+            res.r = fv.r - sum;
+        }
+        if (((r - r_first) & 1) == 0 && r > r_first) {
+            // r = 2Y+1: rows 2Y-1 (rm), 2Y (r0), 2Y+1 (res) are complete
+            const int Y = (r - 1) / 2;
+            const double a_m = __shfl_up_sync(0xffffffffu, rm.r, 1), a_0 = __shfl_up_sync(0xffffffffu, r0.r, 1),
+                         a_p = __shfl_up_sync(0xffffffffu, res.r, 1);     // residual at 2X-1
+            double acc = 0.0;
+            acc = acc + R.w[0] * a_m; acc = acc + R.w[1] * rm.l; acc = acc + R.w[2] * rm.r;
+            acc = acc + R.w[3] * a_0; acc = acc + R.w[4] * r0.l; acc = acc + R.w[5] * r0.r;
+            acc = acc + R.w[6] * a_p; acc = acc + R.w[7] * res.l; acc = acc + R.w[8] * res.r;
+            if (deliver) dst[(long long)Y * gc.pitch + X] = acc;
+        }
+        rm = r0; r0 = res;
+        um = u0; u0 = up;
+        xtra0 = xtra_next;
+    }
+}
+
+static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, const OpSten &st, const TransferW &R, const double *u,
+                                  const double *f, double *dst, cudaStream_t s)
+{
+    Star5 c;
+    if (gf.dim != 2 || gf.n < min_n() || R.nnz != 9 || !match_star5(st.s[0][0], &c)) return false;
+    Dense9 W;
+    for (int i = 0; i < 9; ++i) W.w[i] = 0.0;
+    for (int q = 0; q < R.nnz; ++q) {
+        if (R.oz[q] != 0) return false;
+        W.w[(R.oy[q] + 1) * 3 + (R.ox[q] + 1)] = R.w[q];
+    }
+    const int nci = gc.n - 2;
+    int strips = 1;
+    while ((strips - 1) * 31 + 31 < nci) ++strips;       // strip k delivers coarse nodes 31 k + 1 .. 31 k + 31
+    const int bx = (strips + W2_WARPS - 1) / W2_WARPS;
+    const long long want_warps = (long long)sm_count * 32;
+    int chunks = (int)std::min<long long>(std::max<long long>(1, want_warps / strips), std::max(1, nci / 4));
+    int rows = (nci + chunks - 1) / chunks;
+    chunks = (nci + rows - 1) / rows;
+    k2_residual_restrict_warp<<<dim3(bx, chunks), W2_WARPS * 32, 0, s>>>(gf, gc, c, W, u, f, dst, rows);
+    return cudaGetLastError() == cudaSuccess;
+}
+
 }  // namespace w2
 }  // namespace evo

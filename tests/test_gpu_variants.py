@@ -226,3 +226,26 @@ def test_streamed_fas_sweeps(cuda_backend, oracle_mod, option, star2d):
         gc.apply(1)
         oc.apply(1)
         _equal(gc, oc, prob, [7, 8, 9], (ol.BUF_SOL,))
+
+
+@pytest.mark.parametrize("star2d", [65, 1])
+@pytest.mark.parametrize("level", [7, 8, 9, 10])
+def test_streamed_2d_transfers_bit_exact(cuda_backend, oracle_mod, option, star2d, level):
+    """Fused residual + restriction and prolongation + correction of the 2-D streaming path against the oracle."""
+    option("EVO_STAR2D", star2d)
+    prob = problems.Poisson2D(level - 2, level)
+    z = (0, 0)
+    ops = [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_JACOBI, omega=0.9, unknowns=((0, z),)),
+           ol.Op(ol.OP_RESIDUAL_RESTRICT, level, dst=ol.BUF_RHS, src=ol.BUF_RES),
+           ol.Op(ol.OP_ZERO, level - 1, dst=ol.BUF_SOL),
+           ol.Op(ol.OP_SMOOTH, level - 1, mode=ol.MODE_REDBLACK, omega=1.1, unknowns=((0, z),)),
+           ol.Op(ol.OP_PROLONG_ADD, level, src=ol.BUF_SOL, omega=0.95),
+           ol.Op(ol.OP_RESIDUAL, level, dst=ol.BUF_RES)]
+    prog = cycles.build_program(prob, ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [level], (ol.BUF_SOL, ol.BUF_RES))
+        _equal(gc, oc, prob, [level - 1], (ol.BUF_SOL, ol.BUF_RHS))
