@@ -196,9 +196,9 @@ static bool launch_sweep(int sm_count, const Geom &g, const U &upd, const double
     int strips = 1;
     while (strips * WINT + 63 - NSTAGE - WINT < inner) ++strips;     // last delivered node >= n - 2
     const int bx = (strips + W2_WARPS - 1) / W2_WARPS;
-    // row chunks: ~32 warps per SM when the grid allows it, at least max(4, 2 NSTAGE) rows each (a chunk recomputes
+    // row chunks: ~1.5 waves of 64 warps per SM when the grid allows it, at least max(4, 2 NSTAGE) rows each (a chunk recomputes
     // NSTAGE halo rows at both ends)
-    const long long want_warps = (long long)sm_count * 32;
+    const long long want_warps = (long long)sm_count * 96;
     const int min_rows = std::max(4, 2 * NSTAGE);
     int chunks = (int)std::min<long long>(std::max<long long>(1, want_warps / strips), std::max(1, inner / min_rows));
     int rows = (inner + chunks - 1) / chunks;
@@ -393,7 +393,7 @@ static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, 
     int strips = 1;
     while ((strips - 1) * 31 + 31 < nci) ++strips;       // strip k delivers coarse nodes 31 k + 1 .. 31 k + 31
     const int bx = (strips + W2_WARPS - 1) / W2_WARPS;
-    const long long want_warps = (long long)sm_count * 32;
+    const long long want_warps = (long long)sm_count * 96;
     int chunks = (int)std::min<long long>(std::max<long long>(1, want_warps / strips), std::max(1, nci / 4));
     int rows = (nci + chunks - 1) / chunks;
     chunks = (nci + rows - 1) / rows;
