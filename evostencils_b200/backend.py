@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "evo_cycle_build", "evo_cycle_destroy", "evo_cycle_reset", "evo_cycle_apply",
     "evo_cycle_get_field", "evo_cycle_set_field", "evo_cycle_residual_norm", "evo_cycle_profile_op",
     "evo_cycle_solve", "evo_helmholtz_solve", "evo_batch_solve",
-    "evo_problem_set_slab", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
+    "evo_problem_set_slab", "evo_problem_set_slab_ex", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
     "evo_cycle_residual_plane_sums", "evo_cycle_vecsum", "evo_cycle_vecsum_async", "evo_cycle_read_sum",
     "evo_cycle_swap_slots", "evo_cycle_exec_part", "evo_set_option", "evo_get_option",
 )
@@ -87,6 +87,7 @@ def load_library(path: Optional[str] = None):
     lib.evo_batch_solve.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(ol.CEvoSolveParams),
                                     C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.evo_problem_set_slab.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.evo_problem_set_slab_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.evo_problem_slab_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
     lib.evo_cycle_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.evo_cycle_exec_ops.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.c_int, C.c_int]
@@ -289,7 +290,7 @@ class DeviceProblem:
     backend_name = "cuda"
 
     def __init__(self, problem: Problem, device: int = 0, lib=None, slab: Optional[Tuple[int, int, int]] = None):
-        """slab = (rank, world, coarsest distributed level): hold only this rank's z-slab of every level
+        """slab = (rank, world, coarsest distributed level[, ghost planes per side = 2]): hold only this rank's z-slab of every level
         >= that level (domain decomposition of one grid; see evostencils_b200.domain)."""
         self._lib = lib or load_library()
         n = self._lib.evo_device_count()
@@ -303,7 +304,10 @@ class DeviceProblem:
         _check(self._lib, self._lib.evo_problem_create(C.byref(desc), C.byref(self._h)), "evo_problem_create")
         self.slab = slab
         if slab is not None:
-            _check(self._lib, self._lib.evo_problem_set_slab(self._h, *[int(v) for v in slab]), "evo_problem_set_slab")
+            vals = [int(v) for v in slab]
+            if len(vals) == 3:
+                vals.append(2)
+            _check(self._lib, self._lib.evo_problem_set_slab_ex(self._h, *vals), "evo_problem_set_slab_ex")
         for fi in range(problem.n_fields):
             for buf, arr in ((ol.BUF_SOL, problem.initial_solution(fi)), (ol.BUF_RHS, problem.rhs(fi))):
                 flat = _as_doubles(arr, problem.complex_valued)

@@ -175,22 +175,23 @@ static void free_problem(evo_problem *p)
     delete p;
 }
 
-extern "C" int evo_problem_set_slab(evo_problem *p, int rank, int world, int lc)
+extern "C" int evo_problem_set_slab_ex(evo_problem *p, int rank, int world, int lc, int ghost)
 {
     if (!p) return fail(EVO_ERR_INVALID, "null argument");
     const evo_problem_desc &d = p->desc;
     if (d.dim != 3 || d.n_fields != 1 || d.scalar_words != 1 || d.kind != EVO_PROBLEM_LINEAR)
         return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: 3-D real scalar linear problems only");
     if (world < 1 || rank < 0 || rank >= world) return fail(EVO_ERR_INVALID, "invalid rank/world");
+    if (ghost < 2 || ghost > 16 || (ghost & 1)) return fail(EVO_ERR_INVALID, "ghost planes per side: an even number in [2, 16]");
     if (lc < 5 || lc < d.min_level || lc > d.max_level) return fail(EVO_ERR_INVALID, "coarsest distributed level must be >= 5 and within the hierarchy");
     const int inner = (1 << lc) - 1;
-    if (inner < 2 * world) return fail(EVO_ERR_INVALID, "too many ranks for the coarsest distributed level");
+    if (inner < ghost * world) return fail(EVO_ERR_INVALID, "too many ranks for the coarsest distributed level");
     if (p->live_cycles > 0) return fail(EVO_ERR_INVALID, "set the slab before building cycles");
     CU(cudaSetDevice(d.device));
     p->slab_world = world; p->slab_rank = rank; p->slab_lc = lc;
     const int base = inner / world, rem = inner % world;
     int a = 1 + rank * base + std::min(rank, rem), b = a + base + (rank < rem ? 1 : 0) - 1;
-    const int G = 2;
+    const int G = ghost;
     for (int l = lc; l <= d.max_level; ++l) {
         if (l > lc) { a = 2 * a - 1; b = 2 * b + (rank == world - 1 ? 1 : 0); }
         Geom g = make_geom(l, 3);
@@ -215,6 +216,8 @@ extern "C" int evo_problem_set_slab(evo_problem *p, int rank, int world, int lc)
     }
     return EVO_OK;
 }
+
+extern "C" int evo_problem_set_slab(evo_problem *p, int rank, int world, int lc) { return evo_problem_set_slab_ex(p, rank, world, lc, 2); }
 
 extern "C" int evo_problem_slab_info(evo_problem *p, int level, long long info[8])
 {

@@ -14,8 +14,12 @@ ghost planes between statements.  The numerics are BIT-IDENTICAL to the undecomp
 Layout (mirrors `evo_problem_set_slab`, csrc/evo_runtime.cu): level `lc` splits its inner planes evenly; a
 rank owning planes [a, b] of level l owns [2a-1, 2b] of level l+1 (the last rank also 2b+1).  Coarser levels
 are replicated: the restriction from level lc is computed plane-wise by the owners and all-gathered, and every
-rank runs the (tiny) coarse part of the cycle redundantly.  Each slab carries GHOST = 2 planes per side (one
-red-black sweep = two dependent half sweeps).
+rank runs the (tiny) coarse part of the cycle redundantly.  Each slab carries `ghost` planes per side (layout
+parameter, default GHOST = 6).  One red-black sweep consumes two of them (two dependent half sweeps): with wide ghost
+zones consecutive sweeps and the residual after them recompute the halo redundantly (a statement runs on the owned
+planes extended by e ghost planes, bit-identical to what the neighbour computes) instead of exchanging after every
+statement -- one exchange of 6 planes per level and cycle replaces four exchanges of 2 (communication avoiding:
+the exchanges are latency, not bandwidth, bound).
 
 `SlabLayout` and the exchange schedule are pure Python (tested on CPU with gloo); the statements themselves
 run only through the CUDA library (no CPU fallback).
@@ -23,26 +27,30 @@ run only through the CUDA library (no CPU fallback).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import oplist as ol
 
-GHOST = 2
+GHOST = int(os.environ.get("EVO_DOMAIN_GHOST", "6"))     # default ghost planes per side of a slab (even, 2..16)
 
 
 class SlabLayout:
     """Ownership of global z planes per level and rank."""
 
-    def __init__(self, max_level: int, coarsest_distributed_level: int, world: int):
+    def __init__(self, max_level: int, coarsest_distributed_level: int, world: int, ghost: Optional[int] = None):
         lc = coarsest_distributed_level
+        ghost = GHOST if ghost is None else int(ghost)
+        if ghost < 2 or ghost > 16 or ghost % 2:
+            raise ValueError("ghost planes per side: an even number in [2, 16]")
         if lc < 5 or lc > max_level:
             raise ValueError("coarsest distributed level must be in [5, max_level]")
         inner = (1 << lc) - 1
-        if inner < 2 * world:
+        if inner // world < ghost:
             raise ValueError("too many ranks for the coarsest distributed level")
-        self.max_level, self.lc, self.world = max_level, lc, world
+        self.max_level, self.lc, self.world, self.ghost = max_level, lc, world, ghost
         self.owned: Dict[int, List[Tuple[int, int]]] = {}
         base, rem = divmod(inner, world)
         rows = []
@@ -63,7 +71,8 @@ class SlabLayout:
     def local(self, level: int, rank: int) -> dict:
         """Local array geometry of a distributed level (same numbers as evo_problem_slab_info)."""
         a, b = self.owned[level][rank]
-        return {"zoff": a - GHOST, "nz": b - a + 1 + 2 * GHOST, "zlo": GHOST, "zhi": GHOST + b - a, "g0": a, "g1": b}
+        G = self.ghost
+        return {"zoff": a - G, "nz": b - a + 1 + 2 * G, "zlo": G, "zhi": G + b - a, "g0": a, "g1": b}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -89,6 +98,7 @@ def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int
     """Plan one pass over the op list; `valid` is updated in place (carry it from cycle to cycle)."""
     steps: List[Step] = []
     dist_ = layout.distributed
+    G = layout.ghost
 
     def v(l, b):
         return INF if not dist_(l) else valid.get((l, b), 0)
@@ -96,7 +106,7 @@ def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int
     def need(l, b, depth):
         if v(l, b) < depth:
             steps.append(Step("halo", l, b))
-            valid[(l, b)] = GHOST
+            valid[(l, b)] = G
 
     for idx, op in enumerate(program.ops):
         c, l = op.code, op.level
@@ -118,18 +128,20 @@ def schedule(program: ol.Program, layout: SlabLayout, valid: Dict[Tuple[int, int
             steps.append(Step("op", idx, -1))
             continue
         if c == ol.OP_SMOOTH:
-            if op.mode == ol.MODE_REDBLACK:
-                need(l, ol.BUF_SOL, 2)
+            # one sweep consumes `depth` valid ghost planes of SOL (RB-GS: two dependent half sweeps) and depth - 1 of
+            # RHS; whatever validity is left lets the sweep run on e extra ghost planes, which stay valid afterwards
+            depth = 2 if op.mode == ol.MODE_REDBLACK else 1
+            need(l, ol.BUF_SOL, depth)
+            if depth == 2:
                 need(l, ol.BUF_RHS, 1)
-            else:
-                need(l, ol.BUF_SOL, 1)
-            if overlap:
+            e = max(0, min(v(l, ol.BUF_SOL) - depth, v(l, ol.BUF_RHS) - (depth - 1), G - depth))
+            if overlap and e == 0:
                 # boundary planes, then their exchange travels while the interior planes are swept
                 steps.append(Step("smooth_overlapped", idx))
-                valid[(l, ol.BUF_SOL)] = GHOST
+                valid[(l, ol.BUF_SOL)] = G
             else:
-                steps.append(Step("op", idx, 0))
-                valid[(l, ol.BUF_SOL)] = 0
+                steps.append(Step("op", idx, e))
+                valid[(l, ol.BUF_SOL)] = e
         elif c == ol.OP_RESIDUAL:
             need(l, ol.BUF_SOL, 1)
             e = max(0, min(v(l, ol.BUF_SOL) - 1, v(l, ol.BUF_RHS), 1))
@@ -183,7 +195,7 @@ class SlabRank:
         self.rank, self.layout, self.device, self.stream = rank, layout, device, stream
         self.problem = problem
         with torch.cuda.device(device):
-            self.dp = DeviceProblem(problem, device, slab=(rank, layout.world, layout.lc))
+            self.dp = DeviceProblem(problem, device, slab=(rank, layout.world, layout.lc, layout.ghost))
             self.cycle = self.dp.build(program)
             self.cycle.set_stream(stream.cuda_stream)   # statements and exchanges share one stream per device
             self.cycle.reset()
@@ -218,12 +230,13 @@ class LocalComm:
 
     def halo(self, level: int, buf: int):
         views = [r.view(level, buf) for r in self.ranks]
+        G = self.ranks[0].layout.ghost
         for r in range(self.world - 1):
             lo, hi = self.ranks[r], self.ranks[r + 1]
             il, ih = lo.info[level], hi.info[level]
             # top owned planes of r -> bottom ghosts of r+1; bottom owned planes of r+1 -> top ghosts of r
-            views[r + 1][ih["zlo"] - GHOST:ih["zlo"]].copy_(views[r][il["zhi"] - GHOST + 1:il["zhi"] + 1])
-            views[r][il["zhi"] + 1:il["zhi"] + 1 + GHOST].copy_(views[r + 1][ih["zlo"]:ih["zlo"] + GHOST])
+            views[r + 1][ih["zlo"] - G:ih["zlo"]].copy_(views[r][il["zhi"] - G + 1:il["zhi"] + 1])
+            views[r][il["zhi"] + 1:il["zhi"] + 1 + G].copy_(views[r + 1][ih["zlo"]:ih["zlo"] + G])
 
     def halo_start(self, level: int, buf: int):
         self.halo(level, buf)      # copies on the one stream: nothing to overlap in the emulation
@@ -260,14 +273,15 @@ class DistComm:
     def halo(self, level: int, buf: int):
         dist = self.dist
         me = self.ranks[0]
+        G = me.layout.ghost
         v, i = me.view(level, buf), me.info[level]
         ops = []
         if self.rank + 1 < self.world:
-            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - GHOST + 1:i["zhi"] + 1], self.rank + 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + GHOST], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - G + 1:i["zhi"] + 1], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + G], self.rank + 1, self.group))
         if self.rank > 0:
-            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + GHOST], self.rank - 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - GHOST:i["zlo"]], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + G], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - G:i["zlo"]], self.rank - 1, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -277,14 +291,15 @@ class DistComm:
         the requests; the current stream's work enqueued so far is what the sends wait for."""
         dist = self.dist
         me = self.ranks[0]
+        G = me.layout.ghost
         v, i = me.view(level, buf), me.info[level]
         ops = []
         if self.rank + 1 < self.world:
-            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - GHOST + 1:i["zhi"] + 1], self.rank + 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + GHOST], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.isend, v[i["zhi"] - G + 1:i["zhi"] + 1], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zhi"] + 1:i["zhi"] + 1 + G], self.rank + 1, self.group))
         if self.rank > 0:
-            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + GHOST], self.rank - 1, self.group))
-            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - GHOST:i["zlo"]], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.isend, v[i["zlo"]:i["zlo"] + G], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, v[i["zlo"] - G:i["zlo"]], self.rank - 1, self.group))
         return dist.batch_isend_irecv(ops) if ops else []
 
     def halo_finish(self, reqs):
@@ -292,26 +307,50 @@ class DistComm:
             req.wait()
 
     def gather_planes(self, level: int, buf: int, ranges: Sequence[Tuple[int, int]]):
+        """Replicated level: rank r computed planes ranges[r]; ONE all-gather (padded to the largest share) + one
+        gather kernel make every copy complete (was: one broadcast per rank)."""
+        torch = self.ranks[0].torch
         v = self.ranks[0].view(level, buf)
-        works = []
-        for src, (a, b) in enumerate(ranges):
-            if b >= a:
-                works.append(self.dist.broadcast(v[a:b + 1], src=src, group=self.group, async_op=True))
-        for w in works:
-            w.wait()
+        counts = [max(0, b - a + 1) for (a, b) in ranges]
+        m = max(counts)
+        if m == 0:
+            return
+        key = ("planes", level, buf)
+        cache = self.__dict__.setdefault("_bufs", {})
+        if key not in cache:
+            send = torch.zeros((m,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            recv = torch.empty((self.world * m,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            lo = min(a for (a, b) in ranges if b >= a)
+            hi = max(b for (a, b) in ranges if b >= a)
+            src = {}
+            for r, (a, b) in enumerate(ranges):
+                for z in range(a, b + 1):
+                    src[z] = r * m + (z - a)
+            idx = torch.tensor([src[z] for z in range(lo, hi + 1)], dtype=torch.int64, device=v.device)
+            cache[key] = (send, recv, idx, lo, hi)
+        send, recv, idx, lo, hi = cache[key]
+        a, b = ranges[self.rank]
+        if b >= a:
+            send[:b - a + 1].copy_(v[a:b + 1])
+        self.dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        torch.index_select(recv, 0, idx, out=v[lo:hi + 1])
 
     def gather_sums(self, parts: Sequence, sizes: Sequence[int]):
+        """Concatenation of every rank's plane sums in rank order: one padded all-gather + one gather kernel."""
         torch = self.ranks[0].torch
         mine = parts[0]
-        full = torch.empty(sum(sizes), dtype=mine.dtype, device=mine.device)
-        offs = np.concatenate([[0], np.cumsum(sizes)])
-        works = []
-        full[offs[self.rank]:offs[self.rank + 1]].copy_(mine)
-        for src in range(self.world):
-            works.append(self.dist.broadcast(full[offs[src]:offs[src + 1]], src=src, group=self.group, async_op=True))
-        for w in works:
-            w.wait()
-        return full
+        m = max(sizes)
+        key = ("sums", tuple(sizes))
+        cache = self.__dict__.setdefault("_bufs", {})
+        if key not in cache:
+            send = torch.zeros(m, dtype=mine.dtype, device=mine.device)
+            recv = torch.empty(self.world * m, dtype=mine.dtype, device=mine.device)
+            idx = torch.tensor([r * m + k for r, sz in enumerate(sizes) for k in range(sz)], dtype=torch.int64, device=mine.device)
+            cache[key] = (send, recv, idx)
+        send, recv, idx = cache[key]
+        send[:sizes[self.rank]].copy_(mine)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        return recv.index_select(0, idx)
 
 
 class DomainOutcome:
@@ -353,9 +392,10 @@ class DomainSolver:
 
     # -- factory helpers -------------------------------------------------------------------------------
     @classmethod
-    def emulate(cls, problem, program, world: int, lc: Optional[int] = None, devices: Optional[Sequence[int]] = None):
+    def emulate(cls, problem, program, world: int, lc: Optional[int] = None, devices: Optional[Sequence[int]] = None,
+                ghost: Optional[int] = None):
         """All `world` slabs driven by this process (device list: one entry per slab, default all on cuda:0)."""
-        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world), world)
+        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world, ghost), world, ghost)
         import torch
         devices = list(devices) if devices is not None else [0] * world
         streams = {dv: torch.cuda.Stream(dv) for dv in set(devices)}
@@ -363,8 +403,9 @@ class DomainSolver:
         return cls(problem, program, layout, ranks, LocalComm(ranks))
 
     @classmethod
-    def distributed(cls, problem, program, rank: int, world: int, device: int, lc: Optional[int] = None, group=None):
-        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world), world)
+    def distributed(cls, problem, program, rank: int, world: int, device: int, lc: Optional[int] = None, group=None,
+                    ghost: Optional[int] = None):
+        layout = SlabLayout(problem.max_level, lc or default_lc(problem, world, ghost), world, ghost)
         import torch
         me = SlabRank(problem, program, rank, layout, device, torch.cuda.Stream(device))
         return cls(problem, program, layout, [me], DistComm(me, rank, world, group))
@@ -401,21 +442,22 @@ class DomainSolver:
             op = self.program.ops[st.a]
             lvl = op.level
             target = ol.BUF_NEXT if self._out_of_place(op) else ol.BUF_SOL
+            G = lay.ghost
             for r in self.ranks:
                 i = r.info[lvl]
-                if i["zhi"] - i["zlo"] + 1 < 2 * GHOST + 1:
+                if i["zhi"] - i["zlo"] + 1 < 2 * G + 1:
                     r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"], i["zhi"], True)
                 else:
-                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"], i["zlo"] + GHOST - 1, True)
-                    r.cycle.exec_part(r._c_ops[st.a][1], i["zhi"] - GHOST + 1, i["zhi"], True)
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"], i["zlo"] + G - 1, True)
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zhi"] - G + 1, i["zhi"], True)
             reqs = self.comm.halo_start(lvl, target)
             self.exchanges += 1
             for r in self.ranks:
                 i = r.info[lvl]
-                if i["zhi"] - i["zlo"] + 1 < 2 * GHOST + 1:
+                if i["zhi"] - i["zlo"] + 1 < 2 * G + 1:
                     r.cycle.exec_part(r._c_ops[st.a][1], 1, 0, False)          # only the exchange of the slots
                 else:
-                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"] + GHOST, i["zhi"] - GHOST, False)
+                    r.cycle.exec_part(r._c_ops[st.a][1], i["zlo"] + G, i["zhi"] - G, False)
             self.comm.halo_finish(reqs)
         else:
             op = self.program.ops[st.a]
@@ -461,7 +503,8 @@ class DomainSolver:
 
     def _reset_validity(self):
         top = self.problem.max_level
-        self.valid = {(top, ol.BUF_SOL): GHOST, (top, ol.BUF_RHS): GHOST}   # the upload filled every local plane
+        G = self.layout.ghost
+        self.valid = {(top, ol.BUF_SOL): G, (top, ol.BUF_RHS): G}   # the upload filled every local plane
 
     def residual_norm(self) -> float:
         torch = self.torch
@@ -470,7 +513,7 @@ class DomainSolver:
             if self.valid.get((top_, ol.BUF_SOL), 0) < 1:
                 self.comm.halo(top_, ol.BUF_SOL)
                 self.exchanges += 1
-                self.valid[(top_, ol.BUF_SOL)] = GHOST
+                self.valid[(top_, ol.BUF_SOL)] = self.layout.ghost
             self.valid[(top_, ol.BUF_RES)] = 0
             parts = []
             for r in self.ranks:
@@ -492,7 +535,7 @@ class DomainSolver:
         if self.valid.get((top, ol.BUF_SOL), 0) < 1:
             self.comm.halo(top, ol.BUF_SOL)
             self.exchanges += 1
-            self.valid[(top, ol.BUF_SOL)] = GHOST
+            self.valid[(top, ol.BUF_SOL)] = self.layout.ghost
         self.valid[(top, ol.BUF_RES)] = 0
         parts = []
         for r in self.ranks:
@@ -505,7 +548,8 @@ class DomainSolver:
 
     def _canonical_validity(self):
         top = self.problem.max_level
-        self.valid = {(top, ol.BUF_SOL): GHOST, (top, ol.BUF_RHS): GHOST}
+        G = self.layout.ghost
+        self.valid = {(top, ol.BUF_SOL): G, (top, ol.BUF_RHS): G}
 
     def _capture(self):
         """Two graphs: an iteration starting from the canonical buffer assignment (A) and one starting from the
@@ -618,11 +662,12 @@ class DomainSolver:
         return out
 
 
-def default_lc(problem, world: int) -> int:
+def default_lc(problem, world: int, ghost: Optional[int] = None) -> int:
     """Coarsest distributed level: only the two finest levels are split (measured at 513^3 on 2 GPUs: lc = 8 31.3 ms,
     7 31.9 ms, 5 36.2 ms per evaluation -- exchanges on small levels cost more than computing them redundantly),
     at least 8 planes per rank, never below level 5 (33^3)."""
+    per_rank = max(8, GHOST if ghost is None else ghost)
     lc = max(5, problem.max_level - 1)
-    while lc < problem.max_level and ((1 << lc) - 1) < 8 * world:
+    while lc < problem.max_level and ((1 << lc) - 1) < per_rank * world:
         lc += 1
     return min(lc, problem.max_level)

@@ -193,6 +193,9 @@ int evo_problem_set_field(evo_problem *p, int level, int buf, int field, const d
  *    coarser levels are replicated on every rank.  Each slab carries 2 ghost planes per side.  Must be called
  *    before evo_problem_set_field / evo_cycle_build.  3-D real scalar problems only.                       */
 int evo_problem_set_slab(evo_problem *p, int rank, int world, int coarsest_distributed_level);
+/* ... with `ghost` planes per side instead of 2 (even, <= 16): wide ghost zones let consecutive sweeps recompute the
+ * halo redundantly instead of exchanging it after every statement (communication-avoiding schedule, domain.py)  */
+int evo_problem_set_slab_ex(evo_problem *p, int rank, int world, int coarsest_distributed_level, int ghost);
 /* info[0..7] = zoff (global index of local plane 0), local plane count, first owned local plane, last owned local
  * plane, first owned global plane, last owned global plane, row pitch (entries), plane stride (entries)      */
 int evo_problem_slab_info(evo_problem *p, int level, long long info[8]);

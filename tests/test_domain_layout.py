@@ -12,15 +12,17 @@ import torch.multiprocessing as mp
 from evostencils_b200 import cycles, domain, oplist as ol, problems
 
 
-@pytest.mark.parametrize("max_level,lc,world", [(9, 5, 2), (9, 5, 4), (9, 6, 8), (7, 5, 3), (6, 6, 5), (9, 5, 15)])
-def test_layout_partitions_every_level(max_level, lc, world):
-    lay = domain.SlabLayout(max_level, lc, world)
+@pytest.mark.parametrize("max_level,lc,world,ghost", [(9, 5, 2, 2), (9, 5, 4, 6), (9, 6, 8, 6), (7, 5, 3, 6), (6, 6, 5, 6),
+                                                      (9, 5, 15, 2), (9, 8, 8, 6), (9, 7, 8, 4)])
+def test_layout_partitions_every_level(max_level, lc, world, ghost):
+    lay = domain.SlabLayout(max_level, lc, world, ghost)
+    assert lay.ghost == ghost
     for l in range(lc, max_level + 1):
         n = (1 << l) + 1
         covered = []
         for r in range(world):
             a, b = lay.owned[l][r]
-            assert b - a + 1 >= domain.GHOST            # a slab can fill its neighbour's ghost planes
+            assert b - a + 1 >= lay.ghost               # a slab can fill its neighbour's ghost planes
             covered += list(range(a, b + 1))
         assert covered == list(range(1, n - 1))         # inner planes, no gap, no overlap, ascending
         if l > lc:
@@ -49,23 +51,24 @@ def test_layout_rejects_bad_arguments():
         domain.SlabLayout(6, 7, 2)
 
 
-def test_exchange_schedule_of_a_v_cycle():
+@pytest.mark.parametrize("ghost", [2, 4, 6])
+def test_exchange_schedule_of_a_v_cycle(ghost):
     prob = problems.Poisson3D(2, 7)
     prog = cycles.v_cycle(prob, 2, 1, 1.25, True)
-    lay = domain.SlabLayout(7, 6, 2)
+    lay = domain.SlabLayout(7, 6, 2, ghost)
     domain.check_supported(prog, lay)
-    valid = {(7, ol.BUF_SOL): 2, (7, ol.BUF_RHS): 2}
+    valid = {(7, ol.BUF_SOL): ghost, (7, ol.BUF_RHS): ghost}
     steps = domain.schedule(prog, lay, valid)
     ops = [s for s in steps if s.kind == "op"]
     halos = [(s.a, s.b) for s in steps if s.kind == "halo"]
     assert len(ops) + sum(s.kind == "gather" for s in steps) == len(prog.ops)
     assert all(l >= 6 for l, _ in halos)
     # the statements' dependences are honoured: replay the plan and check the requirement of every statement
-    v = {(7, ol.BUF_SOL): 2, (7, ol.BUF_RHS): 2}
+    v = {(7, ol.BUF_SOL): ghost, (7, ol.BUF_RHS): ghost}
     get = lambda l, b: 99 if l < 6 else v.get((l, b), 0)
     for s in steps:
         if s.kind == "halo":
-            v[(s.a, s.b)] = 2
+            v[(s.a, s.b)] = ghost
             continue
         op = prog.ops[s.a]
         l = op.level
@@ -75,8 +78,11 @@ def test_exchange_schedule_of_a_v_cycle():
         if l < 6:
             continue
         if op.code == ol.OP_SMOOTH:
-            assert get(l, ol.BUF_SOL) >= 2 and get(l, ol.BUF_RHS) >= 1
-            v[(l, ol.BUF_SOL)] = 0
+            # a red-black sweep on the owned planes extended by e = s.b ghost planes reads e + 2 valid ghost planes of
+            # SOL and e + 1 of RHS, and leaves e valid ones behind
+            assert 0 <= s.b <= ghost - 2
+            assert get(l, ol.BUF_SOL) >= s.b + 2 and get(l, ol.BUF_RHS) >= s.b + 1
+            v[(l, ol.BUF_SOL)] = s.b
         elif op.code == ol.OP_RESIDUAL:
             assert get(l, ol.BUF_SOL) >= s.b + 1 and get(l, ol.BUF_RHS) >= s.b
             v[(l, op.dst)] = s.b
@@ -88,8 +94,8 @@ def test_exchange_schedule_of_a_v_cycle():
             v[(l, ol.BUF_SOL)] = s.b
         elif op.code == ol.OP_ZERO:
             v[(l, op.dst)] = 99
-    # fewer exchanges than "after every write" (6 per level and cycle)
-    assert len(halos) <= 9
+    # fewer exchanges than "after every write" (6 per level and cycle); wide ghost zones need fewer still
+    assert len(halos) <= (9 if ghost == 2 else 6)
     # the second cycle starts from the validity the first one left behind and is planned deterministically
     again = domain.schedule(prog, lay, dict(valid))
     assert [repr(s) for s in again] == [repr(s) for s in domain.schedule(prog, lay, dict(valid))]
@@ -100,7 +106,7 @@ class _FakeRank:
 
     def __init__(self, rank, layout, level):
         self.torch = torch
-        self.rank, self.device = rank, "cpu"
+        self.rank, self.device, self.layout = rank, "cpu", layout
         self.info = {level: layout.local(level, rank)}
         i = self.info[level]
         n = (1 << level) + 1
@@ -126,8 +132,8 @@ def _worker(rank, world, port, level, lc):
         comm = domain.DistComm(me, rank, world)
         comm.halo(level, ol.BUF_SOL)
         i = me.info[level]
-        lo = i["zlo"] - (domain.GHOST if rank > 0 else 0)
-        hi = i["zhi"] + (domain.GHOST if rank < world - 1 else 0)
+        lo = i["zlo"] - (lay.ghost if rank > 0 else 0)
+        hi = i["zhi"] + (lay.ghost if rank < world - 1 else 0)
         assert torch.equal(me.data[lo:hi + 1], me.expected[lo:hi + 1])
         # outer ghosts of the first / last rank have no neighbour: untouched
         if rank == 0:

@@ -20,15 +20,18 @@ def _reference(cuda_backend, prob, prog):
     return out, sol
 
 
+@pytest.mark.parametrize("ghost", [2, 6])
 @pytest.mark.parametrize("max_level,world,lc,red_black", [
     (6, 2, 5, True), (6, 3, 5, True), (6, 4, 6, True), (7, 2, 5, True), (7, 5, 6, True), (6, 2, 5, False), (7, 3, 7, True),
 ])
-def test_slab_solve_is_bit_identical(cuda_backend, max_level, world, lc, red_black):
+def test_slab_solve_is_bit_identical(cuda_backend, max_level, world, lc, red_black, ghost):
+    """ghost = 2: an exchange after (almost) every statement; ghost = 6: consecutive sweeps recompute the halo on the
+    extended planes and exchange once per level and cycle."""
     prob = problems.Poisson3D(2, max_level)
     s = prob.settings
     prog = cycles.v_cycle(prob, 2, 1, s.damping if red_black else 0.8, red_black)
     ref, ref_sol = _reference(cuda_backend, prob, prog)
-    dd = domain.DomainSolver.emulate(prob, prog, world, lc)
+    dd = domain.DomainSolver.emulate(prob, prog, world, lc, ghost=ghost)
     try:
         out = dd.solve(s.tol, s.max_iters)
         assert out.iterations == ref.iterations
@@ -69,14 +72,15 @@ def test_fused_residual_restrict_in_slabs(cuda_backend, world, lc):
         dd.close()
 
 
+@pytest.mark.parametrize("ghost", [2, 4, 6])
 @pytest.mark.parametrize("world,lc,red_black", [(2, 6, True), (3, 5, True), (2, 6, False)])
-def test_boundary_first_execution_is_identical(cuda_backend, world, lc, red_black):
+def test_boundary_first_execution_is_identical(cuda_backend, world, lc, red_black, ghost):
     """overlap mode: every smoothing statement runs on the boundary planes first, then (while the halo travels) on the
     interior; the partial launches and the deferred exchange of SOL and its [next] slot must not change a bit."""
     prob = problems.Poisson3D(2, 7)
     prog = cycles.v_cycle(prob, 2, 1, 1.25 if red_black else 0.8, red_black)
     ref, ref_sol = _reference(cuda_backend, prob, prog)
-    dd = domain.DomainSolver.emulate(prob, prog, world, lc)
+    dd = domain.DomainSolver.emulate(prob, prog, world, lc, ghost=ghost)
     dd.overlap = True
     try:
         out = dd.solve(prob.settings.tol, prob.settings.max_iters)
