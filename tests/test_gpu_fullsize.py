@@ -83,3 +83,46 @@ def test_poisson2d_4097_first_iterations_bit_exact(cuda_backend, oracle_mod):
     b = oc.solve(prob.settings.tol, 100, 1)
     assert a.iterations == b.iterations and a.iterations < 12
     assert np.array_equal(a.residuals, b.residuals)
+
+
+def test_poisson3d_513_w_cycle_first_iterations_bit_exact(cuda_backend, oracle_mod, poisson513):
+    """BASELINE configs[1] names V- and W-cycles: W(2,1) red-black GS at 513^3, first two iterations against the oracle
+    (the coarse levels are revisited 2^k times per iteration: the latency-bound part of the path)."""
+    prob = poisson513
+    s = prob.settings
+    prog = lowering.optimise(cycles.w_cycle(prob, s.num_pre, s.num_post, s.damping, s.red_black))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    a = gc.solve(s.tol, 2, 1)
+    b = oc.solve(s.tol, 2, 1)
+    assert a.iterations == b.iterations == 2
+    assert np.array_equal(a.residuals, b.residuals)
+    # ... and the complete W-cycle solve converges like the V-cycle or better, monotonically
+    full = gc.solve(s.tol, s.max_iters, 1)
+    assert full.status == 0 and full.iterations <= 10 and np.all(np.diff(full.residuals) < 0)
+    gc.close()
+
+
+@pytest.mark.parametrize("kind", ["poisson", "elasticity"])
+def test_full_size_population_individuals_bit_exact(cuda_backend, oracle_mod, kind):
+    """Eight random individuals of the generation bench.py evaluates (tree.random_individual, seed 0) at the FULL sizes
+    of BASELINE configs[4] -- Poisson 2D 513^2 (levels 5..9), LinearElasticity 257^2 (levels 4..8): complete residual
+    histories against the oracle, through the drop-in's lowering (block smoothers, decoupled / collective sweeps,
+    order-dependent coloured sweeps)."""
+    import random
+    from evostencils_b200 import tree
+    from evostencils_b200.program_generator import B200ProgramGenerator
+    prob = problems.Poisson2D(5, 9) if kind == "poisson" else problems.LinearElasticity2D(4, 8)
+    rng = random.Random(0)
+    pg = B200ProgramGenerator(problem=prob)
+    storages = pg.generate_storage(prob.min_level, prob.max_level, pg.finest_grid)
+    ref = oracle_mod.OracleProblem(prob)
+    st = prob.settings
+    for _ in range(8):
+        expr = tree.build_tree(prob, tree.random_individual(prob, rng, maximum_local_system_size=4))
+        t, cf, its = pg.generate_and_evaluate(expr, storages, prob.min_level, prob.max_level, "", evaluation_samples=1)
+        prog = pg._finalise(pg.lower(expr, prob.min_level))
+        o = ref.build(prog).solve(st.tol, st.max_iters, 1)
+        assert pg.last_outcome.iterations == o.iterations
+        assert np.array_equal(pg.last_outcome.residuals, o.residuals, equal_nan=True)
+    pg.close()

@@ -32,7 +32,9 @@ def test_helmholtz_cycle_statements_bit_exact(cuda_backend, oracle_mod):
                 assert np.array_equal(gc.get_field(l, b), oc.get_field(l, b)), (l, b)
 
 
-@pytest.mark.parametrize("k,levels", [(40.0, (3, 6)), (80.0, (3, 7))])
+# (80, 3..7) is the shipped configuration; (160, 4..8) and (320, 5..9) are the generalisation steps of BASELINE configs[3]
+# (one level finer, k doubled: optimization/program.py:110-146 -> exastencils.py:196-215)
+@pytest.mark.parametrize("k,levels", [(40.0, (3, 6)), (80.0, (3, 7)), (160.0, (4, 8)), (320.0, (5, 9))])
 def test_helmholtz_outer_solver_parity(cuda_backend, oracle_mod, k, levels):
     prob = problems.Helmholtz2D(levels[0], levels[1], k=k)
     prog = cycles.default_solver_cycle(prob)

@@ -125,7 +125,7 @@ def test_block_jacobi_bit_exact(cuda_backend, oracle_mod, shape):
     for _ in range(2):
         gc.apply(1)
         oc.apply(1)
-        _fields_equal(gc, oc, prob, [5], exact=False)   # dense solves: pivot ties may reorder rounding
+        _fields_equal(gc, oc, prob, [5])   # dense solves share pivot rule and operation order with the oracle: bitwise
 
 
 def test_elasticity_statements(cuda_backend, oracle_mod):
