@@ -533,9 +533,13 @@ def measure_generation(args, D: Dist):
     D.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pr = lower_all()
-        _, res2, _ = evaluate(pr)
-        all_fitness = popmod.evaluate_sharded(individuals, lambda _m: ordered(pr, res2), D.rank, D.world, D.dist)
+        # trees in, fitness tuples out: evaluate_population lowers them in a background thread while the device works
+        res2 = []
+        for k in (0, 1):
+            trees_k = [tree.build_tree(probs[k], s) for kk, s in mine if kk == k]
+            r, _t = gens[k].evaluate_population(trees_k, max_in_flight=args.in_flight)
+            res2 += r
+        all_fitness = popmod.evaluate_sharded(individuals, lambda _m: ordered(progs, res2), D.rank, D.world, D.dist)
     D.barrier()
     t_e2e = time.perf_counter() - t0
     # ---- the literal plugin call, one individual after the other (what Optimizer's toolbox.map does) ---------------
@@ -630,7 +634,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--population", type=int, default=256)
-    ap.add_argument("--in-flight", type=int, default=256)
+    ap.add_argument("--in-flight", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch kernels directly (host-side solver loop) so that ncu can see them; not a bench value")

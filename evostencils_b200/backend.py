@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "evo_problem_set_slab", "evo_problem_set_slab_ex", "evo_problem_slab_info", "evo_cycle_set_stream", "evo_cycle_exec_ops", "evo_cycle_buffer",
     "evo_cycle_residual_plane_sums", "evo_cycle_vecsum", "evo_cycle_vecsum_async", "evo_cycle_read_sum",
     "evo_cycle_swap_slots", "evo_cycle_exec_part", "evo_set_option", "evo_get_option",
+    "evo_cycle_solve_begin", "evo_cycle_solve_end", "evo_cycle_solve_retime",
 )
 
 _lib = None
@@ -98,6 +99,9 @@ def load_library(path: Optional[str] = None):
     lib.evo_cycle_read_sum.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.evo_cycle_swap_slots.argtypes = [C.c_void_p, C.c_int]
     lib.evo_cycle_exec_part.argtypes = [C.c_void_p, C.POINTER(ol.CEvoOp), C.c_int, C.c_int, C.c_int]
+    lib.evo_cycle_solve_begin.argtypes = [C.c_void_p, C.POINTER(ol.CEvoSolveParams)]
+    lib.evo_cycle_solve_end.argtypes = [C.c_void_p, C.POINTER(ol.CEvoSolveParams), C.POINTER(ol.CEvoSolveResult), C.POINTER(C.c_double)]
+    lib.evo_cycle_solve_retime.argtypes = [C.c_void_p, C.POINTER(ol.CEvoSolveParams), C.POINTER(ol.CEvoSolveResult)]
     lib.evo_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.evo_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     if lib.evo_abi_version() != ol.ABI_VERSION:
@@ -266,6 +270,33 @@ class DeviceCycle:
         _check(self._lib, self._lib.evo_cycle_solve(self._h, C.byref(prm), C.byref(res),
                                                     hist.ctypes.data_as(C.POINTER(C.c_double))), "evo_cycle_solve")
         return SolveOutcome(res, hist)
+
+
+def _solve_begin(cycle: "DeviceCycle", tol: float, max_iters: int, timeout_ms: int = 0):
+    """Enqueue one complete solve on the cycle's stream and return at once (pipeline of many individuals)."""
+    cycle._prm = ol.CEvoSolveParams(tol, max_iters, 1, 0, int(timeout_ms))
+    _check(cycle._lib, cycle._lib.evo_cycle_solve_begin(cycle._h, C.byref(cycle._prm)), "evo_cycle_solve_begin")
+
+
+def _solve_end(cycle: "DeviceCycle") -> SolveOutcome:
+    prm = cycle._prm
+    cycle._res = ol.CEvoSolveResult()
+    hist = np.zeros(prm.max_iters + 1, dtype=np.float64)
+    _check(cycle._lib, cycle._lib.evo_cycle_solve_end(cycle._h, C.byref(prm), C.byref(cycle._res),
+                                                      hist.ctypes.data_as(C.POINTER(C.c_double))), "evo_cycle_solve_end")
+    cycle._hist = hist
+    return SolveOutcome(cycle._res, hist)
+
+
+def _solve_retime(cycle: "DeviceCycle") -> SolveOutcome:
+    """Time the finished solve again with the device to itself (call when nothing else is in flight)."""
+    _check(cycle._lib, cycle._lib.evo_cycle_solve_retime(cycle._h, C.byref(cycle._prm), C.byref(cycle._res)), "evo_cycle_solve_retime")
+    return SolveOutcome(cycle._res, cycle._hist)
+
+
+DeviceCycle.solve_begin = _solve_begin
+DeviceCycle.solve_end = _solve_end
+DeviceCycle.solve_retime = _solve_retime
 
 
 def _helmholtz_solve(cycle: "DeviceCycle", tol: float, max_iters: int, samples: int = 1, timeout_ms: int = 0) -> SolveOutcome:

@@ -1719,6 +1719,54 @@ static int solo_run(evo_cycle *c, int cap, float *ms)
     return EVO_OK;
 }
 
+// The batch / pipeline times include the contention of everything else that was in flight.  Time is an optimisation
+// objective (optimization/program.py:413, :449), so a member that converged is timed again with the GPU to itself: the
+// whole solve when it is short, else 1 and 4 iterations (SolveState::cap) extrapolated to its iteration count.  Members
+// that hit the iteration limit or diverged keep their time (unused: their fitness is the sentinel).
+static int retime_solo(evo_cycle *c, const evo_solve_params *prm, evo_solve_result *res)
+{
+    const int its = res->iterations;
+    if (res->status != 0 || its < 1 || its >= prm->max_iters) return EVO_OK;
+    CU(cudaSetDevice(c->p->desc.device));
+    float t_full = 0.f, t1 = 0.f, t4 = 0.f;
+    if (its <= 6) {
+        EV(solo_run(c, 0, &t_full));
+        res->time_ms = res->time_ms_min = t_full;
+    } else {
+        EV(solo_run(c, 1, &t1));
+        EV(solo_run(c, 4, &t4));
+        const double per_it = std::max(0.0, ((double)t4 - t1) / 3.0);
+        res->time_ms = res->time_ms_min = t1 + per_it * (its - 1);
+    }
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_solve_begin(evo_cycle *c, const evo_solve_params *prm)
+{
+    if (!c || !prm) return fail(EVO_ERR_INVALID, "null argument");
+    if (prm->flags & EVO_SOLVE_NO_GRAPH) return fail(EVO_ERR_UNSUPPORTED, "the solve pipeline needs the device-side outer loop");
+    EV(prepare_solve(c, prm));
+    return enqueue_solve(c, prm);
+}
+
+extern "C" int evo_cycle_solve_end(evo_cycle *c, const evo_solve_params *prm, evo_solve_result *res, double *res_hist)
+{
+    if (!c || !prm || !res) return fail(EVO_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->p->desc.device));
+    memset(res, 0, sizeof(*res));
+    float ms = 0.f;
+    EV(collect_solve(c, prm, res, res_hist, &ms));
+    res->time_ms = res->time_ms_min = ms;
+    return EVO_OK;
+}
+
+extern "C" int evo_cycle_solve_retime(evo_cycle *c, const evo_solve_params *prm, evo_solve_result *res)
+{
+    if (!c || !prm || !res) return fail(EVO_ERR_INVALID, "null argument");
+    if (!c->exec) return fail(EVO_ERR_INVALID, "no finished solve to time again");
+    return retime_solo(c, prm, res);
+}
+
 // population evaluation on one GPU: every individual's complete solve is one graph launch on its own
 // stream, nothing synchronises until all are in flight (reference: the sequential toolbox.map of
 // optimization/program.py:491, one subprocess chain per individual)
@@ -1761,29 +1809,8 @@ extern "C" int evo_batch_solve(evo_cycle **cycles, int n, const evo_solve_params
         results[i].time_ms = times[i][times[i].size() / 2];
         results[i].time_ms_min = times[i][0];
     }
-    if (prm->flags & EVO_SOLVE_SOLO_TIMING) {
-        // The times above include the contention of everything else that was in flight.  Time is an optimisation
-        // objective (optimization/program.py:413, :449), so every member that converged is timed again with the GPU
-        // to itself: the whole solve when it is short, else 1 and 4 iterations (SolveState::cap) extrapolated to its
-        // iteration count.  Members that hit the iteration limit or diverged keep the batch time (unused: their
-        // fitness is the sentinel).
-        for (int i = 0; i < n; ++i) {
-            const int its = results[i].iterations;
-            if (results[i].status != 0 || its < 1 || its >= prm->max_iters) continue;
-            evo_cycle *c = cycles[i];
-            CU(cudaSetDevice(c->p->desc.device));
-            float t_full = 0.f, t1 = 0.f, t4 = 0.f;
-            if (its <= 6) {
-                EV(solo_run(c, 0, &t_full));
-                results[i].time_ms = results[i].time_ms_min = t_full;
-            } else {
-                EV(solo_run(c, 1, &t1));
-                EV(solo_run(c, 4, &t4));
-                const double per_it = std::max(0.0, ((double)t4 - t1) / 3.0);
-                results[i].time_ms = results[i].time_ms_min = t1 + per_it * (its - 1);
-            }
-        }
-    }
+    if (prm->flags & EVO_SOLVE_SOLO_TIMING)
+        for (int i = 0; i < n; ++i) EV(retime_solo(cycles[i], prm, &results[i]));
     std::sort(wall.begin(), wall.end());
     if (batch_ms) *batch_ms = wall[wall.size() / 2];
     cudaEventDestroy(b0);

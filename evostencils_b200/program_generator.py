@@ -71,6 +71,40 @@ def _problem_from_paths(settings_path: Optional[str], knowledge_path: Optional[s
     return prob
 
 
+class _LoweredStream:
+    """Programs of a list of trees, lowered by a background thread in order (len() and iteration like a list; a tree
+    the lowering rejects yields None)."""
+
+    def __init__(self, generator, expressions, min_level):
+        import queue
+        import threading
+        self._n = len(expressions)
+        self._q = queue.Queue(maxsize=256)
+
+        def produce():
+            for e in expressions:
+                try:
+                    self._q.put(generator._finalise(generator.lower(e, min_level)))
+                except lowering.LoweringError:
+                    self._q.put(None)
+                except BaseException as exc:     # surfaced in the consumer
+                    self._q.put(exc)
+                    return
+
+        self._thread = threading.Thread(target=produce, daemon=True)
+        self._thread.start()
+
+    def __len__(self):
+        return self._n
+
+    def __iter__(self):
+        for _ in range(self._n):
+            item = self._q.get()
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+
 class B200ProgramGenerator:
     def __init__(self, absolute_compiler_path: Optional[str] = None, base_path: Optional[str] = None,
                  settings_path: Optional[str] = None, knowledge_path: Optional[str] = None,
@@ -399,11 +433,14 @@ class B200ProgramGenerator:
 
     # ---- beyond the reference surface: a whole generation in one call -----------------------------------
     def evaluate_population(self, expressions: Sequence, min_level: Optional[int] = None, infinity=1e100,
-                            evaluation_samples: int = 1, max_in_flight: int = 64, programs: Optional[Sequence[ol.Program]] = None,
+                            evaluation_samples: int = 1, max_in_flight: int = 48, programs: Optional[Sequence[ol.Program]] = None,
                             solo_timing: bool = True):
-        """Fitness tuples of many individuals; up to ``max_in_flight`` solves run concurrently on the GPU,
-        one CUDA stream and one device-side solver loop each (the reference evaluates one after the other,
-        program.py:491).  Returns (list of tuples, device milliseconds).
+        """Fitness tuples of many individuals; a sliding window of ``max_in_flight`` solves runs concurrently on the
+        GPU, one CUDA stream and one device-side solver loop each (the reference evaluates one after the other,
+        program.py:491), while the host lowers and builds the next individuals (trees are lowered by a background
+        thread: the main thread spends its time inside C calls that release the interpreter lock).  ~48 in flight
+        saturate a B200 (the kernel launch rate, not the SMs, bounds this regime; more in flight is slower).
+        Returns (list of tuples, milliseconds of the whole pipeline).
 
         ``solo_timing`` (default): the time entry of every converged individual is measured again with the GPU to
         itself (a few iterations, extrapolated to its iteration count), so that it is the same objective
@@ -420,11 +457,7 @@ class B200ProgramGenerator:
         if programs is not None:
             progs = [self._finalise(p) for p in programs]
         else:
-            for e in expressions:
-                try:
-                    progs.append(self._finalise(self.lower(e, min_level)))
-                except lowering.LoweringError:
-                    progs.append(None)
+            progs = _LoweredStream(self, list(expressions), min_level)
         sentinel = (infinity, infinity, infinity)
         if dev.problem.kind == ol.PROBLEM_HELMHOLTZ:
             for p in progs:
@@ -439,42 +472,72 @@ class B200ProgramGenerator:
                         raise
                     results.append(sentinel)
             return results, total_ms
-        for a in range(0, len(progs), max_in_flight):
-            chunk = progs[a:a + max_in_flight]
-            cycles: List[Optional[backend.DeviceCycle]] = []
-            try:
-                for p in chunk:
-                    if p is None:
-                        cycles.append(None)
-                        continue
-                    try:
-                        cycles.append(dev.build(p))
-                    except backend.BackendError as e:
-                        if e.infrastructure:
-                            raise
-                        cycles.append(None)
-                live = [c for c in cycles if c is not None]
-                outs, ms = dev.batch_solve(live, s.tol, s.max_iters, samples=max(1, evaluation_samples), solo_timing=solo_timing,
-                                           timeout_ms=self._timeout_ms()) if live else ([], 0.0)
-                total_ms += ms
-                it = iter(outs)
-                for c in cycles:
-                    if c is None:
-                        results.append(sentinel)
-                        continue
-                    o = next(it)
-                    self.total_kernel_launches += o.kernel_launches * max(1, evaluation_samples)
+        # ---- pipeline: a sliding window of `max_in_flight` solves; each one is enqueued as soon as its cycle is built
+        # (evo_cycle_solve_begin) and collected in order (evo_cycle_solve_end) while the host builds the next ones
+        from collections import deque
+        window: deque = deque()
+        done: List[Tuple[int, backend.DeviceCycle, backend.SolveOutcome]] = []
+        slots: List[Optional[Tuple[float, float, float]]] = [None] * len(progs)
+        t_start = time.perf_counter()
+
+        def finish(batch):
+            # the device is idle here: contention-free time of the members that converged, then the fitness tuples
+            for j, c, o in batch:
+                try:
+                    if solo_timing:
+                        o = c.solve_retime()
+                    self.total_kernel_launches += o.kernel_launches
                     if o.status == 2:
-                        results.append(sentinel)
-                        continue
-                    t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
-                                                              self._solver_iteration_limit)
-                    results.append(self._apply_sentinels(t, cf, its, infinity))
-            finally:
-                for c in cycles:
-                    if c is not None:
-                        c.close()
-        return results, total_ms
+                        slots[j] = sentinel
+                    else:
+                        t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
+                                                                  self._solver_iteration_limit)
+                        slots[j] = self._apply_sentinels(t, cf, its, infinity)
+                finally:
+                    c.close()
+
+        try:
+            for j, p in enumerate(progs):
+                if p is None:
+                    slots[j] = sentinel
+                    continue
+                try:
+                    c = dev.build(p)
+                except backend.BackendError as e:
+                    if e.infrastructure:
+                        raise
+                    slots[j] = sentinel
+                    continue
+                try:
+                    c.solve_begin(s.tol, s.max_iters, self._timeout_ms())
+                except backend.BackendError as e:
+                    c.close()
+                    if e.infrastructure:
+                        raise
+                    slots[j] = sentinel
+                    continue
+                window.append((j, c))
+                if len(window) >= max_in_flight:
+                    k, ck = window.popleft()
+                    done.append((k, ck, ck.solve_end()))
+                if len(done) >= 512:                   # bound the device memory held by finished cycles
+                    while window:
+                        k, ck = window.popleft()
+                        done.append((k, ck, ck.solve_end()))
+                    finish(done)
+                    done = []
+            while window:
+                k, ck = window.popleft()
+                done.append((k, ck, ck.solve_end()))
+            finish(done)
+            done = []
+        finally:
+            for _, c in window:
+                c.close()
+            for _, c, _o in done:
+                c.close()
+        total_ms += (time.perf_counter() - t_start) * 1e3
+        return [r if r is not None else sentinel for r in slots], total_ms
 
     def close(self):
         for d in self._device_problems.values():

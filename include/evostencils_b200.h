@@ -257,6 +257,15 @@ int evo_helmholtz_solve(evo_cycle *c, const evo_level_operator *A, const evo_sol
 /* many individuals in flight on one GPU, one stream each (population evaluation, program.py:491) */
 int evo_batch_solve(evo_cycle **cycles, int n_cycles, const evo_solve_params *params, evo_solve_result *results,
                     double *res_hist /* n_cycles * (max_iters+1) */, double *batch_ms);
+/* The same, as a pipeline the host drives: evo_cycle_solve_begin captures / instantiates the solver graph and enqueues
+ * one complete solve on the cycle's own stream WITHOUT waiting; evo_cycle_solve_end waits for it and returns the result
+ * (time_ms = the solve's span on the device, other solves may have been in flight); evo_cycle_solve_retime measures the
+ * time of a finished solve again with nothing else in flight (EVO_SOLVE_SOLO_TIMING semantics: call it when the device
+ * is idle) and updates result->time_ms.  A sliding window of begin / end calls keeps a constant number of
+ * individuals in flight while the host lowers and builds the next ones.                                           */
+int evo_cycle_solve_begin(evo_cycle *c, const evo_solve_params *params);
+int evo_cycle_solve_end(evo_cycle *c, const evo_solve_params *params, evo_solve_result *result, double *res_hist);
+int evo_cycle_solve_retime(evo_cycle *c, const evo_solve_params *params, evo_solve_result *result);
 
 #ifdef __cplusplus
 }

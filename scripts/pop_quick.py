@@ -25,7 +25,7 @@ def main():
     def evaluate(solo):
         ms = 0.0
         for k in (0, 1):
-            _, t = gens[k].evaluate_population([], programs=progs[k], max_in_flight=256, solo_timing=solo)
+            _, t = gens[k].evaluate_population([], programs=progs[k], max_in_flight=int(os.environ.get('IN_FLIGHT', '48')), solo_timing=solo)
             ms += t
         return ms
 
