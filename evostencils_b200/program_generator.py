@@ -434,7 +434,7 @@ class B200ProgramGenerator:
     # ---- beyond the reference surface: a whole generation in one call -----------------------------------
     def evaluate_population(self, expressions: Sequence, min_level: Optional[int] = None, infinity=1e100,
                             evaluation_samples: int = 1, max_in_flight: int = 48, programs: Optional[Sequence[ol.Program]] = None,
-                            solo_timing: bool = True):
+                            solo_timing: bool = True, keep_for_retime: bool = False):
         """Fitness tuples of many individuals; a sliding window of ``max_in_flight`` solves runs concurrently on the
         GPU, one CUDA stream and one device-side solver loop each (the reference evaluates one after the other,
         program.py:491), while the host lowers and builds the next individuals (trees are lowered by a background
@@ -446,6 +446,9 @@ class B200ProgramGenerator:
         itself (a few iterations, extrapolated to its iteration count), so that it is the same objective
         ``generate_and_evaluate`` returns and does not depend on the batch composition.  With ``False`` the time is the
         individual's span inside the concurrent batch -- higher throughput, but NOT comparable between batches.
+        ``keep_for_retime``: return the concurrent-pipeline results but keep the finished cycles, so that
+        :meth:`finish_retime` can re-time them later when the device is idle (several generators -- e.g. the two problems
+        of a generation -- run their pipelines at the same time from different host threads, then re-time in turn).
         Helmholtz problems (outer BiCGStab) are evaluated one after the other through the same path as
         ``generate_and_evaluate``."""
         min_level = self.min_level if min_level is None else min_level
@@ -480,21 +483,29 @@ class B200ProgramGenerator:
         slots: List[Optional[Tuple[float, float, float]]] = [None] * len(progs)
         t_start = time.perf_counter()
 
+        def tuple_of(o):
+            if o.status == 2:
+                return sentinel
+            t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity, self._solver_iteration_limit)
+            return self._apply_sentinels(t, cf, its, infinity)
+
+        kept: List[Tuple[int, backend.DeviceCycle]] = []
+
         def finish(batch):
-            # the device is idle here: contention-free time of the members that converged, then the fitness tuples
+            # solo_timing: the device is idle here -> contention-free time of the members that converged
             for j, c, o in batch:
+                keep = False
                 try:
                     if solo_timing:
                         o = c.solve_retime()
                     self.total_kernel_launches += o.kernel_launches
-                    if o.status == 2:
-                        slots[j] = sentinel
-                    else:
-                        t, cf, its = fitness.fitness_from_history(o.residuals, o.time_ms, s.max_iters, infinity,
-                                                                  self._solver_iteration_limit)
-                        slots[j] = self._apply_sentinels(t, cf, its, infinity)
+                    slots[j] = tuple_of(o)
+                    keep = keep_for_retime
                 finally:
-                    c.close()
+                    if keep:
+                        kept.append((j, c))
+                    else:
+                        c.close()
 
         try:
             for j, p in enumerate(progs):
@@ -537,7 +548,24 @@ class B200ProgramGenerator:
             for _, c, _o in done:
                 c.close()
         total_ms += (time.perf_counter() - t_start) * 1e3
-        return [r if r is not None else sentinel for r in slots], total_ms
+        results = [r if r is not None else sentinel for r in slots]
+        if keep_for_retime:
+            self._pending_retime = (kept, results, tuple_of)
+        return results, total_ms
+
+    def finish_retime(self):
+        """Second phase of ``evaluate_population(..., keep_for_retime=True)``: with the device idle, measure the time
+        objective of every converged member again with the GPU to itself; returns (fitness tuples, milliseconds)."""
+        kept, results, tuple_of = getattr(self, "_pending_retime", ([], [], None))
+        self._pending_retime = ([], [], None)
+        t0 = time.perf_counter()
+        try:
+            for j, c in kept:
+                results[j] = tuple_of(c.solve_retime())
+        finally:
+            for _, c in kept:
+                c.close()
+        return results, (time.perf_counter() - t0) * 1e3
 
     def close(self):
         for d in self._device_problems.values():
