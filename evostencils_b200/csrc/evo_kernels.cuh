@@ -100,6 +100,7 @@ struct SolveState {
     int cap;          // > 0: stop after this many iterations (solo re-timing of a batch member); 0 = no extra cap
     unsigned long long t_start;     // %globaltimer at the initial residual
     unsigned long long timeout_ns;  // > 0: watchdog, checked after every iteration
+    unsigned long long t_it1, t_last;   // %globaltimer after the first / the latest iteration (per-iteration time of a capped run)
     int timed_out;
     int pad;
 };
@@ -162,6 +163,8 @@ static __global__ void k_outer_update(SolveState *st, double *hist, double tol, 
     }
     if (st->done) return;
     st->it += 1;
+    st->t_last = global_timer_ns();
+    if (st->it == 1) st->t_it1 = st->t_last;
     hist[st->it] = res;
     st->res_prev = st->res;
     st->res = res;

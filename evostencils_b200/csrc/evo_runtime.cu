@@ -1728,15 +1728,22 @@ static int retime_solo(evo_cycle *c, const evo_solve_params *prm, evo_solve_resu
     const int its = res->iterations;
     if (res->status != 0 || its < 1 || its >= prm->max_iters) return EVO_OK;
     CU(cudaSetDevice(c->p->desc.device));
-    float t_full = 0.f, t1 = 0.f, t4 = 0.f;
-    if (its <= 6) {
+    float t_full = 0.f;
+    if (its <= 4) {
         EV(solo_run(c, 0, &t_full));
         res->time_ms = res->time_ms_min = t_full;
     } else {
-        EV(solo_run(c, 1, &t1));
-        EV(solo_run(c, 4, &t4));
-        const double per_it = std::max(0.0, ((double)t4 - t1) / 3.0);
-        res->time_ms = res->time_ms_min = t1 + per_it * (its - 1);
+        // ONE run capped at 3 iterations: its span (CUDA events) + the remaining iterations at the per-iteration time the
+        // device-side loop stamped (%globaltimer after iterations 1 and 3)
+        const int cap = 3;
+        EV(solo_run(c, cap, &t_full));
+        CU(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const SolveState &st = *c->h_state;
+        double per_it = 0.0;
+        if (st.it >= 2 && st.t_last > st.t_it1) per_it = (double)(st.t_last - st.t_it1) * 1e-6 / (st.it - 1);
+        else per_it = t_full / cap;
+        res->time_ms = res->time_ms_min = t_full + per_it * (its - st.it);
     }
     return EVO_OK;
 }
