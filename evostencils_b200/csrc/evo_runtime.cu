@@ -1406,7 +1406,8 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
         cap.open = false;
         if (ce != cudaSuccess || e != cudaSuccess) return fail(EVO_ERR_CUDA, "epilogue capture failed");
     }
-    c->kernels_per_cycle = c->launch_counter;
+    // (kernels_per_cycle was taken after the FIRST body: the second half of a ping-pong body is another cycle, not more
+    // launches per cycle)
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, g, 0);
     if (e != cudaSuccess) return fail(EVO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
