@@ -8,15 +8,19 @@ template <typename T, int DIM, int NF> struct Launch {
     // d_partials holds the canonical row sums [NF][nzi][ni]; reduce them to SolveState::sum
     static int reduce_rows(evo_cycle *c, int ni, cudaStream_t s)
     {
+        const double *vals = c->d_partials;
         if (DIM == 3) {
             double *planes = c->d_partials + (size_t)NF * ni * ni;
             k_reduce_planes<<<(unsigned)((NF * ni + 7) / 8), 256, 0, s>>>(c->d_partials, NF * ni, ni, planes);
-            k_reduce_final<<<1, 32, 0, s>>>(planes, NF, ni, c->d_state);
-            c->launch_counter += 2;
-        } else {
-            k_reduce_final<<<1, 32, 0, s>>>(c->d_partials, NF, ni, c->d_state);
             c->launch_counter += 1;
+            vals = planes;
         }
+        const evo_cycle::Finish &fin = c->fin;
+        if (fin.on)     // solver graph: the loop's bookkeeping rides on the last reduction
+            k_reduce_final_update<<<1, 32, 0, s>>>(vals, NF, ni, c->d_state, c->d_hist, fin.tol, fin.max_iters, fin.mode, fin.n_handles,
+                                                   fin.h[0], fin.h[1]);
+        else k_reduce_final<<<1, 32, 0, s>>>(vals, NF, ni, c->d_state);
+        c->launch_counter += 1;
         CU(cudaGetLastError());
         return EVO_OK;
     }
@@ -31,6 +35,15 @@ template <typename T, int DIM, int NF> struct Launch {
         if (norm && star::try_residual_norm<T, DIM, NF>(g, c->sten[l], u, f, r, c->d_partials, !c->res_dead_on_entry, s)) {
             // residual and canonical row sums in one pass; the field itself is only stored if a later
             // statement may read it
+            c->launch_counter += 1;
+            EV(reduce_rows(c, ni, s));
+            return EVO_OK;
+        }
+        if (norm && DIM == 2 && !slab_level(c->p, l)) {
+            // 2-D (and complex) convergence norm: generic residual and row sums in one launch
+            const unsigned nb = (unsigned)((ni + 3) / 4);
+            if (c->res_dead_on_entry) k_residual_rowsum<T, DIM, NF, false><<<nb, 128, 0, s>>>(g, c->sten[l], u, f, r, c->d_partials);
+            else k_residual_rowsum<T, DIM, NF, true><<<nb, 128, 0, s>>>(g, c->sten[l], u, f, r, c->d_partials);
             c->launch_counter += 1;
             EV(reduce_rows(c, ni, s));
             return EVO_OK;
@@ -327,7 +340,8 @@ template <typename T, int DIM, int NF> struct Launch {
         if constexpr (DIM == 2 && NF == 1 && std::is_same<T, double>::value)
             done2d = !slab_level(c->p, l) && w2::try_residual_restrict(c->p->sm_count, gf, gc, c->sten[l], c->p->R, (const double *)u.p[0],
                                                                       (const double *)f.p[0], (double *)dst.p[0], s);
-        if (!done2d && !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
+        if (!done2d && !star::try_residual_restrict_col<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s) &&
+            !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
             if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
             k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
         }

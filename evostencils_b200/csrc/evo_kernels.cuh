@@ -149,9 +149,8 @@ static __global__ void __launch_bounds__(32) k_reduce_final(const double *vals, 
 
 // bookkeeping of the outer loop: `until res < tol*res0 or it >= maxIts`
 // (example_problems/Poisson/2D_FD_Poisson_fromL2.exa3:3-4); mode 0 = initial residual, 1 = after a cycle
-static __global__ void k_outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
+__device__ __forceinline__ void outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double res = sqrt(st->sum);
     if (mode == 0) {
         st->res0 = res; st->res_prev = res; st->res = res; st->it = 0; st->bad = 0; st->timed_out = 0;
@@ -171,6 +170,50 @@ static __global__ void k_outer_update(SolveState *st, double *hist, double tol, 
     if (!isfinite(res)) { st->bad = 1; st->done = 1; }
     else if (res < tol * st->res0 || st->it >= max_iters || (st->cap > 0 && st->it >= st->cap)) st->done = 1;
     else if (st->timeout_ns && global_timer_ns() - st->t_start > st->timeout_ns) { st->timed_out = 1; st->done = 1; }
+}
+static __global__ void k_outer_update(SolveState *st, double *hist, double tol, int max_iters, int mode)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    outer_update(st, hist, tol, max_iters, mode);
+}
+// k_reduce_final + k_outer_update + the conditional handles of the solver graph's loop in one launch
+static __global__ void __launch_bounds__(32) k_reduce_final_update(const double *vals, int nf, int m, SolveState *st, double *hist,
+                                                                   double tol, int max_iters, int mode, int n_handles,
+                                                                   cudaGraphConditionalHandle h0, cudaGraphConditionalHandle h1)
+{
+    double total = 0.0;
+    for (int i = 0; i < nf; ++i) total = total + warp_vecsum(vals + (long long)i * m, m);
+    if (threadIdx.x != 0) return;
+    st->sum = total;
+    outer_update(st, hist, tol, max_iters, mode);
+    const unsigned v = st->done ? 0u : 1u;
+    if (n_handles >= 1) cudaGraphSetConditional(h0, v);
+    if (n_handles >= 2) cudaGraphSetConditional(h1, v);
+}
+
+// residual and canonical row sums of |r|^2 in one pass (generic stencil tables; one warp per row, the lanes walk the
+// row in the canonical order); STORE = also write the residual field
+template <typename T, int DIM, int NF, bool STORE>
+__global__ void __launch_bounds__(128) k_residual_rowsum(const Geom g, const __grid_constant__ OpSten st, Fields<T> u, Fields<T> f,
+                                                         Fields<T> r, double *rows)
+{
+    const int ni = g.n - 2, nzi = DIM == 3 ? ni : 1, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= (long long)ni * nzi) return;
+    const int y = 1 + (int)(row % ni), z = DIM == 3 ? 1 + (int)(row / ni) : 0;
+    const long long base = node_index(g, 1, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        double acc = 0.0;
+        for (int x = lane; x < ni; x += 32) {
+            const long long idx = base + x;
+            const T v = f.p[i][idx] - apply_row<T, NF>(g, st, u, i, idx);
+            if (STORE) r.p[i][idx] = v;
+            acc = acc + abs2(v);
+        }
+        acc = warp_butterfly(acc);
+        if (lane == 0) rows[(long long)i * ni * nzi + row] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

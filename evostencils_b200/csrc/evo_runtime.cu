@@ -1173,15 +1173,6 @@ __global__ void k_set_while_condition(cudaGraphConditionalHandle handle, const S
     if (threadIdx.x == 0 && blockIdx.x == 0) cudaGraphSetConditional(handle, st->done ? 0u : 1u);
 }
 
-// after an odd cycle of a ping-pong body: continue with the second half (IF node) and the loop only if not done
-__global__ void k_set_two_conditions(cudaGraphConditionalHandle a, cudaGraphConditionalHandle b, const SolveState *st)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const unsigned v = st->done ? 0u : 1u;
-        cudaGraphSetConditional(a, v);
-        cudaGraphSetConditional(b, v);
-    }
-}
 // after the loop: an odd number of cycles leaves the solution in the [next] slots
 __global__ void k_set_odd_condition(cudaGraphConditionalHandle h, const SolveState *st)
 {
@@ -1317,13 +1308,14 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
         rc = enqueue_cycle(c, s);
         std::swap(none, c->ops);
     }
-    if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
     cudaGraphConditionalHandle h_if = 0;
-    if (rc == EVO_OK) {
-        k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 1);
-        c->launch_counter += 2;
-        if (!c->pingpong) k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
-    }
+    if (rc == EVO_OK && c->pingpong) CU(cudaGraphConditionalHandleCreate(&h_if, g, 0, cudaGraphCondAssignDefault));
+    // the last reduction of the norm also updates the loop state and sets the loop's condition(s)
+    struct FinishOff { evo_cycle *c; ~FinishOff() { c->fin.on = false; } } finish_off{c};
+    c->fin.on = true; c->fin.tol = tol; c->fin.max_iters = max_iters; c->fin.mode = 1;
+    c->fin.n_handles = c->pingpong ? 2 : 1; c->fin.h[0] = handle; c->fin.h[1] = h_if;
+    if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
+    c->fin.on = false;
     c->kernels_per_cycle = c->launch_counter;
     e = cudaStreamEndCapture(s, nullptr);
     cap.open = false;
@@ -1332,25 +1324,13 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
     if (c->pingpong) {
         std::vector<cudaGraphNode_t> bl;
         EV(graph_leaves(body, bl));
-        CU(cudaGraphConditionalHandleCreate(&h_if, g, 0, cudaGraphCondAssignDefault));
-        cudaGraphNode_t setc;
-        {
-            cudaKernelNodeParams kp;
-            memset(&kp, 0, sizeof(kp));
-            void *args[3] = {(void *)&handle, (void *)&h_if, (void *)&c->d_state};
-            kp.func = (void *)k_set_two_conditions;
-            kp.gridDim = dim3(1);
-            kp.blockDim = dim3(32);
-            kp.kernelParams = args;
-            CU(cudaGraphAddKernelNode(&setc, body, bl.data(), bl.size(), &kp));
-        }
         cudaGraphNodeParams ip = {cudaGraphNodeTypeConditional};
         ip.type = cudaGraphNodeTypeConditional;
         ip.conditional.handle = h_if;
         ip.conditional.type = cudaGraphCondTypeIf;
         ip.conditional.size = 1;
         cudaGraphNode_t inode;
-        CU(cudaGraphAddNode(&inode, body, &setc, 1, &ip));
+        CU(cudaGraphAddNode(&inode, body, bl.data(), bl.size(), &ip));
         cudaGraph_t second = ip.conditional.phGraph_out[0];
         CU(cudaStreamBeginCaptureToGraph(s, second, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
         cap.open = true; cap.owns_graph = false;
@@ -1359,11 +1339,9 @@ static int build_solver_graph(evo_cycle *c, double tol, int max_iters)
         for (int l = c->p->desc.min_level; l <= c->p->desc.max_level; ++l)
             for (int i = 0; i < c->p->desc.n_fields; ++i) still = still || c->lv[l].swapped[i];
         if (rc == EVO_OK && still) rc = fail(EVO_ERR_INVALID, "ping-pong body did not return to the canonical slots");
+        c->fin.on = true; c->fin.n_handles = 1; c->fin.h[0] = handle; c->fin.h[1] = 0;
         if (rc == EVO_OK) rc = dispatch_residual_norm(c, s);
-        if (rc == EVO_OK) {
-            k_outer_update<<<1, 32, 0, s>>>(c->d_state, c->d_hist, tol, max_iters, 1);
-            k_set_while_condition<<<1, 32, 0, s>>>(handle, c->d_state);
-        }
+        c->fin.on = false;
         e = cudaStreamEndCapture(s, nullptr);
         cap.open = false;
         if (rc != EVO_OK) return rc;

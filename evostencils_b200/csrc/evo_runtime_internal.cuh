@@ -14,6 +14,7 @@
 #include "evo_kernels.cuh"
 #include "evo_kernels_star.cuh"
 #include "evo_kernels_rbcol.cuh"
+#include "evo_kernels_rrcol.cuh"
 #include "evo_kernels_warp2d.cuh"
 #include "evo_kernels_fas.cuh"
 #include "evo_kernels_helm.cuh"
@@ -101,6 +102,14 @@ struct evo_cycle {
     int graph_max_iters;
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
+    // While a solver-graph body is captured: the final reduction of the convergence norm also does the outer loop's
+    // bookkeeping and sets the loop's conditional handles (one launch instead of three).
+    struct Finish {
+        bool on = false;
+        double tol = 0.0;
+        int max_iters = 0, mode = 0, n_handles = 0;
+        cudaGraphConditionalHandle h[2] = {0, 0};
+    } fin;
     bool use_while_graph;
     bool pingpong = false;                               // the WHILE body holds two cycles (see build_solver_graph)
     bool odd_swap[EVO_MAX_LEVELS][EVO_MAX_FIELDS] = {};  // levels whose SOL ends in the [next] slot after one cycle

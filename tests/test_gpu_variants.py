@@ -249,3 +249,26 @@ def test_streamed_2d_transfers_bit_exact(cuda_backend, oracle_mod, option, star2
         oc.apply(1)
         _equal(gc, oc, prob, [level], (ol.BUF_SOL, ol.BUF_RES))
         _equal(gc, oc, prob, [level - 1], (ol.BUF_SOL, ol.BUF_RHS))
+
+
+# fused residual + restriction, 3-D: 0-4 shared-memory ring kernel (tile shapes), 10-17 register-carried column kernel
+@pytest.mark.parametrize("variant", [0, 9, 1, 2, 3, 4, 10, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("level", [6, 7])
+def test_residual_restrict_3d_variants_bit_exact(cuda_backend, oracle_mod, option, variant, level):
+    option("EVO_RR_VARIANT", variant)
+    prob = problems.Poisson3D(level - 2, level)
+    z = (0, 0, 0)
+    ops = [ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_JACOBI, omega=0.9, unknowns=((0, z),)),
+           ol.Op(ol.OP_SMOOTH, level, mode=ol.MODE_REDBLACK, omega=1.2, unknowns=((0, z),)),
+           ol.Op(ol.OP_RESIDUAL_RESTRICT, level, dst=ol.BUF_RHS, src=ol.BUF_RES),
+           ol.Op(ol.OP_ZERO, level - 1, dst=ol.BUF_SOL),
+           ol.Op(ol.OP_SMOOTH, level - 1, mode=ol.MODE_REDBLACK, omega=1.1, unknowns=((0, z),)),
+           ol.Op(ol.OP_PROLONG_ADD, level, src=ol.BUF_SOL, omega=0.95)]
+    prog = cycles.build_program(prob, ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, [level], (ol.BUF_SOL,))
+        _equal(gc, oc, prob, [level - 1], (ol.BUF_SOL, ol.BUF_RHS))
