@@ -4,6 +4,9 @@
 #include "evo_runtime_internal.cuh"
 #include "evo_kernels_run.cuh"
 
+// grids up to this many inner nodes are latency bound: single-CTA / warp-per-node variants of the generic kernels
+static constexpr long long SMALL_GRID_NODES = 4096;
+
 template <typename T, int DIM, int NF> struct Launch {
     // d_partials holds the canonical row sums [NF][nzi][ni]; reduce them to SolveState::sum
     static int reduce_rows(evo_cycle *c, int ni, cudaStream_t s)
@@ -206,6 +209,11 @@ template <typename T, int DIM, int NF> struct Launch {
                     } else {
                         return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
                     }
+                } else if ((long long)(g.n - 2) * (g.n - 2) * (DIM == 3 ? g.n - 2 : 1) <= SMALL_GRID_NODES && !slab_level(c->p, l)) {
+                    // tiny grid: every remaining sweep and both colours in one launch
+                    k_smooth_rb_small<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs, reps - rep);
+                    c->launch_counter++;
+                    rep = reps;
                 } else {
                     for (int color = 0; color < 2; ++color) {
                         sp.color = color;
@@ -336,14 +344,26 @@ template <typename T, int DIM, int NF> struct Launch {
         if (c->zc_lo >= 0) { gc.zlo = c->zc_lo; gc.zhi = c->zc_hi; }   // domain decomposition: only these coarse planes
         auto u = fields_of<T>(c->lv[l].buf[EVO_BUF_SOL], NF), f = fields_of<T>(c->lv[l].buf[EVO_BUF_RHS], NF),
              dst = fields_of<T>(c->lv[l - 1].buf[EVO_BUF_RHS], NF);
+        // `SOL@(l-1) = 0` as the next statement: the 2-D kernels store the zeros of the inner nodes along with the
+        // coarse right-hand side (the boundary layer of a correction level is never written, it stays 0)
+        Fields<T> zero;
+        for (int i = 0; i < EVO_MAX_FIELDS; ++i) zero.p[i] = nullptr;
+        if (c->fuse_zero)
+            for (int i = 0; i < NF; ++i) zero.p[i] = (T *)c->lv[l - 1].buf[EVO_BUF_SOL][i];
         bool done2d = false;
         if constexpr (DIM == 2 && NF == 1 && std::is_same<T, double>::value)
             done2d = !slab_level(c->p, l) && w2::try_residual_restrict(c->p->sm_count, gf, gc, c->sten[l], c->p->R, (const double *)u.p[0],
-                                                                      (const double *)f.p[0], (double *)dst.p[0], s);
-        if (!done2d && !star::try_residual_restrict_col<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s) &&
-            !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
+                                                                      (const double *)f.p[0], (double *)dst.p[0], (double *)zero.p[0], s);
+        if (done2d) {
+            if (zero.p[0]) c->fuse_zero = false;
+        } else if (!star::try_residual_restrict_col<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s) &&
+                   !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
             if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
-            k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst);
+            const long long cn = (long long)(gc.n - 2) * (gc.n - 2) * (DIM == 3 ? gc.n - 2 : 1);
+            if (cn <= SMALL_GRID_NODES / (DIM == 3 ? 8 : 4))      // tiny coarse grid: one warp per coarse node
+                k_residual_restrict_warp<T, DIM, NF><<<(unsigned)((cn + 3) / 4), 128, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst, zero);
+            else k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst, zero);
+            if (zero.p[0]) c->fuse_zero = false;
         }
         c->launch_counter++;
         CU(cudaGetLastError());
@@ -435,10 +455,12 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
         if (!disabled && smem <= 160 * 1024 && NF * nrows <= 512 && (DIM == 2 || ni <= 64)) {
             static bool attr = false;
             if (!attr) {
-                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                 attr = true;
             }
-            k_coarse_cg_smem<DIM, NF><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
+            if (nrows <= 16 && smem <= 40 * 1024)      // tiny grid (5^3, 9^2 ...): four warps, cheap block barriers
+                k_coarse_cg_smem<DIM, NF, 128><<<1, 128, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
+            else k_coarse_cg_smem<DIM, NF, 1024><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
             c->launch_counter++;
             CU(cudaGetLastError());
             return EVO_OK;

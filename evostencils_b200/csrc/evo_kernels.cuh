@@ -63,6 +63,11 @@ __device__ __forceinline__ cplx shfl_xor(cplx v, int o)
 {
     return cplx(__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o));
 }
+__device__ __forceinline__ double shfl_idx(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cplx shfl_idx(cplx v, int src)
+{
+    return cplx(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src));
+}
 template <typename T> __device__ __forceinline__ T warp_butterfly(T v)
 {
 #pragma unroll
@@ -392,6 +397,32 @@ __global__ void __launch_bounds__(BX) k_smooth(const Geom g, const __grid_consta
     local_solve<T, DIM, NF, NU>(g, st, sp, src, dst, rhs, x, y, z);
 }
 
+// order-independent coloured sweeps on a tiny grid (<= 4096 inner nodes): ONE CTA runs all `sweeps` repetitions and both
+// colours, a block barrier between the colours -- 2 x sweeps kernel nodes become one.  Same local_solve per anchor as
+// k_smooth, anchors of one colour are independent -> bit-identical.
+template <typename T, int DIM, int NF, int NU>
+__global__ void __launch_bounds__(1024) k_smooth_rb_small(const Geom g, const __grid_constant__ OpSten st,
+                                                          const __grid_constant__ SmoothParams sp, Fields<T> u, Fields<T> rhs,
+                                                          const int sweeps)
+{
+    SmoothParams loc = sp;
+    const int ni = g.n - 2, nzi = DIM == 3 ? ni : 1;
+    const int half = (ni + 1) / 2;                  // anchors of one colour per row (upper bound)
+    const int total = half * ni * nzi;
+    for (int sw = 0; sw < sweeps; ++sw)
+        for (int color = 0; color < 2; ++color) {
+            loc.color = color;
+            for (int t = threadIdx.x; t < total; t += 1024) {
+                const int tx = t % half, row = t / half;
+                const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
+                const int x = 1 + 2 * tx + ((1 + y + z + color) & 1);
+                if (x <= g.n - 2) local_solve<T, DIM, NF, NU>(g, st, loc, u, u, rhs, x, y, z);
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+}
+
 // order-dependent coloured sweep (e.g. collective RB-GS on the elasticity system, whose dxy corner
 // terms couple same-colour nodes): the reference's loop is sequential, i0 fastest; anchors of one row
 // are mutually independent for 3^d stencils, rows depend on the previous row -> one CTA walks the rows
@@ -513,7 +544,7 @@ template <typename T, int DIM, int NF>
 __global__ void __launch_bounds__(BX) k_residual_restrict(const Geom gf, const Geom gc,
                                                           const __grid_constant__ OpSten st,
                                                           const __grid_constant__ TransferW R, Fields<T> u, Fields<T> f,
-                                                          Fields<T> dst)
+                                                          Fields<T> dst, Fields<T> zero /* coarse fields to clear, or null */)
 {
     const int x = 1 + blockIdx.x * BX + threadIdx.x, y = 1 + blockIdx.y, z = DIM == 3 ? 1 + blockIdx.z : 0;
     if (x > gc.n - 2) return;
@@ -531,6 +562,42 @@ __global__ void __launch_bounds__(BX) k_residual_restrict(const Geom gf, const G
             acc = acc + R.w[q] * rv;
         }
         dst.p[i][cidx] = acc;
+        if (zero.p[i]) zero.p[i][cidx] = T(0.0);
+    }
+}
+
+// the same statement on a tiny coarse grid: one WARP per coarse node, lane q evaluates the fine residual of restriction
+// entry q, lane 0 adds the R.nnz products in ascending q like the loop above (bit-identical).  The thread-per-node kernel
+// spends 20+ us on a 7^3 grid (27 dependent stencil evaluations per thread); this one ~4 us.
+template <typename T, int DIM, int NF>
+__global__ void __launch_bounds__(128) k_residual_restrict_warp(const Geom gf, const Geom gc, const __grid_constant__ OpSten st,
+                                                                const __grid_constant__ TransferW R, Fields<T> u, Fields<T> f,
+                                                                Fields<T> dst, Fields<T> zero)
+{
+    const int nci = gc.n - 2, lane = threadIdx.x & 31;
+    const long long node = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long long count = (long long)nci * nci * (DIM == 3 ? nci : 1);
+    if (node >= count) return;
+    const int x = 1 + (int)(node % nci), y = 1 + (int)((node / nci) % nci), z = DIM == 3 ? 1 + (int)(node / ((long long)nci * nci)) : 0;
+    const long long cidx = node_index(gc, x, y, z);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        T term = T(0.0);
+        if (lane < R.nnz) {
+            const int fx = 2 * x + R.ox[lane], fy = 2 * y + R.oy[lane], fz = DIM == 3 ? 2 * z + R.oz[lane] : 0;
+            T rv = T(0.0);
+            if (fx >= 1 && fx <= gf.n - 2 && fy >= 1 && fy <= gf.n - 2 && (DIM == 2 || (fz >= 1 && fz <= gf.n - 2))) {
+                const long long idx = node_index(gf, fx, fy, fz);
+                rv = f.p[i][idx] - apply_row<T, NF>(gf, st, u, i, idx);
+            }
+            term = R.w[lane] * rv;
+        }
+        T acc = T(0.0);
+        for (int q = 0; q < R.nnz; ++q) acc = acc + shfl_idx(term, q);
+        if (lane == 0) {
+            dst.p[i][cidx] = acc;
+            if (zero.p[i]) zero.p[i][cidx] = T(0.0);
+        }
     }
 }
 
@@ -667,8 +734,10 @@ __global__ void __launch_bounds__(1024) k_coarse_cg(const Geom g, const __grid_c
 // Shared-memory resident CG for coarsest levels that fit (4 vectors x fields x n^d doubles): the
 // global-memory version above spends ~7 us per iteration on dependent global round trips; here a CG
 // iteration is 5 block barriers.  Same arithmetic and the same canonical reductions -> bit-identical.
-template <int DIM, int NF>
-__global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __grid_constant__ OpSten st, Fields<double> xg,
+// NT threads: 1024, or 128 for grids with at most 16 rows (block barriers among 4 warps instead of 32: a 5^3 solve takes
+// a third of the time, and it runs 128 times per W-cycle on 513^3)
+template <int DIM, int NF, int NT>
+__global__ void __launch_bounds__(NT) k_coarse_cg_smem(const Geom g, const __grid_constant__ OpSten st, Fields<double> xg,
                                                          Fields<double> bg, int max_it, double tol, int *iters_out)
 {
     extern __shared__ double sm[];
@@ -680,10 +749,10 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *x = sm, *r = sm + (size_t)NF * vol, *p = sm + 2 * (size_t)NF * vol, *ap = sm + 3 * (size_t)NF * vol;
     // compact index of node (ix, iy, iz): (iz*n + iy)*n + ix
-    for (int t = threadIdx.x; t < 4 * NF * vol; t += 1024) sm[t] = 0.0;
+    for (int t = threadIdx.x; t < 4 * NF * vol; t += NT) sm[t] = 0.0;
     __syncthreads();
     for (int i = 0; i < NF; ++i)
-        for (int row = warp; row < nrows; row += 32) {
+        for (int row = warp; row < nrows; row += NT / 32) {
             const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
             for (int xx = 1 + lane; xx <= ni; xx += 32) {
                 const double v = bg.p[i][node_index(g, xx, y, z)];
@@ -702,7 +771,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
         const double *rs = rowsum + rs_flip * 512;
         for (int i = 0; i < NF; ++i) {
             if (DIM == 3) {
-                for (int zz = warp; zz < nzi; zz += 32) {
+                for (int zz = warp; zz < nzi; zz += NT / 32) {
                     double sacc = warp_vecsum(rs + i * nrows + zz * ni, ni);
                     if (lane == 0) planes[zz] = sacc;
                 }
@@ -718,7 +787,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
     };
     // r.r
     for (int i = 0; i < NF; ++i)
-        for (int row = warp; row < nrows; row += 32) {
+        for (int row = warp; row < nrows; row += NT / 32) {
             const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
             double acc = 0.0;
             for (int xx = 1 + lane; xx <= ni; xx += 32) {
@@ -735,7 +804,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
         while (it < max_it) {
             // pass A: ap = A p and the row sums of p.ap
             for (int i = 0; i < NF; ++i)
-                for (int row = warp; row < nrows; row += 32) {
+                for (int row = warp; row < nrows; row += NT / 32) {
                     const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
                     double acc = 0.0;
                     for (int xx = 1 + lane; xx <= ni; xx += 32) {
@@ -757,7 +826,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
             const double alpha = rr / pap;
             // pass B: x += alpha p, r -= alpha ap and the row sums of r.r
             for (int i = 0; i < NF; ++i)
-                for (int row = warp; row < nrows; row += 32) {
+                for (int row = warp; row < nrows; row += NT / 32) {
                     const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
                     double acc = 0.0;
                     for (int xx = 1 + lane; xx <= ni; xx += 32) {
@@ -774,7 +843,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
             ++it;
             if (!(sqrt(rr_new) > tol * r0)) break;
             const double beta = rr_new / rr;
-            for (int t = threadIdx.x; t < NF * vol; t += 1024) p[t] = r[t] + beta * p[t];   // boundary entries stay 0
+            for (int t = threadIdx.x; t < NF * vol; t += NT) p[t] = r[t] + beta * p[t];   // boundary entries stay 0
             rr = rr_new;
             __syncthreads();
         }
@@ -782,7 +851,7 @@ __global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __g
     __syncthreads();
     // x -> SOL (inner nodes; the boundary layer of SOL is 0 on the coarsest level and stays so)
     for (int i = 0; i < NF; ++i)
-        for (int row = warp; row < nrows; row += 32) {
+        for (int row = warp; row < nrows; row += NT / 32) {
             const int y = 1 + row % ni, z = DIM == 3 ? 1 + row / ni : 0;
             for (int xx = 1 + lane; xx <= ni; xx += 32) xg.p[i][node_index(g, xx, y, z)] = x[i * vol + (z * n + y) * n + xx];
         }

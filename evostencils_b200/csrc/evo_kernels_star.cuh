@@ -1086,7 +1086,7 @@ static bool launch_residual_restrict(int sm_count, const Geom &gf, const Geom &g
     const long long slots = (long long)occ * sm_count;
     int best = 1;
     double best_cost = 1e300;
-    for (int ch = 1; ch <= 32 && (ch == 1 || ch * 8 <= planes); ++ch) {
+    for (int ch = 1; ch <= 32 && (ch == 1 || ch * 4 <= planes); ++ch) {
         const int zc = (planes + ch - 1) / ch;
         const long long ctas = (long long)tx * ty * ((planes + zc - 1) / zc);
         const double cost = (double)((ctas + slots - 1) / slots) * (zc + 3);

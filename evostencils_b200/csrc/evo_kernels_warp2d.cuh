@@ -308,7 +308,8 @@ static bool try_prolong_add(const Geom &gf, const Geom &gc, const TransferW &P, 
 // like k_residual_restrict / the oracle; the residual counts as 0 on the boundary layer.
 static __global__ void __launch_bounds__(W2_WARPS * 32) k2_residual_restrict_warp(const Geom gf, const Geom gc, const Star5 c, const Dense9 R,
                                                                           const double *__restrict__ u, const double *__restrict__ f,
-                                                                          double *__restrict__ dst, const int rows_per_chunk)
+                                                                          double *__restrict__ dst, double *__restrict__ zero,
+                                                                          const int rows_per_chunk)
 {
     const int n = gf.n, nc = gc.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -370,7 +371,10 @@ static __global__ void __launch_bounds__(W2_WARPS * 32) k2_residual_restrict_war
             acc = acc + R.w[0] * a_m; acc = acc + R.w[1] * rm.l; acc = acc + R.w[2] * rm.r;
             acc = acc + R.w[3] * a_0; acc = acc + R.w[4] * r0.l; acc = acc + R.w[5] * r0.r;
             acc = acc + R.w[6] * a_p; acc = acc + R.w[7] * res.l; acc = acc + R.w[8] * res.r;
-            if (deliver) dst[(long long)Y * gc.pitch + X] = acc;
+            if (deliver) {
+                dst[(long long)Y * gc.pitch + X] = acc;
+                if (zero) zero[(long long)Y * gc.pitch + X] = 0.0;       // the coarse initial guess (`SOL@(l-1) = 0`)
+            }
         }
         rm = r0; r0 = res;
         um = u0; u0 = up;
@@ -379,7 +383,7 @@ static __global__ void __launch_bounds__(W2_WARPS * 32) k2_residual_restrict_war
 }
 
 static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, const OpSten &st, const TransferW &R, const double *u,
-                                  const double *f, double *dst, cudaStream_t s)
+                                  const double *f, double *dst, double *zero, cudaStream_t s)
 {
     Star5 c;
     if (gf.dim != 2 || gf.n < min_n() || R.nnz != 9 || !match_star5(st.s[0][0], &c)) return false;
@@ -397,7 +401,7 @@ static bool try_residual_restrict(int sm_count, const Geom &gf, const Geom &gc, 
     int chunks = (int)std::min<long long>(std::max<long long>(1, want_warps / strips), std::max(1, nci / 4));
     int rows = (nci + chunks - 1) / chunks;
     chunks = (nci + rows - 1) / rows;
-    k2_residual_restrict_warp<<<dim3(bx, chunks), W2_WARPS * 32, 0, s>>>(gf, gc, c, W, u, f, dst, rows);
+    k2_residual_restrict_warp<<<dim3(bx, chunks), W2_WARPS * 32, 0, s>>>(gf, gc, c, W, u, f, dst, zero, rows);
     return cudaGetLastError() == cudaSuccess;
 }
 

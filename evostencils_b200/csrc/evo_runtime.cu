@@ -721,7 +721,21 @@ static int enqueue_cycle_ops(evo_cycle *c, cudaStream_t s)
             EV(enqueue_fused_run(c, &c->ops[t], (int)(e - t), s));
             t = e;
         } else {
-            EV(dispatch_op(c, c->ops[t], s));
+            const evo_op &op = c->ops[t];
+            const evo_problem_desc &d = c->p->desc;
+            // `RHS@(l-1) = R (f - A u)` followed by `SOL@(l-1) = 0`: one kernel writes both coarse fields
+            if (op.code == EVO_OP_RESIDUAL_RESTRICT && t + 1 < n && c->ops[t + 1].code == EVO_OP_ZERO && c->ops[t + 1].level == op.level - 1 &&
+                c->ops[t + 1].dst == EVO_BUF_SOL && d.kind == EVO_PROBLEM_LINEAR && d.scalar_words == 1 && c->zc_lo < 0 &&
+                option(OPT_NO_ZERO_FUSE) == 0) {
+                c->fuse_zero = true;
+                const int rc = dispatch_op(c, op, s);
+                const bool folded = !c->fuse_zero;
+                c->fuse_zero = false;
+                EV(rc);
+                t += folded ? 2 : 1;
+                continue;
+            }
+            EV(dispatch_op(c, op, s));
             ++t;
         }
     }

@@ -5,7 +5,7 @@ bit-identical to the plain loops of the oracle."""
 import numpy as np
 import pytest
 
-from evostencils_b200 import cycles, oplist as ol, problems
+from evostencils_b200 import cycles, lowering, oplist as ol, problems
 
 pytestmark = pytest.mark.gpu
 
@@ -272,3 +272,37 @@ def test_residual_restrict_3d_variants_bit_exact(cuda_backend, oracle_mod, optio
         oc.apply(1)
         _equal(gc, oc, prob, [level], (ol.BUF_SOL,))
         _equal(gc, oc, prob, [level - 1], (ol.BUF_SOL, ol.BUF_RHS))
+
+
+@pytest.mark.parametrize("name", ["p2", "el", "p3"])
+@pytest.mark.parametrize("no_fuse", [0, 1])
+def test_zero_folded_into_the_restriction(cuda_backend, oracle_mod, option, name, no_fuse):
+    """`RHS@(l-1) = R (f - A u)` followed by `SOL@(l-1) = 0` (every coarse-grid correction, exastencils.py:698-716): the
+    generic and the 2-D streaming restriction kernels store the zeros themselves (EVO_NO_ZERO_FUSE = 1: separate memset
+    node).  Both ways must equal the oracle on every level after complete cycles."""
+    option("EVO_NO_ZERO_FUSE", no_fuse)
+    option("EVO_STAR2D", 65)
+    prob = {"p2": problems.Poisson2D(3, 8), "el": problems.LinearElasticity2D(3, 6), "p3": problems.Poisson3D(2, 5)}[name]
+    prog = lowering.optimise(cycles.v_cycle(prob, 2, 1, 1.1, True))
+    assert any(o.code == ol.OP_RESIDUAL_RESTRICT for o in prog.ops) and any(o.code == ol.OP_ZERO for o in prog.ops)
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(3):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, range(prob.min_level, prob.max_level + 1), (ol.BUF_SOL, ol.BUF_RHS))
+
+
+@pytest.mark.parametrize("name,lo,hi", [("p3", 2, 4), ("p3", 2, 3), ("p2", 2, 6), ("p2", 3, 5), ("el", 2, 5)])
+def test_tiny_grid_kernels_bit_exact(cuda_backend, oracle_mod, name, lo, hi):
+    """Grids up to 4096 inner nodes: all repetitions and both colours of a red-black sweep run in one single-CTA launch
+    (k_smooth_rb_small), the fused residual+restriction uses one warp per coarse node (k_residual_restrict_warp).  W-cycle
+    with three merged pre-smoothing sweeps against the oracle."""
+    prob = {"p2": problems.Poisson2D, "el": problems.LinearElasticity2D, "p3": problems.Poisson3D}[name](lo, hi)
+    prog = lowering.optimise(cycles.w_cycle(prob, 3, 2, 1.15, True))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, range(prob.min_level, prob.max_level + 1), (ol.BUF_SOL, ol.BUF_RHS))
