@@ -455,12 +455,10 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
         if (!disabled && smem <= 160 * 1024 && NF * nrows <= 512 && (DIM == 2 || ni <= 64)) {
             static bool attr = false;
             if (!attr) {
-                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                CU(cudaFuncSetAttribute(k_coarse_cg_smem<DIM, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                 attr = true;
             }
-            if (nrows <= 16 && smem <= 40 * 1024)      // tiny grid (5^3, 9^2 ...): four warps, cheap block barriers
-                k_coarse_cg_smem<DIM, NF, 128><<<1, 128, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
-            else k_coarse_cg_smem<DIM, NF, 1024><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
+            k_coarse_cg_smem<DIM, NF><<<1, 1024, smem, s>>>(g, c->sten[l], x, b, op.count, op.tol, c->d_cg_iters);
             c->launch_counter++;
             CU(cudaGetLastError());
             return EVO_OK;
@@ -518,6 +516,23 @@ template <typename T, int DIM, int NF> int enqueue_op(evo_cycle *c, const evo_op
 
 
 // ---- fused runs of statements on small levels (evo_kernels_run.cuh) -------------------------------------------------
+constexpr size_t RUN_SMEM_BUDGET = 200 * 1024;
+template <int DIM> inline size_t run_compact_doubles(const Geom &g) { return ((size_t)g.n * g.n * (DIM == 3 ? g.n : 1) + 1) & ~(size_t)1; }
+// highest level of a shared-memory resident run (EVO_COARSE_FUSE = 5)
+template <int DIM, int NF> int run_resident_cap(const evo_problem *p)
+{
+    const int lo = p->desc.min_level;
+    size_t bytes = 4 * NF * run_compact_doubles<DIM>(p->geom[lo]) * sizeof(double);      // CG vectors
+    int cap = lo - 1;
+    for (int l = lo; l <= p->desc.max_level && l - lo < RUN_MAX_LEVELS; ++l) {
+        bytes += 3 * NF * run_compact_doubles<DIM>(p->geom[l]) * sizeof(double);
+        const long long ni = p->geom[l].n - 2;
+        if (bytes > RUN_SMEM_BUDGET || ni * ni * (DIM == 3 ? ni : 1) > 16 * 1024) break;
+        cap = l;
+    }
+    return cap;
+}
+
 // can this statement be part of a fused run?
 template <typename T, int DIM, int NF> bool run_eligible(const evo_cycle *c, const evo_op &op)
 {
@@ -530,15 +545,26 @@ template <typename T, int DIM, int NF> bool run_eligible(const evo_cycle *c, con
         if (l < p->desc.min_level || l > p->desc.max_level) return false;
         if (l - p->desc.min_level >= RUN_MAX_LEVELS) return false;
         // EVO_COARSE_FUSE: 1 (default) 2-D up to 129^2 / 3-D up to 17^3 in one CTA; 2 also 257^2 / 33^3 (thread-block
-        // cluster); 3 only up to 65^2 / 17^3
+        // cluster); 3 only up to 65^2 / 17^3; 4 only 3-D up to 17^3
         const int mode = option(OPT_COARSE_FUSE);
-        const int nmax = DIM == 2 ? (mode == 2 ? 257 : (mode == 3 ? 65 : 129)) : (mode == 2 ? 33 : 17);
-        if (p->geom[l].n > nmax) return false;
+        const int nmax = DIM == 2 ? (mode == 2 ? 257 : (mode == 3 ? 65 : (mode == 4 ? 0 : 129))) : (mode == 2 ? 33 : 17);
+        if (mode == 5) {
+            // shared-memory resident runs: the levels from the coarsest one up whose arrays (three per field: SOL, its
+            // [next] slot, RHS) fit into one CTA's shared memory together with the CG vectors
+            if (l > run_resident_cap<DIM, NF>(p)) return false;
+        } else if (p->geom[l].n > nmax) return false;
         switch (op.code) {
         case EVO_OP_ZERO: case EVO_OP_COPY: return true;
         case EVO_OP_RESIDUAL: return c->has_sten[l];
         case EVO_OP_RESTRICT: case EVO_OP_PROLONG_ADD: case EVO_OP_PROLONG_SET: return l > p->desc.min_level;
         case EVO_OP_RESIDUAL_RESTRICT: return l > p->desc.min_level && c->has_sten[l];
+        case EVO_OP_COARSE_SOLVE: {
+            // the shared-memory CG as a device function; one CTA must hold the level (<= 16 nodes per thread)
+            const int ni = p->geom[l].n - 2, nrows = ni * (DIM == 3 ? ni : 1);
+            const size_t vol = (size_t)p->geom[l].n * p->geom[l].n * (DIM == 3 ? p->geom[l].n : 1);
+            return l == p->desc.min_level && c->has_sten[l] && option(OPT_CG_GLOBAL) == 0 && 4 * NF * vol * sizeof(double) <= 40 * 1024 &&
+                   NF * nrows <= 512 && (long long)nrows * ni <= 16 * 1024;
+        }
         case EVO_OP_SMOOTH: {
             if (op.kind != EVO_KIND_LINEAR || !c->has_sten[l] || op.n_unknowns < 1 || op.n_unknowns > EVO_MAX_UNKNOWNS) return false;
             SmoothParams sp;
@@ -587,6 +613,7 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
             tab.sp = c->d_run_sp;
             tab.rp = c->d_run_rp;
             long long nodes_max = 1;
+            size_t cg_smem = 0;      // > 0: the run holds a coarse-grid solve (one CTA, dynamic shared memory for the CG vectors)
             for (int q = 0; q < m; ++q) {
                 const evo_op &op = ops[i0 + q];
                 const int l = op.level;
@@ -627,6 +654,13 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
                         r.b[f] = lv.buf[op.code == EVO_OP_PROLONG_ADD ? EVO_BUF_SOL : op.dst][f];
                     }
                     break;
+                case EVO_OP_COARSE_SOLVE:
+                    for (int f = 0; f < NF; ++f) { r.a[f] = lv.buf[EVO_BUF_SOL][f]; r.b[f] = lv.buf[EVO_BUF_RHS][f]; }
+                    r.c[0] = c->d_cg_iters;
+                    r.reps = op.count;
+                    r.omega = op.tol;
+                    cg_smem = std::max(cg_smem, 4 * NF * (size_t)g.n * g.n * (DIM == 3 ? g.n : 1) * sizeof(double));
+                    break;
                 case EVO_OP_SMOOTH: {
                     const ptrdiff_t idx = &op - c->ops.data();
                     if (idx < 0 || idx >= (ptrdiff_t)c->ops.size()) return fail(EVO_ERR_INVALID, "fused runs take statements of the cycle");
@@ -652,15 +686,63 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
             int numax = 1;
             for (int q = 0; q < m; ++q)
                 if (tab.op[q].code == EVO_OP_SMOOTH) numax = std::max(numax, tab.op[q].nu);
+            // EVO_COARSE_FUSE = 5: every field array the run touches lives in shared memory for the whole launch
+            size_t run_smem = cg_smem;
+            if (option(OPT_COARSE_FUSE) == 5) {
+                int n_stage = 0, off = 0;
+                bool fits = true;
+                auto stage = [&](void *&ptr, int li) {        // replace a device pointer by its shared-memory tag
+                    if (!ptr || !fits) return;
+                    for (int e = 0; e < n_stage; ++e)
+                        if (tab.stage[e].ptr == ptr && tab.stage[e].li == li) { ptr = run_tag(tab.stage[e].off); return; }
+                    if (n_stage == RUN_MAX_STAGE) { fits = false; return; }
+                    tab.stage[n_stage] = RunStage{ptr, li, off};
+                    ptr = run_tag(off);
+                    off += (int)run_compact_doubles<DIM>(tab.geom[li]);
+                    ++n_stage;
+                };
+                RunTable saved = tab;
+                for (int q = 0; q < m && fits; ++q) {
+                    RunOp &r = tab.op[q];
+                    for (int f = 0; f < NF; ++f) {
+                        switch (r.code) {
+                        case EVO_OP_ZERO: stage(r.b[f], r.li); break;
+                        case EVO_OP_COPY: stage(r.a[f], r.li); stage(r.b[f], r.li); break;
+                        case EVO_OP_RESIDUAL: case EVO_OP_SMOOTH: stage(r.a[f], r.li); stage(r.b[f], r.li); stage(r.c[f], r.li); break;
+                        case EVO_OP_RESTRICT: stage(r.a[f], r.li); stage(r.b[f], r.lj); break;
+                        case EVO_OP_RESIDUAL_RESTRICT: stage(r.a[f], r.li); stage(r.c[f], r.li); stage(r.b[f], r.lj); break;
+                        case EVO_OP_PROLONG_ADD: case EVO_OP_PROLONG_SET: stage(r.a[f], r.lj); stage(r.b[f], r.li); break;
+                        case EVO_OP_COARSE_SOLVE: stage(r.a[f], r.li); stage(r.b[f], r.li); break;
+                        default: fits = false; break;
+                        }
+                    }
+                }
+                const size_t bytes = (size_t)off * sizeof(double) + cg_smem;
+                if (fits && bytes <= RUN_SMEM_BUDGET && nodes_max <= 16 * 1024) {
+                    tab.n_stage = n_stage;
+                    tab.cg_off = off;
+                    run_smem = bytes;
+                    for (int li = 0; li < RUN_MAX_LEVELS; ++li) {          // compact geometry: pitch = n
+                        Geom &g = tab.geom[li];
+                        if (g.n == 0) continue;
+                        g.pitch = g.n;
+                        g.plane = (long long)g.n * g.n;
+                        g.total = g.plane * (DIM == 3 ? g.n : 1);
+                    }
+                } else {
+                    tab = saved;       // does not fit: the run works on device memory as before
+                }
+            }
             // one CTA (block barriers) up to 16 nodes per thread, else a cluster of up to 8 CTAs
             const int tmax = numax <= 2 ? 1024 : 512;
             int ctas = 1;
-            while (ctas < 8 && nodes_max > (long long)ctas * tmax * 16) ctas *= 2;
+            while (cg_smem == 0 && tab.n_stage == 0 && ctas < 8 && nodes_max > (long long)ctas * tmax * 16) ctas *= 2;
             const int threads = nodes_max >= tmax ? tmax : (int)((nodes_max + 31) / 32 * 32);
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(ctas);
             cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = run_smem;
             cfg.stream = s;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -672,6 +754,13 @@ template <typename T, int DIM, int NF> int enqueue_run(evo_cycle *c, const evo_o
                 else if (numax <= 4) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 4, true>, tab));
                 else CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 8, true>, tab));
             } else {
+                static bool attr = false;
+                if (!attr) {
+                    CU(cudaFuncSetAttribute(k_run<DIM, NF, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM_BUDGET));
+                    CU(cudaFuncSetAttribute(k_run<DIM, NF, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM_BUDGET));
+                    CU(cudaFuncSetAttribute(k_run<DIM, NF, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM_BUDGET));
+                    attr = true;
+                }
                 if (numax <= 2) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 2, false>, tab));
                 else if (numax <= 4) CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 4, false>, tab));
                 else CU(cudaLaunchKernelEx(&cfg, k_run<DIM, NF, 8, false>, tab));

@@ -734,13 +734,14 @@ __global__ void __launch_bounds__(1024) k_coarse_cg(const Geom g, const __grid_c
 // Shared-memory resident CG for coarsest levels that fit (4 vectors x fields x n^d doubles): the
 // global-memory version above spends ~7 us per iteration on dependent global round trips; here a CG
 // iteration is 5 block barriers.  Same arithmetic and the same canonical reductions -> bit-identical.
-// NT threads: 1024, or 128 for grids with at most 16 rows (block barriers among 4 warps instead of 32: a 5^3 solve takes
-// a third of the time, and it runs 128 times per W-cycle on 513^3)
-template <int DIM, int NF, int NT>
-__global__ void __launch_bounds__(NT) k_coarse_cg_smem(const Geom g, const __grid_constant__ OpSten st, Fields<double> xg,
-                                                         Fields<double> bg, int max_it, double tol, int *iters_out)
+// Device function: the whole CTA (any multiple of 32 threads) calls it -- from k_coarse_cg_smem and from the fused-run
+// interpreter (evo_kernels_run.cuh).  (A 4-warp launch for the 5^3 grid was measured SLOWER than 32 warps: the table-driven
+// A p of a row, not the block barriers, is the latency of an iteration.)
+template <int DIM, int NF>
+__device__ __forceinline__ void coarse_cg_smem(const Geom &g, const OpSten &st, Fields<double> xg, Fields<double> bg, int max_it,
+                                               double tol, int *iters_out, double *sm)
 {
-    extern __shared__ double sm[];
+    const int NT = (int)blockDim.x;
     __shared__ double rowsum[1024];
     __shared__ double planes[64];
     const int n = g.n, ni = n - 2, nzi = DIM == 3 ? ni : 1;
@@ -856,6 +857,14 @@ __global__ void __launch_bounds__(NT) k_coarse_cg_smem(const Geom g, const __gri
             for (int xx = 1 + lane; xx <= ni; xx += 32) xg.p[i][node_index(g, xx, y, z)] = x[i * vol + (z * n + y) * n + xx];
         }
     if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
+template <int DIM, int NF>
+__global__ void __launch_bounds__(1024) k_coarse_cg_smem(const Geom g, const __grid_constant__ OpSten st, Fields<double> xg,
+                                                         Fields<double> bg, int max_it, double tol, int *iters_out)
+{
+    extern __shared__ double cg_sm[];
+    coarse_cg_smem<DIM, NF>(g, st, xg, bg, max_it, tol, iters_out, cg_sm);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -146,16 +146,19 @@ def test_model_based_mode_through_the_drop_in(cuda_backend, oracle_mod):
 
 
 # ---- fused runs of statements on the small levels (evo_kernels_run.cuh) -------------------------------------------
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 @pytest.mark.parametrize("name", ["p2", "el", "p3"])
-def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name):
-    """EVO_COARSE_FUSE: maximal runs of statements on small levels are interpreted by one cluster kernel; the residual
-    history must be bit-identical to one launch per statement (and to the oracle), with far fewer launches."""
+def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name, mode):
+    """EVO_COARSE_FUSE: maximal runs of statements on small levels -- coarse-grid CG included -- are interpreted by one
+    kernel (one CTA or a cluster); the residual history must be bit-identical to one launch per statement (and to the
+    oracle), with fewer launches.  Modes: 1 one CTA, 2 clusters on the larger levels, 3 smallest levels, 5 field arrays resident in shared memory."""
     import random
     from evostencils_b200 import lowering, tree
     prob = {"p2": problems.Poisson2D(3, 8), "el": problems.LinearElasticity2D(3, 7), "p3": problems.Poisson3D(2, 5)}[name]
     rng = random.Random(5)
-    progs = [cycles.default_solver_cycle(prob), lowering.optimise(cycles.default_solver_cycle(prob))]
-    for _ in range(6):
+    progs = [cycles.default_solver_cycle(prob), lowering.optimise(cycles.default_solver_cycle(prob)),
+             lowering.optimise(cycles.w_cycle(prob, 2, 1, 1.1, True))]
+    for _ in range(5):
         s = tree.random_individual(prob, rng, maximum_local_system_size=4)
         progs.append(lowering.optimise(lowering.lower_cycle(tree.build_tree(prob, s), prob.min_level, prob.max_level, prob.n_fields,
                                                             prob.dim, cgs_max_iters=prob.settings.cgs_max_iters,
@@ -169,7 +172,7 @@ def test_fused_runs_equal_single_launches(cuda_backend, oracle_mod, option, name
     for prog in progs:
         option("EVO_COARSE_FUSE", 0)
         a = dev.build(prog).solve(st.tol, st.max_iters, 1)
-        option("EVO_COARSE_FUSE", 1)
+        option("EVO_COARSE_FUSE", mode)
         b = dev.build(prog).solve(st.tol, st.max_iters, 1)
         c = dev.build(prog).solve(st.tol, st.max_iters, 1, ol.SOLVE_NO_GRAPH)
         o = ref.build(prog).solve(st.tol, st.max_iters, 1)
