@@ -26,12 +26,38 @@ from . import oplist as ol
 
 # ------------------------------------------------------------------------------------------------
 # duck typing helpers
-def _names(obj) -> Tuple[str, ...]:
-    return tuple(c.__name__ for c in type(obj).__mro__)
+_NAMES: Dict[type, frozenset] = {}
+
+
+def _names(obj) -> frozenset:
+    t = type(obj)
+    names = _NAMES.get(t)
+    if names is None:
+        names = _NAMES[t] = frozenset(c.__name__ for c in t.__mro__)
+    return names
 
 
 def _is(obj, name: str) -> bool:
     return name in _names(obj)
+
+
+# Results that depend only on an operator OBJECT (its stencil tables, the statements of a smoother built on it) are
+# kept per object: the terminals of a grammar are shared by all individuals of a run (the reference builds them once,
+# grammar/multigrid.py:74-137; tree.py caches them per problem), so a generation lowers each of them once.  The cache
+# holds a reference to the object, which keeps its id() unique.
+_PER_OBJECT: Dict[Tuple, Tuple[object, object]] = {}
+
+
+def _per_object(kind: str, obj, extra, compute):
+    key = (kind, id(obj), extra)
+    hit = _PER_OBJECT.get(key)
+    if hit is not None and hit[0] is obj:
+        return hit[1]
+    if len(_PER_OBJECT) > 4096:        # individuals built from uncached terminals: do not grow without bound
+        _PER_OBJECT.clear()
+    value = compute()
+    _PER_OBJECT[key] = (obj, value)
+    return value
 
 
 def _is_system_approximation(obj) -> bool:
@@ -78,7 +104,15 @@ def _constant_entries(stencil) -> List[Tuple[Tuple[int, ...], complex]]:
 
 def operator_table(system_operator, n_fields: int) -> np.ndarray:
     """Coefficient table [nf, nf, 27] of a system operator (``system.Operator`` of stencil expressions,
-    built by grammar/multigrid.py:74-137 from the problem's equations)."""
+    built by grammar/multigrid.py:74-137 from the problem's equations); read-only, cached per operator object."""
+    def compute():
+        table = _operator_table(system_operator, n_fields)
+        table.setflags(write=False)
+        return table
+    return _per_object("A", system_operator, n_fields, compute)
+
+
+def _operator_table(system_operator, n_fields: int) -> np.ndarray:
     table = np.zeros((n_fields, n_fields, ol.STENCIL_POINTS), dtype=np.complex128)
     for i, row in enumerate(system_operator.entries):
         for j, entry in enumerate(row):
@@ -92,7 +126,15 @@ def operator_table(system_operator, n_fields: int) -> np.ndarray:
 
 
 def transfer_table(intergrid_system_operator) -> np.ndarray:
-    """Weights (3^d table) of the restriction / prolongation of field 0 (all fields share it)."""
+    """Weights (3^d table) of the restriction / prolongation of field 0 (all fields share it); read-only, cached."""
+    def compute():
+        w = _transfer_table(intergrid_system_operator)
+        w.setflags(write=False)
+        return w
+    return _per_object("T", intergrid_system_operator, None, compute)
+
+
+def _transfer_table(intergrid_system_operator) -> np.ndarray:
     entry = intergrid_system_operator.entries[0][0]
     w = np.zeros(ol.STENCIL_POINTS)
     for offset, value in _constant_entries(entry.generate_stencil()):
@@ -171,6 +213,18 @@ def _smoother_blocks(smoothing_operator, system_operator, n_fields: int, dim: in
 
 
 def local_system_statements(smoothing_operator, system_operator, n_fields: int, dim: int):
+    """Cached per smoother: Diagonal / ElementwiseDiagonal are thin wrappers created per individual around the shared
+    system operator (key: wrapper type + operand); block splittings are shared objects themselves (tree.py)."""
+    tname = type(smoothing_operator).__name__
+    if tname in ("Diagonal", "ElementwiseDiagonal"):
+        anchor, extra = smoothing_operator.operand, (tname, n_fields, dim)
+    else:
+        anchor, extra = smoothing_operator, (tname, n_fields, dim)
+    return _per_object("S", anchor, extra,
+                       lambda: _local_system_statements(smoothing_operator, system_operator, n_fields, dim))
+
+
+def _local_system_statements(smoothing_operator, system_operator, n_fields: int, dim: int):
     """Statements ``[(unknowns, ...)]`` a smoother expands to, in emission order.
 
     Mirrors exastencils.py:769-822: the keys of ``obtain_sympy_expression_for_local_system`` are

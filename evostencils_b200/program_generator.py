@@ -71,6 +71,37 @@ def _problem_from_paths(settings_path: Optional[str], knowledge_path: Optional[s
     return prob
 
 
+class _FastGilSwitch:
+    """While trees are lowered by background threads (pure Python) the submitting thread returns from a C call every
+    few hundred microseconds and must get the interpreter lock back quickly: with the default switch interval of 5 ms it
+    would wait up to 5 ms per call and the device would run dry.  Process-wide setting, reference counted."""
+    _lock = None
+    _users = 0
+    _saved = None
+
+    def __enter__(self):
+        import sys
+        import threading
+        cls = _FastGilSwitch
+        if cls._lock is None:
+            cls._lock = threading.Lock()
+        with cls._lock:
+            if cls._users == 0:
+                cls._saved = sys.getswitchinterval()
+                sys.setswitchinterval(min(cls._saved, 2e-4))
+            cls._users += 1
+        return self
+
+    def __exit__(self, *exc):
+        import sys
+        cls = _FastGilSwitch
+        with cls._lock:
+            cls._users -= 1
+            if cls._users == 0 and cls._saved is not None:
+                sys.setswitchinterval(cls._saved)
+        return False
+
+
 class _LoweredStream:
     """Programs of a list of trees, lowered by a background thread in order (len() and iteration like a list; a tree
     the lowering rejects yields None)."""
@@ -460,7 +491,8 @@ class B200ProgramGenerator:
         if programs is not None:
             progs = [self._finalise(p) for p in programs]
         else:
-            progs = _LoweredStream(self, list(expressions), min_level)
+            # a sized iterable is consumed lazily by the lowering thread (e.g. trees built on the fly from grammar strings)
+            progs = _LoweredStream(self, expressions if hasattr(expressions, "__len__") else list(expressions), min_level)
         sentinel = (infinity, infinity, infinity)
         if dev.problem.kind == ol.PROBLEM_HELMHOLTZ:
             for p in progs:
@@ -507,6 +539,9 @@ class B200ProgramGenerator:
                     else:
                         c.close()
 
+        gil = _FastGilSwitch() if programs is None else None
+        if gil:
+            gil.__enter__()
         try:
             for j, p in enumerate(progs):
                 if p is None:
@@ -543,6 +578,8 @@ class B200ProgramGenerator:
             finish(done)
             done = []
         finally:
+            if gil:
+                gil.__exit__(None, None, None)
             for _, c in window:
                 c.close()
             for _, c, _o in done:

@@ -235,7 +235,28 @@ def _grids(problem: Problem, level: int) -> List[Grid]:
     return [Grid((n,) * problem.dim, (1.0 / n,) * problem.dim, level) for _ in range(problem.n_fields)]
 
 
+def _problem_cache(problem: Problem, key, factory):
+    """Immutable terminals (operators, inter-grid operators, block splittings) are built once per problem object and
+    shared by every context / individual -- like the reference, whose terminals live in the primitive set of a run
+    (grammar/multigrid.py:74-137).  Only the nodes the productions MUTATE (approximations, cycles) are fresh per context."""
+    try:
+        cache = problem.__dict__.setdefault("_tree_terminals", {})
+        # run-time parameters that enter the operators (wave number of the k / 2k / 4k runs, user parameters)
+        params = getattr(problem, "parameters", None)
+        key = key + (getattr(problem, "wave_number", None), tuple(sorted(params.items())) if isinstance(params, dict) else None)
+    except (AttributeError, TypeError):
+        return factory()
+    hit = cache.get(key)
+    if hit is None:
+        hit = cache[key] = factory()
+    return hit
+
+
 def system_operator(problem: Problem, level: int, name: str) -> Operator:
+    return _problem_cache(problem, ("A", level, name), lambda: _system_operator(problem, level, name))
+
+
+def _system_operator(problem: Problem, level: int, name: str) -> Operator:
     table = problem.operator(level)
     grids = _grids(problem, level)
     rows = []
@@ -250,6 +271,10 @@ def system_operator(problem: Problem, level: int, name: str) -> Operator:
 
 
 def _transfer(problem: Problem, level: int, kind: str, name: str):
+    return _problem_cache(problem, ("T", level, kind, name), lambda: _make_transfer(problem, level, kind, name))
+
+
+def _make_transfer(problem: Problem, level: int, kind: str, name: str):
     fine, coarse = _grids(problem, level), _grids(problem, level - 1)
     w = problem.restrict_weights() if kind == "R" else problem.prolong_weights()
     ent = [(ol.stencil_offset(p, problem.dim), w[p]) for p in range(ol.STENCIL_POINTS) if w[p] != 0]
@@ -352,7 +377,10 @@ def grammar_context(problem: Problem, min_level: Optional[int] = None, max_level
             return smoothing(weight_index, partitioning, ElementwiseDiagonal, cycle)
 
         def collective_block_jacobi(weight_index, block_shape, cycle):
-            return smoothing(weight_index, Single, lambda op: block_jacobi_operator(op, block_shape, problem.dim), cycle)
+            shape_key = tuple(tuple(int(v) for v in sh) for sh in block_shape)
+            return smoothing(weight_index, Single,
+                             lambda op: _problem_cache(problem, ("B", id(op), shape_key),
+                                                       lambda: block_jacobi_operator(op, block_shape, problem.dim)), cycle)
 
         def restrict(restriction, cycle):
             if fas:   # coarse rhs = R r + A_c (R u): grammar/multigrid.py:287-293
