@@ -1157,15 +1157,35 @@ extern "C" int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, 
     if (op->code == EVO_OP_SMOOTH && op->mode == EVO_SMOOTH_JACOBI && !c->lv[op->level].slot[0])
         return fail(EVO_ERR_INVALID, "the cycle was built without a jacobi slot on level %d", op->level);
     cudaStream_t s = c->stream;
-    EV(dispatch_op(c, *op, s));  // warm-up
+    EV(dispatch_op(c, *op, s));  // warm-up (lazy attribute settings, first-touch of the kernels)
     CU(cudaStreamSynchronize(s));
+    // the statement `repeat` times as kernel nodes of ONE graph: what it costs inside a solver graph (an eager loop of
+    // tiny launches would measure the host's launch rate instead)
     c->launch_counter = 0;
-    CU(cudaEventRecord(c->ev0, s));
-    for (int r = 0; r < repeat; ++r) EV(dispatch_op(c, *op, s));
-    CU(cudaEventRecord(c->ev1, s));
-    CU(cudaStreamSynchronize(s));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int rc2 = EVO_OK;
+    for (int r = 0; r < repeat && rc2 == EVO_OK; ++r) rc2 = dispatch_op(c, *op, s);
+    cudaError_t ce = cudaStreamEndCapture(s, &g);
+    if (rc2 != EVO_OK || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc2 != EVO_OK) return rc2;
+        return fail(EVO_ERR_CUDA, "profile capture: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&ge, g, 0);
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ce == cudaSuccess) ce = cudaGraphLaunch(ge, s);          // warm-up of the graph itself
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce == cudaSuccess) ce = cudaEventRecord(c->ev0, s);
+    if (ce == cudaSuccess) ce = cudaGraphLaunch(ge, s);
+    if (ce == cudaSuccess) ce = cudaEventRecord(c->ev1, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    if (ge) cudaGraphExecDestroy(ge);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(EVO_ERR_CUDA, "profile graph: %s", cudaGetErrorString(ce));
     if (ms_per_exec) *ms_per_exec = (double)ms / repeat;
     if (launches_per_exec) *launches_per_exec = c->launch_counter / repeat;
     // restore the canonical jacobi slot assignment
