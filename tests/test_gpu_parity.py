@@ -262,8 +262,10 @@ def test_batch_solve_matches_single(cuda_backend, oracle_mod):
 
 @pytest.mark.parametrize("level,sweeps", [(5, 1), (5, 2), (6, 3), (7, 2), (7, 1)])
 def test_poisson3d_streaming_rbgs_bit_exact(cuda_backend, oracle_mod, level, sweeps):
-    """TMA-staged streaming RB-GS kernel (colours and up to 2 sweeps fused, z-slabs, XY tiles with halo
-    recomputation) against the plain colour-by-colour loops of the oracle: bit-identical."""
+    """The default 3-D RB-GS path (register-carried pair-column kernel k3_rbgs_col: both colours of ONE sweep per launch,
+    z-slabs, XY tiles with halo recomputation; consecutive sweeps are separate launches by default -- the two-sweeps-per-
+    launch kernel is covered by tests/test_gpu_variants.py::test_rbgs_two_sweeps_per_launch) against the plain
+    colour-by-colour loops of the oracle: bit-identical."""
     prob = problems.Poisson3D(level - 1, level)
     z = (0, 0, 0)
     # start from a non-trivial state: one Jacobi sweep first, then `sweeps` RB-GS sweeps, then the residual
