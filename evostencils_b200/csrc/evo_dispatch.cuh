@@ -210,8 +210,11 @@ template <typename T, int DIM, int NF> struct Launch {
                         return fail(EVO_ERR_UNSUPPORTED, "coloured block smoothers are not generated by the grammar");
                     }
                 } else if ((long long)(g.n - 2) * (g.n - 2) * (DIM == 3 ? g.n - 2 : 1) <= SMALL_GRID_NODES && !slab_level(c->p, l)) {
-                    // tiny grid: every remaining sweep and both colours in one launch
-                    k_smooth_rb_small<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs, reps - rep);
+                    // tiny grid: every remaining sweep and both colours in one launch (5-/7-point star, pointwise: on
+                    // shared memory with straight-line arithmetic; else the generic local_solve)
+                    const bool pointwise = NU == 1 && sp.field[0] == 0 && !sp.off[0][0] && !sp.off[0][1] && !sp.off[0][2];
+                    if (!(pointwise && small::try_rb_small<T, DIM, NF>(g, c->sten[l], u, rhs, sp.omega, reps - rep, s)))
+                        k_smooth_rb_small<T, DIM, NF, NU><<<1, 1024, 0, s>>>(g, c->sten[l], sp, u, rhs, reps - rep);
                     c->launch_counter++;
                     rep = reps;
                 } else {

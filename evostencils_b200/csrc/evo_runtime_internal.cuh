@@ -16,6 +16,7 @@
 #include "evo_kernels_rbcol.cuh"
 #include "evo_kernels_rrcol.cuh"
 #include "evo_kernels_warp2d.cuh"
+#include "evo_kernels_small.cuh"
 #include "evo_kernels_fas.cuh"
 #include "evo_kernels_helm.cuh"
 
