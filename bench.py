@@ -78,10 +78,31 @@ def make_workload(name: str, fuse: bool = True):
         raise SystemExit(f"unknown workload {name}")
     s_ = prob.settings
     prog = cycles.w_cycle(prob, s_.num_pre, s_.num_post, s_.damping, s_.red_black) if wcycle else cycles.default_solver_cycle(prob)
+    from evostencils_b200 import lowering
+    expr = None if wcycle else workload_tree(name, prob)
+    if expr is not None:
+        # the cycle as the grammar individual Optimizer hands over, lowered like the drop-in lowers it: the op list of the
+        # device-resident run, the CPU arm and the plugin call are then the same one (the grammar's weight grid
+        # linspace(0.1, 1.9, 37) holds 0.9999999999999999 for the coarse-grid correction, not 1.0)
+        prog = lowering.lower_cycle(expr, prob.min_level, prob.max_level, prob.n_fields, prob.dim, cgs_max_iters=s_.cgs_max_iters,
+                                    cgs_tol=s_.cgs_tol, default_restrict=prob.restrict_weights(), default_prolong=prob.prolong_weights())
     if fuse:
-        from evostencils_b200 import lowering
         prog = lowering.optimise(prog)
     return prob, prog
+
+
+def make_workload_cycle(name: str, prob):
+    """The workload's cycle for another level range of the same problem (CPU samples on coarser hierarchies)."""
+    from evostencils_b200 import lowering
+    s_ = prob.settings
+    if name.endswith("_w"):
+        return lowering.optimise(cycles.w_cycle(prob, s_.num_pre, s_.num_post, s_.damping, s_.red_black))
+    expr = workload_tree(name, prob)
+    if expr is None:
+        return cycles.default_solver_cycle(prob)
+    return lowering.optimise(lowering.lower_cycle(expr, prob.min_level, prob.max_level, prob.n_fields, prob.dim,
+                                                  cgs_max_iters=s_.cgs_max_iters, cgs_tol=s_.cgs_tol,
+                                                  default_restrict=prob.restrict_weights(), default_prolong=prob.prolong_weights()))
 
 
 def workload_tree(name: str, prob):
@@ -207,7 +228,7 @@ def _cpu_threads(threads=None):
     return orc.num_threads()
 
 
-def cpu_grid_sample(workload: str, threads=None, budget_s: float = 12.0):
+def cpu_grid_sample(workload: str, threads=None, budget_s: float = 25.0):
     """Oracle on the grid workload: ONE COMPLETE SOLVE (initial residual, V-cycles to 1e-12) at the finest level whose
     solve fits the time budget, scaled to the workload's DOF count.  Multigrid cost is linear in the DOFs and the
     iteration count is h-independent (the parity tests assert equal counts), so the only extrapolation is the DOF
@@ -222,7 +243,7 @@ def cpu_grid_sample(workload: str, threads=None, budget_s: float = 12.0):
     # probe: one full solve two levels below, predicts the cost of the finer ones (x 2^dim per level)
     probe_level = max(prob.min_level + 1, prob.max_level - 2)
     probe = prob.with_levels(prob.min_level, probe_level)
-    oc = orc.OracleProblem(probe).build(cycles.default_solver_cycle(probe))
+    oc = orc.OracleProblem(probe).build(make_workload_cycle(workload, probe))
     oc.solve(probe.settings.tol, probe.settings.max_iters, 1)
     t0 = time.perf_counter()
     ref = oc.solve(probe.settings.tol, probe.settings.max_iters, 1)
@@ -233,7 +254,7 @@ def cpu_grid_sample(workload: str, threads=None, budget_s: float = 12.0):
         predicted = t_probe * (2 ** prob.dim) ** (cand - probe_level)
         if need < 0.4 * avail and need < (24 << 30) and predicted <= budget_s:
             sp = prob.with_levels(prob.min_level, cand)
-            oc = orc.OracleProblem(sp).build(cycles.default_solver_cycle(sp))
+            oc = orc.OracleProblem(sp).build(make_workload_cycle(workload, sp))
             t0 = time.perf_counter()
             ref = oc.solve(sp.settings.tol, sp.settings.max_iters, 1)
             t_solve, level, its = time.perf_counter() - t0, cand, ref.iterations
