@@ -237,8 +237,9 @@ int evo_cycle_vecsum_async(evo_cycle *c, const double *device_vals, int m);
 int evo_cycle_read_sum(evo_cycle *c, double *out);
 int evo_cycle_swap_slots(evo_cycle *c, int level);
 
-/* measurement hook (bench.py roofline): launch the kernels of ONE statement `repeat` times on the
- * cycle's stream, bracketed by CUDA events; returns the average milliseconds per execution and the
+/* measurement hook (bench.py roofline, measured-cost surrogate): the kernels of ONE statement `repeat`
+ * times as nodes of one CUDA graph on the cycle's stream (what the statement costs inside the solver
+ * graph), bracketed by CUDA events; returns the average milliseconds per execution and the
  * number of kernel launches one execution makes.  The reference's counterpart is the per-function
  * timer output of the generated binary (printAllTimers, Helmholtz/...exa4:13-19).                 */
 int evo_cycle_profile_op(evo_cycle *c, const evo_op *op, int repeat, double *ms_per_exec, int64_t *launches_per_exec);
