@@ -726,7 +726,7 @@ static int enqueue_cycle_ops(evo_cycle *c, cudaStream_t s)
             // `RHS@(l-1) = R (f - A u)` followed by `SOL@(l-1) = 0`: one kernel writes both coarse fields
             if (op.code == EVO_OP_RESIDUAL_RESTRICT && t + 1 < n && c->ops[t + 1].code == EVO_OP_ZERO && c->ops[t + 1].level == op.level - 1 &&
                 c->ops[t + 1].dst == EVO_BUF_SOL && d.kind == EVO_PROBLEM_LINEAR && d.scalar_words == 1 && c->zc_lo < 0 &&
-                option(OPT_NO_ZERO_FUSE) == 0) {
+                !c->coarse_sol_written && option(OPT_NO_ZERO_FUSE) == 0) {
                 c->fuse_zero = true;
                 const int rc = dispatch_op(c, op, s);
                 const bool folded = !c->fuse_zero;
@@ -995,6 +995,13 @@ extern "C" int evo_cycle_set_field(evo_cycle *c, int level, int buf, int field, 
     if (n_doubles != (size_t)g.n * g.n * (g.dim == 3 ? g.n : 1) * c->p->words) return fail(EVO_ERR_INVALID, "field size mismatch");
     CU(cudaSetDevice(c->p->desc.device));
     EV(copy_field(g, c->p->words, dev, host, nullptr, c->stream));
+    if (buf == EVO_BUF_SOL && level < c->p->desc.max_level && !c->coarse_sol_written) {
+        // the caller may have put values on the boundary layer of a correction level: from now on `SOL = 0` clears the
+        // whole array again (solver graphs captured before are rebuilt)
+        c->coarse_sol_written = true;
+        if (c->exec) { cudaGraphExecDestroy(c->exec); c->exec = nullptr; }
+        if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+    }
     if (buf == EVO_BUF_SOL && c->lv[level].slot[field])  // keep the boundary invariant of the jacobi slot
         EV(copy_field(g, c->p->words, c->lv[level].slot[field], host, nullptr, c->stream));
     return EVO_OK;

@@ -103,6 +103,8 @@ struct evo_cycle {
     int graph_max_iters;
     int64_t kernels_per_cycle, kernels_prologue;
     int64_t launch_counter;  // counts kernel launches while enqueueing
+    bool coarse_sol_written = false;   // evo_cycle_set_field wrote SOL of a correction level: its boundary layer may be non-zero,
+                                       // `SOL = 0` stays a full memset from then on (no folding into the restriction)
     bool fuse_zero = false;  // set around a restriction whose next statement zeroes SOL of the coarse level: a kernel that
                              // also stores those zeros clears the flag (the memset node is then skipped)
     // While a solver-graph body is captured: the final reduction of the convergence norm also does the outer loop's

@@ -309,3 +309,24 @@ def test_tiny_grid_kernels_bit_exact(cuda_backend, oracle_mod, name, lo, hi):
         gc.apply(1)
         oc.apply(1)
         _equal(gc, oc, prob, range(prob.min_level, prob.max_level + 1), (ol.BUF_SOL, ol.BUF_RHS))
+
+
+def test_zero_fold_is_dropped_after_a_user_write_to_a_coarse_solution(cuda_backend, oracle_mod):
+    """The folded `SOL@(l-1) = 0` clears the inner nodes only (the boundary layer of a correction level is never written
+    by a kernel).  After evo_cycle_set_field put values on that boundary layer the statement must clear the whole array
+    again, like the oracle's memset -- also in a solver graph that was captured before the write."""
+    prob = problems.Poisson2D(3, 6)
+    prog = lowering.optimise(cycles.v_cycle(prob, 2, 1, 1.1, True))
+    gc = cuda_backend.DeviceProblem(prob).build(prog)
+    oc = oracle_mod.OracleProblem(prob).build(prog)
+    a = gc.solve(1e-30, 2, 1)
+    b = oc.solve(1e-30, 2, 1)
+    assert np.array_equal(a.residuals, b.residuals)
+    rng = np.random.default_rng(3)
+    junk = rng.standard_normal(gc.get_field(4, ol.BUF_SOL, 0).shape)      # non-zero boundary layer included
+    for c in (gc, oc):
+        c.set_field(4, ol.BUF_SOL, 0, junk)
+    for _ in range(2):
+        gc.apply(1)
+        oc.apply(1)
+        _equal(gc, oc, prob, range(prob.min_level, prob.max_level + 1), (ol.BUF_SOL, ol.BUF_RHS))
