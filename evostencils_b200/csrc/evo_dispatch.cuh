@@ -187,11 +187,14 @@ template <typename T, int DIM, int NF> struct Launch {
                             if (canonical && !disabled && !no_pipe && k > 0 && dense_ok) {
                                 static bool attr_p = false;
                                 if (!attr_p) {
-                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                    CU(cudaFuncSetAttribute(k2_smooth_rowseq_pipe<NF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                                     attr_p = true;
                                 }
                                 const size_t sm2 = (size_t)(4 * k + 3) * 2 * NF * g.pitch * sizeof(double);
-                                k2_smooth_rowseq_pipe<NF><<<1, ROWSEQ_NT, sm2, s>>>(g, c->sten[l], dn, sp.omega, u, rhs, k);
+                                if (dense9_pattern<NF>(dn) == 1)      // star / corner blocks: static sparsity (half the dependent adds)
+                                    k2_smooth_rowseq_pipe<NF, 1><<<1, ROWSEQ_NT, sm2, s>>>(g, c->sten[l], dn, sp.omega, u, rhs, k);
+                                else k2_smooth_rowseq_pipe<NF, 0><<<1, ROWSEQ_NT, sm2, s>>>(g, c->sten[l], dn, sp.omega, u, rhs, k);
                                 done = true;
                                 rep += k - 1;
                             } else if (canonical && !disabled && smem <= 200 * 1024) {
@@ -449,7 +452,9 @@ template <int DIM, int NF> static int coarse_cg(evo_cycle *c, const evo_op &op, 
                     }
                 }
             if (dense_ok) {
-                k2_coarse_cg_reg<NF><<<1, 1024, NF * vol * sizeof(double), s>>>(g, dn, x, b, op.count, op.tol, c->d_cg_iters);
+                if (dense9_pattern<NF>(dn) == 1)
+                    k2_coarse_cg_reg<NF, 1><<<1, 1024, NF * vol * sizeof(double), s>>>(g, dn, x, b, op.count, op.tol, c->d_cg_iters);
+                else k2_coarse_cg_reg<NF, 0><<<1, 1024, NF * vol * sizeof(double), s>>>(g, dn, x, b, op.count, op.tol, c->d_cg_iters);
                 c->launch_counter++;
                 CU(cudaGetLastError());
                 return EVO_OK;

@@ -960,12 +960,29 @@ __global__ void __launch_bounds__(1024) k2_smooth_rowseq_win(const Geom g, const
 // dense 3x3 coefficient tables of the NF x NF blocks (table order p = (dy+1)*3 + (dx+1)); zero = no entry
 template <int NF> struct Dense9 { double w[NF][NF][9]; };
 
+// Sparsity pattern known at compile time (PAT = 1): 5-point star on the diagonal blocks, the four corners on the
+// off-diagonal blocks -- the 2-D Poisson operator and the linear-elasticity system (dxx/dyy + the mixed dxy terms).  With the
+// generic run-time masks (PAT = 0) the compiler turns "skip the absent entry" into a select, so every table entry costs a
+// dependent fp64 add (~50 cycles each on the latency-bound kernels below); the static pattern halves those chains.
+__host__ __device__ constexpr bool dense9_star_corner(int a, int j, int p)
+{
+    return a == j ? (p == 1 || p == 3 || p == 4 || p == 5 || p == 7) : (p == 0 || p == 2 || p == 6 || p == 8);
+}
+template <int NF> inline int dense9_pattern(const Dense9<NF> &dn)
+{
+    for (int a = 0; a < NF; ++a)
+        for (int j = 0; j < NF; ++j)
+            for (int p = 0; p < 9; ++p)
+                if ((dn.w[a][j][p] != 0.0) != dense9_star_corner(a, j, p)) return 0;
+    return 1;
+}
+
 // CG on a 2-D coarsest grid with at most 32 x 32 inner nodes: ONE node per thread (warp = row, lane = x), x / r / p /
 // A p of the node live in registers for the whole solve, only p is mirrored in shared memory for the neighbours.
 // Statement for statement the arithmetic of k_coarse_cg_smem (A p accumulated in table order, row sums by the xor
 // butterfly, rows and fields added by warp_vecsum in order) -> the same iterates bit for bit, at a third of the
 // latency per iteration (the coarse solve was half of a 2-D Poisson cycle).
-template <int NF>
+template <int NF, int PAT>
 __global__ void __launch_bounds__(1024) k2_coarse_cg_reg(const Geom g, const __grid_constant__ Dense9<NF> dn, Fields<double> xg,
                                                         Fields<double> bg, int max_it, double tol, int *iters_out)
 {
@@ -1021,7 +1038,10 @@ __global__ void __launch_bounds__(1024) k2_coarse_cg_reg(const Geom g, const __g
 #pragma unroll
                         for (int q = 0; q < 9; ++q) {
                             const double cf = dn.w[i][j][q];
-                            if (cf != 0.0) a = a + cf * psm[j * vol + c0 + (q / 3 - 1) * n + (q % 3 - 1)];
+                            bool on;
+                            if constexpr (PAT == 1) on = dense9_star_corner(i, j, q);
+                            else on = cf != 0.0;
+                            if (on) a = a + cf * psm[j * vol + c0 + (q / 3 - 1) * n + (q % 3 - 1)];
                         }
                 }
                 av[i] = a;
@@ -1060,7 +1080,7 @@ __global__ void __launch_bounds__(1024) k2_coarse_cg_reg(const Geom g, const __g
 // CTA; a step is one __syncthreads.  Rows stream through a shared-memory window once (cp.async in, 16-byte stores
 // out when a row has left the last pass), so k sweeps cost (n + 4k) row steps instead of 2k n.
 constexpr int ROWSEQ_NT = 512;   // 2 CTAs (or other kernels of a population) fit beside it on an SM
-template <int NF>
+template <int NF, int PAT>
 __global__ void __launch_bounds__(ROWSEQ_NT, 2) k2_smooth_rowseq_pipe(const Geom g, const __grid_constant__ OpSten st, const __grid_constant__ Dense9<NF> dn,
                                                               const double omega, Fields<double> u, Fields<double> rhs, const int sweeps)
 {
@@ -1175,7 +1195,10 @@ __global__ void __launch_bounds__(ROWSEQ_NT, 2) k2_smooth_rowseq_pipe(const Geom
 #pragma unroll
                         for (int p = 0; p < 9; ++p) {
                             if (p == 4) continue;
-                            if ((nz[a][j] >> p) & 1u) sacc = sacc + dn.w[a][j][p] * nbv[j][p];
+                            bool on;
+                            if constexpr (PAT == 1) on = dense9_star_corner(a, j, p);
+                            else on = (nz[a][j] >> p) & 1u;
+                            if (on) sacc = sacc + dn.w[a][j][p] * nbv[j][p];
                         }
                     b[a] = fr[a * pitch + x] - sacc;
                 }
