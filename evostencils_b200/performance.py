@@ -29,7 +29,7 @@ from . import oplist as ol
 
 # fraction of the measured HBM peak the kernel family reaches at large sizes (profiles/, round 2)
 EFFICIENCY: Dict[str, float] = {
-    "rbgs3d": 0.94, "jacobi3d": 0.87, "residual3d": 0.87, "residual_restrict3d": 0.57, "restrict": 0.40,
+    "rbgs3d": 0.95, "jacobi3d": 0.87, "residual3d": 0.87, "residual_restrict3d": 0.95, "restrict": 0.40,
     "prolong3d": 0.98, "generic": 0.35,
     # 2-D streaming kernels (>= 513^2): one pass per (up to) two sweeps
     "sweep2d": 0.75, "residual_restrict2d": 0.70, "prolong2d": 0.90, "residual2d": 0.55,

@@ -25,7 +25,7 @@ def test_estimate_matches_the_measured_513_cycle():
     prob = problems.Poisson3D(2, 9)
     prog = lowering.optimise(cycles.default_solver_cycle(prob))
     est_ms = B200PerformanceEvaluator().estimate_runtime(prog) * 1e3
-    line = json.load(open(os.path.join(HERE, "..", "profiles", "r2_a_bench_grid513.json")))
+    line = json.load(open(os.path.join(HERE, "..", "profiles", "r2_e_bench_grid513.json")))
     cycle_ms = line["ms_per_cycle"] - 0.40      # the bench figure includes the norm residual of the solver loop
     assert abs(est_ms - cycle_ms) / cycle_ms < 0.3, (est_ms, cycle_ms)
 
