@@ -32,6 +32,7 @@ enum {
     OPT_STAR2D,          // EVO_STAR2D          0 = generic 2-D kernels only (no specialised 5-point path)
     OPT_COARSE_FUSE,     // EVO_COARSE_FUSE     fused runs on small levels: 0 off (default: measured slower), 1 one CTA, 2 also clusters, 3 smallest only
     OPT_NO_ZERO_FUSE,    // EVO_NO_ZERO_FUSE    keep `SOL@(l-1) = 0` as its own node instead of folding it into the restriction before it
+    OPT_RR_WARP_NODES,   // EVO_RR_WARP_NODES   generic fused residual+restriction: warp-per-coarse-node kernel up to this many coarse nodes (0 = default)
     OPT_COUNT
 };
 struct OptionTable {
@@ -42,7 +43,7 @@ inline const char *option_name(int id)
 {
     static const char *names[OPT_COUNT] = {"EVO_RB_VARIANT", "EVO_RB_FUSE2", "EVO_RR_VARIANT", "EVO_NO_PINGPONG", "EVO_CG_GLOBAL",
                                            "EVO_CG_NOREG", "EVO_ROWSEQ_GLOBAL", "EVO_ROWSEQ_NOPIPE", "EVO_FAS_CGS",
-                                           "EVO_FAS_CGS_GLOBAL", "EVO_LEX_VARIANT", "EVO_STAR2D", "EVO_COARSE_FUSE", "EVO_NO_ZERO_FUSE"};
+                                           "EVO_FAS_CGS_GLOBAL", "EVO_LEX_VARIANT", "EVO_STAR2D", "EVO_COARSE_FUSE", "EVO_NO_ZERO_FUSE", "EVO_RR_WARP_NODES"};
     return names[id];
 }
 inline OptionTable &option_table()

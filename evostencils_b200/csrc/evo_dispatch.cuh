@@ -366,7 +366,11 @@ template <typename T, int DIM, int NF> struct Launch {
                    !star::try_residual_restrict<T, DIM, NF>(c->p->sm_count, gf, gc, c->sten[l], c->p->R, u, f, dst, s)) {
             if (slab_level(c->p, l)) return fail(EVO_ERR_UNSUPPORTED, "domain decomposition: fused residual+restriction needs the fast path");
             const long long cn = (long long)(gc.n - 2) * (gc.n - 2) * (DIM == 3 ? gc.n - 2 : 1);
-            if (cn <= SMALL_GRID_NODES / (DIM == 3 ? 8 : 4))      // tiny coarse grid: one warp per coarse node
+            // measured (scripts/op_costs.py): two fields, 63^2 coarse nodes: 6.9 us (warp) vs 13.4 us (thread per node); 127^2: 18.8 vs
+            // 13.9 us; one field: the thread-per-node kernel wins from 63^2 on
+            const long long warp_max = option(OPT_RR_WARP_NODES) > 0 ? option(OPT_RR_WARP_NODES)
+                                                                      : (DIM == 3 ? SMALL_GRID_NODES / 8 : (NF >= 2 ? SMALL_GRID_NODES : SMALL_GRID_NODES / 4));
+            if (cn <= warp_max)      // tiny coarse grid: one warp per coarse node
                 k_residual_restrict_warp<T, DIM, NF><<<(unsigned)((cn + 3) / 4), 128, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst, zero);
             else k_residual_restrict<T, DIM, NF><<<row_grid(gc), BX, 0, s>>>(gf, gc, c->sten[l], c->p->R, u, f, dst, zero);
             if (zero.p[0]) c->fuse_zero = false;
